@@ -1,0 +1,84 @@
+"""ctypes binding of libfn3.so (the C-ABI declared in include/fn3.h).
+
+There is deliberately no fallback: if the shared object is missing or a symbol is
+absent, importing/using the engine raises.  The product path never touches oracle/.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfn3.so")
+
+FN3_OK = 0
+FN3_EARG = -1
+FN3_ENOTFOUND = -2
+FN3_ECAPACITY = -3
+FN3_ECUDA = -4
+FN3_ENOMEM = -5
+
+
+class Hit(C.Structure):
+    _fields_ = [("row", C.c_int64), ("dist", C.c_int32), ("n1", C.c_int32),
+                ("n2", C.c_int32), ("nboth", C.c_int32)]
+
+
+class Edge(C.Structure):
+    _fields_ = [("row1", C.c_int64), ("row2", C.c_int64), ("dist", C.c_int32),
+                ("n1", C.c_int32), ("n2", C.c_int32), ("nboth", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_live", C.c_int64), ("n_invalid", C.c_int64),
+                ("store_words", C.c_int64), ("store_bytes", C.c_int64), ("positions", C.c_int64)]
+
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/fn3.h one to one
+SIGNATURES = {
+    "fn3_abi_version": (C.c_int, []),
+    "fn3_create": (_vp, [C.c_int64, C.c_int32]),
+    "fn3_destroy": (C.c_int, [_vp]),
+    "fn3_last_error": (C.c_char_p, [_vp]),
+    "fn3_append": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, _i64p]),
+    "fn3_append_bulk": (C.c_int, [_vp, C.c_int64, _i32p, _i64p, _u8p, _i64p]),
+    "fn3_remove": (C.c_int, [_vp, C.c_int64]),
+    "fn3_stats_get": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "fn3_row_get": (C.c_int, [_vp, C.c_int64, _i32p, C.c_int64, _i32p, _i32p, _i64p]),
+    "fn3_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, _i64p, C.c_int64, C.POINTER(Hit), C.c_int64, _i64p]),
+    "fn3_lists_vs_all": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, C.c_int64,
+                                   C.POINTER(Hit), C.c_int64, _i64p]),
+    "fn3_all_vs_all": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                 C.POINTER(Edge), C.c_int64, _i64p]),
+    "fn3_pair": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(Hit), _i32p]),
+    "fn3_pair_lists": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, _i32p, _i32p, C.c_int32, C.c_int32,
+                                 C.POINTER(Hit), _i32p]),
+    "fn3_set_reference": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64]),
+    "fn3_compress": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64, _i32p, C.c_char_p, C.c_int64, _i64p]),
+    "fn3_profile_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i64p, _i64p]),
+    "fn3_launch_count": (C.c_int64, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libfn3.so and bind every symbol of include/fn3.h.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libfn3.so is not built (%s). Run `python -m findneighbour3_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

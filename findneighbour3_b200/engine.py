@@ -1,0 +1,249 @@
+"""Thin Python face of the C-ABI (include/fn3.h): numpy arrays in, numpy structured arrays out.
+
+`Engine` owns one fn3_engine (one CUDA device).  It knows nothing about guids or the
+reference's dict format — that is seqComparer.py / packing.py.  Every method maps to
+exactly one C entry point; errors become the exception classes the reference's API uses
+(SURVEY.md §8(b)): FN3_EARG -> ValueError, FN3_ENOTFOUND -> KeyError, the rest -> RuntimeError.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+HIT_DTYPE = np.dtype([("row", "<i8"), ("dist", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("nboth", "<i4")])
+EDGE_DTYPE = np.dtype([("row1", "<i8"), ("row2", "<i8"), ("dist", "<i4"), ("n1", "<i4"), ("n2", "<i4"),
+                       ("nboth", "<i4")])
+assert HIT_DTYPE.itemsize == C.sizeof(N.Hit) and EDGE_DTYPE.itemsize == C.sizeof(N.Edge)
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+class Engine:
+    def __init__(self, genome_length, device=0):
+        self._lib = N.load()
+        self._h = self._lib.fn3_create(int(genome_length), int(device))
+        if not self._h:
+            msg = self._lib.fn3_last_error(None)
+            raise EngineError("fn3_create failed: %s" % (msg.decode() if msg else "unknown"))
+        self.genome_length = int(genome_length)
+        self.device = int(device)
+        self._hits = np.empty(4096, dtype=HIT_DTYPE)
+        self._edges = np.empty(1 << 16, dtype=EDGE_DTYPE)
+
+    # -- plumbing -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fn3_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == N.FN3_OK:
+            return
+        msg = self._lib.fn3_last_error(self._h)
+        msg = msg.decode() if msg else "fn3 error %d" % rc
+        if rc == N.FN3_EARG:
+            raise ValueError(msg)
+        if rc == N.FN3_ENOTFOUND:
+            raise KeyError(msg)
+        if rc == N.FN3_ENOMEM:
+            raise MemoryError(msg)
+        raise EngineError("fn3 error %d: %s" % (rc, msg))
+
+    # -- store ----------------------------------------------------------------------------
+    def append(self, pos, off, invalid=False):
+        """persist one sample (six sorted lists A,C,G,T,N,M as pos + 7 offsets) -> row index."""
+        row = C.c_int64(-1)
+        if invalid:
+            rc = self._lib.fn3_append(self._h, None, None, 1, C.byref(row))
+        else:
+            pos = _as_i32(pos)
+            off = _as_i32(off)
+            if off.shape != (7,):
+                raise ValueError("off must have 7 entries")
+            rc = self._lib.fn3_append(self._h, _ptr(pos, _i32p), _ptr(off, _i32p), 0, C.byref(row))
+        self._check(rc)
+        return row.value
+
+    def append_bulk(self, pos, off, invalid=None):
+        """persist n samples: pos concatenated, off int64[6n+1], invalid uint8[n] or None -> first row."""
+        pos = _as_i32(pos)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        n = (off.size - 1) // 6
+        if off.size != 6 * n + 1:
+            raise ValueError("off must have 6*n+1 entries")
+        inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        if inv is not None and inv.size != n:
+            raise ValueError("invalid must have n entries")
+        first = C.c_int64(-1)
+        rc = self._lib.fn3_append_bulk(self._h, n, _ptr(pos, _i32p), _ptr(off, _i64p), _ptr(inv, _u8p), C.byref(first))
+        self._check(rc)
+        return first.value
+
+    def remove(self, row):
+        self._check(self._lib.fn3_remove(self._h, int(row)))
+
+    def stats(self):
+        st = N.Stats()
+        self._check(self._lib.fn3_stats_get(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in N.Stats._fields_}
+
+    def row_get(self, row):
+        """-> (pos int32[], off int32[7], invalid bool) of a stored row."""
+        off = np.zeros(7, dtype=np.int32)
+        inv = C.c_int32(0)
+        npos = C.c_int64(0)
+        cap = 1024
+        while True:
+            pos = np.empty(cap, dtype=np.int32)
+            rc = self._lib.fn3_row_get(self._h, int(row), _ptr(pos, _i32p), cap, _ptr(off, _i32p),
+                                       C.byref(inv), C.byref(npos))
+            if rc == N.FN3_ECAPACITY:
+                cap = int(npos.value)
+                continue
+            self._check(rc)
+            return pos[: npos.value].copy(), off, bool(inv.value)
+
+    # -- ingest ---------------------------------------------------------------------------
+    def set_reference(self, reference, excluded=None):
+        """upload the reference string and the excluded positions (needed by compress only)."""
+        ref = reference.encode("ascii") if isinstance(reference, str) else bytes(reference)
+        if len(ref) != self.genome_length:
+            raise ValueError("reference length differs from the engine's genome length")
+        ex = None
+        if excluded is not None and len(excluded) > 0:
+            ex = np.sort(np.fromiter(excluded, dtype=np.int64, count=len(excluded))).astype(np.int32)
+        self._check(self._lib.fn3_set_reference(self._h, ref, _ptr(ex, _i32p), 0 if ex is None else ex.size))
+        self._cpos = np.empty(1 << 16, dtype=np.int32)
+        self._cm = C.create_string_buffer(1 << 12)
+
+    def compress(self, seq_bytes):
+        """device compress of one sequence (bytes, len = genome length) -> (pos int32[], off int32[7], m_chars bytes)."""
+        if len(seq_bytes) != self.genome_length:
+            raise ValueError("sequence length differs from the engine's genome length")
+        off = np.zeros(7, dtype=np.int32)
+        npos = C.c_int64(0)
+        while True:
+            rc = self._lib.fn3_compress(self._h, seq_bytes, _ptr(self._cpos, _i32p), self._cpos.size,
+                                        _ptr(off, _i32p), self._cm, len(self._cm), C.byref(npos))
+            if rc == N.FN3_ECAPACITY:
+                n_m = int(off[6] - off[5])
+                if npos.value > self._cpos.size:
+                    self._cpos = np.empty(int(npos.value) * 2, dtype=np.int32)
+                if n_m > len(self._cm):
+                    self._cm = C.create_string_buffer(n_m * 2)
+                continue
+            self._check(rc)
+            n_m = int(off[6] - off[5])
+            return self._cpos[: npos.value].copy(), off, self._cm.raw[:n_m]
+
+    # -- hot path -------------------------------------------------------------------------
+    def _hit_buf(self, n):
+        if self._hits.size < n:
+            self._hits = np.empty(max(n, 2 * self._hits.size), dtype=HIT_DTYPE)
+        return self._hits
+
+    def one_vs_all(self, query_row, ceiling, rows=None):
+        """mcompare: stored row vs all (or `rows`); -> structured array of survivors (copy)."""
+        rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        n_cand = self.stats()["n_rows"] if rows_a is None else rows_a.size
+        buf = self._hit_buf(max(int(n_cand), 1))
+        n_out = C.c_int64(0)
+        rc = self._lib.fn3_one_vs_all(self._h, int(query_row), int(ceiling), _ptr(rows_a, _i64p),
+                                      0 if rows_a is None else rows_a.size,
+                                      buf.ctypes.data_as(C.POINTER(N.Hit)), buf.size, C.byref(n_out))
+        self._check(rc)
+        return buf[: n_out.value].copy()
+
+    def lists_vs_all(self, pos, off, invalid, ceiling, rows=None):
+        rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        n_cand = self.stats()["n_rows"] if rows_a is None else rows_a.size
+        buf = self._hit_buf(max(int(n_cand), 1))
+        n_out = C.c_int64(0)
+        if invalid:
+            pos_a, off_a = None, None
+        else:
+            pos_a, off_a = _as_i32(pos), _as_i32(off)
+        rc = self._lib.fn3_lists_vs_all(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
+                                        int(ceiling), _ptr(rows_a, _i64p), 0 if rows_a is None else rows_a.size,
+                                        buf.ctypes.data_as(C.POINTER(N.Hit)), buf.size, C.byref(n_out))
+        self._check(rc)
+        return buf[: n_out.value].copy()
+
+    def all_vs_all(self, ceiling, upper_only=True, row_begin=0, row_end=None, stride=1, phase=0):
+        """distmat over the block rows this caller owns -> structured array of edges (copy)."""
+        if row_end is None:
+            row_end = self.stats()["n_rows"]
+        n_out = C.c_int64(0)
+        while True:
+            buf = self._edges
+            rc = self._lib.fn3_all_vs_all(self._h, int(ceiling), 1 if upper_only else 0, int(row_begin), int(row_end),
+                                          int(stride), int(phase), buf.ctypes.data_as(C.POINTER(N.Edge)), buf.size,
+                                          C.byref(n_out))
+            if rc == N.FN3_ECAPACITY:
+                self._edges = np.empty(int(n_out.value) + 1024, dtype=EDGE_DTYPE)
+                continue
+            self._check(rc)
+            return buf[: n_out.value].copy()
+
+    def pair(self, row1, row2, ceiling):
+        """countDifferences_byKey on stored rows -> (dist,n1,n2,nboth) or None."""
+        hit = N.Hit()
+        has = C.c_int32(0)
+        self._check(self._lib.fn3_pair(self._h, int(row1), int(row2), int(ceiling), C.byref(hit), C.byref(has)))
+        if not has.value:
+            return None
+        return (hit.dist, hit.n1, hit.n2, hit.nboth)
+
+    def pair_lists(self, pos1, off1, invalid1, pos2, off2, invalid2, ceiling):
+        """countDifferences on two un-stored samples -> (dist,n1,n2,nboth) or None."""
+        hit = N.Hit()
+        has = C.c_int32(0)
+        p1 = None if invalid1 else _as_i32(pos1)
+        o1 = None if invalid1 else _as_i32(off1)
+        p2 = None if invalid2 else _as_i32(pos2)
+        o2 = None if invalid2 else _as_i32(off2)
+        rc = self._lib.fn3_pair_lists(self._h, _ptr(p1, _i32p), _ptr(o1, _i32p), 1 if invalid1 else 0,
+                                      _ptr(p2, _i32p), _ptr(o2, _i32p), 1 if invalid2 else 0, int(ceiling),
+                                      C.byref(hit), C.byref(has))
+        self._check(rc)
+        if not has.value:
+            return None
+        return (hit.dist, hit.n1, hit.n2, hit.nboth)
+
+    # -- measurement ----------------------------------------------------------------------
+    def profile_one_vs_all(self, query_row, ceiling, iters=10, flush_l2=False, count_bytes=True):
+        ms_total = np.zeros(iters, dtype=np.float32)
+        ms_cmp = np.zeros(iters, dtype=np.float32)
+        n_hits = C.c_int64(0)
+        touched = C.c_int64(0)
+        rc = self._lib.fn3_profile_one_vs_all(self._h, int(query_row), int(ceiling), int(iters), 1 if flush_l2 else 0,
+                                              _ptr(ms_total, _f32p), _ptr(ms_cmp, _f32p), C.byref(n_hits),
+                                              C.byref(touched) if count_bytes else None)
+        self._check(rc)
+        return {"ms_total": ms_total, "ms_compare": ms_cmp, "n_hits": n_hits.value,
+                "bytes_touched": touched.value if count_bytes else None}
+
+    def launch_count(self):
+        return int(self._lib.fn3_launch_count(self._h))

@@ -1,0 +1,229 @@
+"""Seeded synthetic "M. tuberculosis-shaped" collections, generated directly in list form.
+
+Semantics follow the reference's generator (src/LargeSequenceSetGenerator.py:64-141 and its
+documented TB invocation `1000 500 3 50 1e-8`, doc/demos_technical.md:91):
+  * n_anc ancestors = reference + k1 random substitutions (:92-93);
+  * every ancestor roots a random tree of max_c nodes; a child = its parent + Poisson(s)
+    substitutions (:95-98).  ete3 is not available, so the topology is "node i>0 picks a
+    uniform random earlier node of the same family as parent" (SURVEY.md §8(d));
+  * substitution rule 'lss': G->T, anything else ->G (:136-139); rule 'any': a uniformly
+    random different base (exercises all four base lists);
+  * the reference's i.i.d. N model with p=1e-8 (:112-127) yields ~0 N, unlike mapped reads,
+    so N is added as `n_blocks` contiguous blocks totalling ~Poisson(n_mean) positions
+    (SURVEY.md §8(d)); mixed bases (M) as Poisson(m_mean) scattered positions;
+  * a fraction `p_invalid` of samples is all-N, i.e. invalid under maxNs.
+Excluded positions are dropped exactly as compress() does (src/seqComparer.py:292).
+
+Everything is numpy; a 50 000-sample TB collection takes a few tens of seconds.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+TB_LENGTH = 4411532          # src/seqComparer.py:2140
+TB_EXCLUDED = 288069         # reference/TB-exclude.txt line count
+TB_EXCLUDED_RUNS = 481
+
+_BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+@dataclass
+class Collection:
+    genome_length: int
+    pos: np.ndarray          # int32, all samples' lists concatenated
+    off: np.ndarray          # int64 [6n+1]
+    invalid: np.ndarray      # uint8 [n]
+    family: np.ndarray       # int32 [n] ancestor index of each sample
+
+    @property
+    def n(self):
+        return int(self.invalid.size)
+
+    def lists(self, i):
+        """-> (pos int32[], off int32[7], invalid bool) of sample i (engine.append format)."""
+        o = self.off[6 * i: 6 * i + 7]
+        return self.pos[o[0]:o[6]], (o - o[0]).astype(np.int32), bool(self.invalid[i])
+
+    def as_dict(self, i, m_char="R"):
+        """sample i as the reference's compressed_sequence dict (for the oracle port)."""
+        if self.invalid[i]:
+            return {"invalid": 1}
+        p, o, _ = self.lists(i)
+        d = {"invalid": 0}
+        for b, k in enumerate("ACGTN"):
+            d[k] = set(int(x) for x in p[o[b]:o[b + 1]])
+        d["M"] = {int(x): m_char for x in p[o[5]:o[6]]}
+        return d
+
+    def positions_per_sample(self):
+        return (self.off[6::6] - self.off[0:-1:6]).astype(np.int64)
+
+    def bytes_canonical(self):
+        """Sum over samples of B_pair = 4*(|A|+|C|+|G|+|T|+|N|+|M|) + 32."""
+        return 4 * self.positions_per_sample() + 32
+
+    def subset(self, idx):
+        idx = np.asarray(idx, dtype=np.int64)
+        chunks, off, total = [], np.zeros(6 * idx.size + 1, dtype=np.int64), 0
+        for j, i in enumerate(idx):
+            o = self.off[6 * i: 6 * i + 7]
+            chunks.append(self.pos[o[0]:o[6]])
+            off[6 * j: 6 * j + 7] = total + (o - o[0])
+            total += int(o[6] - o[0])
+        pos = np.concatenate(chunks) if chunks else np.empty(0, dtype=np.int32)
+        return Collection(self.genome_length, pos, off, self.invalid[idx].copy(), self.family[idx].copy())
+
+
+def random_reference(length, seed=962):
+    """uint8 codes 0..3 (A,C,G,T): seeded stand-in for the missing NC_000962 FASTA."""
+    return np.random.default_rng(seed).integers(0, 4, size=length, dtype=np.uint8)
+
+
+def reference_string(ref_codes):
+    return _BASES[ref_codes].tobytes().decode("ascii")
+
+
+def synthetic_mask(length, n_excluded, n_runs, seed=7):
+    """boolean[length], True = excluded; n_runs runs totalling ~n_excluded (TB-exclude-shaped)."""
+    rng = np.random.default_rng(seed)
+    ex = np.zeros(length, dtype=bool)
+    if n_excluded <= 0 or n_runs <= 0:
+        return ex
+    lens = rng.multinomial(n_excluded, np.ones(n_runs) / n_runs)
+    starts = np.sort(rng.integers(0, max(1, length - int(lens.max()) - 1), size=n_runs))
+    for s, l in zip(starts, lens):
+        ex[s:s + l] = True
+    return ex
+
+
+def _mutate(vpos, vbase, ref, count, rng, rule):
+    """apply `count` substitutions at uniformly random positions to the variant map (vpos sorted, vbase codes)."""
+    if count <= 0:
+        return vpos, vbase
+    new_pos = np.unique(rng.integers(0, ref.size, size=count))
+    # current base at those positions: variant base if present else reference
+    idx = np.searchsorted(vpos, new_pos)
+    present = (idx < vpos.size)
+    present[present] = vpos[idx[present]] == new_pos[present]
+    cur = ref[new_pos].copy()
+    cur[present] = vbase[idx[present]]
+    if rule == "lss":
+        nb = np.where(cur == 2, 3, 2).astype(np.uint8)          # G->T else ->G
+    else:
+        nb = ((cur + rng.integers(1, 4, size=new_pos.size)) % 4).astype(np.uint8)
+    # merge: drop old entries at these positions, add the new ones unless they revert to reference
+    keep = np.ones(vpos.size, dtype=bool)
+    keep[idx[present]] = False
+    add = nb != ref[new_pos]
+    pos = np.concatenate([vpos[keep], new_pos[add]])
+    base = np.concatenate([vbase[keep], nb[add]])
+    order = np.argsort(pos, kind="stable")
+    return pos[order], base[order]
+
+
+def _blocks(length, n_blocks, total, rng):
+    """sorted unique positions of `n_blocks` contiguous blocks with `total` positions overall."""
+    if total <= 0 or n_blocks <= 0:
+        return np.empty(0, dtype=np.int64)
+    lens = rng.multinomial(total, np.ones(n_blocks) / n_blocks)
+    starts = rng.integers(0, max(1, length - int(lens.max()) - 1), size=n_blocks)
+    parts = [np.arange(s, s + l, dtype=np.int64) for s, l in zip(starts, lens) if l > 0]
+    return np.unique(np.concatenate(parts)) if parts else np.empty(0, dtype=np.int64)
+
+
+def make_collection(n_anc, max_c, genome_length=TB_LENGTH, k1=500, s=3.0, n_blocks=20, n_mean=4000, m_mean=0,
+                    p_invalid=0.01, seed=1, rule="lss", ref_seed=962, excluded=None, n_lognormal_sigma=None,
+                    max_ns=130000):
+    """Generate n_anc*max_c samples -> Collection.  `excluded`: boolean[L] or None."""
+    rng = np.random.default_rng(seed)
+    ref = random_reference(genome_length, ref_seed)
+    n = n_anc * max_c
+    off = np.zeros(6 * n + 1, dtype=np.int64)
+    invalid = np.zeros(n, dtype=np.uint8)
+    family = np.repeat(np.arange(n_anc, dtype=np.int32), max_c)
+    chunks = []
+    total = 0
+    i = 0
+    for a in range(n_anc):
+        nodes = []
+        for c in range(max_c):
+            if c == 0:
+                vp, vb = _mutate(np.empty(0, dtype=np.int64), np.empty(0, dtype=np.uint8), ref, k1, rng, rule)
+            else:
+                pp, pb = nodes[int(rng.integers(0, c))]
+                vp, vb = _mutate(pp, pb, ref, int(rng.poisson(s)), rng, rule)
+            nodes.append((vp, vb))
+            if rng.random() < p_invalid:
+                invalid[i] = 1
+                off[6 * i + 1: 6 * i + 7] = total
+                i += 1
+                continue
+            if n_lognormal_sigma is None:
+                n_total = int(rng.poisson(n_mean)) if n_mean > 0 else 0
+            else:
+                n_total = int(rng.lognormal(np.log(max(n_mean, 1)), n_lognormal_sigma))
+            npos = _blocks(genome_length, n_blocks, n_total, rng)
+            mpos = np.unique(rng.integers(0, genome_length, size=int(rng.poisson(m_mean)))) if m_mean > 0 \
+                else np.empty(0, dtype=np.int64)
+            if excluded is not None:
+                npos = npos[~excluded[npos]]
+                mpos = mpos[~excluded[mpos]]
+            mpos = np.setdiff1d(mpos, npos, assume_unique=True)
+            if npos.size + mpos.size > max_ns:
+                invalid[i] = 1
+                off[6 * i + 1: 6 * i + 7] = total
+                i += 1
+                continue
+            keep = np.ones(vp.size, dtype=bool)
+            if excluded is not None:
+                keep &= ~excluded[vp]
+            if npos.size:
+                j = np.searchsorted(npos, vp)
+                hit = j < npos.size
+                hit[hit] = npos[j[hit]] == vp[hit]
+                keep &= ~hit
+            if mpos.size:
+                j = np.searchsorted(mpos, vp)
+                hit = j < mpos.size
+                hit[hit] = mpos[j[hit]] == vp[hit]
+                keep &= ~hit
+            p, b = vp[keep], vb[keep]
+            lists = [p[b == code] for code in range(4)] + [npos, mpos]
+            sizes = [x.size for x in lists]
+            off[6 * i + 1: 6 * i + 7] = total + np.cumsum(sizes)
+            total += int(sum(sizes))
+            chunks.append(np.concatenate(lists).astype(np.int32))
+            i += 1
+    pos = np.concatenate(chunks) if chunks else np.empty(0, dtype=np.int32)
+    return Collection(genome_length, pos, off, invalid, family)
+
+
+def new_sample_like(coll, i, extra_snps, seed, rule="lss", ref_seed=962):
+    """a 'newly sequenced' relative of sample i: its lists + `extra_snps` fresh substitutions (same N/M)."""
+    rng = np.random.default_rng(seed)
+    ref = random_reference(coll.genome_length, ref_seed)
+    p, o, inv = coll.lists(i)
+    if inv:
+        return p, o, inv
+    vp = np.concatenate([p[o[b]:o[b + 1]] for b in range(4)]).astype(np.int64)
+    vb = np.concatenate([np.full(o[b + 1] - o[b], b, dtype=np.uint8) for b in range(4)])
+    order = np.argsort(vp, kind="stable")
+    vp, vb = _mutate(vp[order], vb[order], ref, extra_snps, rng, rule)
+    unc = np.concatenate([p[o[4]:o[5]], p[o[5]:o[6]]]).astype(np.int64)
+    if unc.size:
+        keep = ~np.isin(vp, unc)
+        vp, vb = vp[keep], vb[keep]
+    lists = [vp[vb == code] for code in range(4)] + [p[o[4]:o[5]].astype(np.int64), p[o[5]:o[6]].astype(np.int64)]
+    off = np.zeros(7, dtype=np.int32)
+    off[1:] = np.cumsum([x.size for x in lists])
+    return np.concatenate(lists).astype(np.int32), off, False
+
+
+def to_string(ref_codes, pos, off, excluded=None, m_char="R"):
+    """render one sample as a sequence string (small genomes only; used to exercise compress())."""
+    seq = _BASES[ref_codes].copy()
+    for b in range(4):
+        seq[pos[off[b]:off[b + 1]]] = _BASES[b]
+    seq[pos[off[4]:off[5]]] = ord("N")
+    seq[pos[off[5]:off[6]]] = ord(m_char)
+    return seq.tobytes().decode("ascii")

@@ -1,0 +1,197 @@
+/*
+ * fn3.h — C-ABI of the B200-native SNV-distance engine (libfn3.so).
+ *
+ * This is the drop-in boundary for ONE path of davidhwyllie/findNeighbour3: the masked
+ * pairwise SNV distance computation of class `seqComparer`.  The reference has no FFI
+ * (it is pure Python); every entry point below names the reference method whose work it
+ * takes over (paths relative to the reference checkout, `src/seqComparer.py` unless
+ * stated).  The Python class `findneighbour3_b200.seqComparer.seqComparer` binds these
+ * symbols with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller allocates every output buffer;
+ *   - return value: FN3_OK (0) or a negative FN3_E* class, text via fn3_last_error();
+ *   - a sample is handed over as SIX sorted, mutually disjoint, 0-based int32 position
+ *     lists concatenated in the order A,C,G,T,N,M with 7 CSR offsets `off[0..6]`
+ *     (off[0]=0, list b is pos[off[b] .. off[b+1]) ).  That is the reference's
+ *     `compressed_sequence` dict (seqComparer.py:290-305) with sets sorted and the M
+ *     dict reduced to its keys (the compare path never reads the M characters,
+ *     seqComparer.py:449-450, 416-417);
+ *   - `invalid != 0` reproduces `{'invalid':1}` (seqComparer.py:301-303): nothing is
+ *     stored and every pair involving the row yields "no distance";
+ *   - "no distance" (the reference's None) is never emitted: only pairs with
+ *     dist <= ceiling come back (seqComparer.py:455, server.py:532-538);
+ *   - all calls are thread-safe; appends may run concurrently with queries
+ *     (server.py:513-516 runs compress+persist outside the write semaphore).
+ *
+ * There is no CPU implementation behind this ABI: fn3_create fails (NULL) when no
+ * CUDA device is usable.
+ */
+#ifndef FN3_H
+#define FN3_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FN3_ABI_VERSION 1
+
+/* status codes */
+#define FN3_OK          0
+#define FN3_EARG       -1   /* bad argument (unsorted / out of range / overlapping lists, bad row) */
+#define FN3_ENOTFOUND  -2   /* row does not exist or was removed */
+#define FN3_ECAPACITY  -3   /* caller's output buffer too small; *n_out holds the required count */
+#define FN3_ECUDA      -4   /* CUDA runtime failure (text in fn3_last_error) */
+#define FN3_ENOMEM     -5   /* host or device allocation failed */
+
+typedef struct fn3_engine fn3_engine;
+
+/* One surviving neighbour: what mcompare()/countDifferences_byKey() report for a pair
+ * whose distance is <= the ceiling (seqComparer.py:415-419).
+ *   dist  = |{p : code_q[p] != code_c[p], p not in N_q u M_q, p not in N_c u M_c}|   (:446-453)
+ *   n1    = |N_q u M_q|            (:416)
+ *   n2    = |N_c u M_q|            (:417 — sic: the reference uses seq1's M keys)
+ *   nboth = |N_q u M_q u N_c|      (:418, :378)                                        */
+typedef struct fn3_hit {
+    int64_t row;      /* candidate row (seq2) */
+    int32_t dist;
+    int32_t n1;
+    int32_t n2;
+    int32_t nboth;
+} fn3_hit;
+
+/* One edge of the all-vs-all sparse matrix (distmat(), seqComparer.py:174-197):
+ * row1 is seq1 (the query), row2 is seq2. */
+typedef struct fn3_edge {
+    int64_t row1;
+    int64_t row2;
+    int32_t dist;
+    int32_t n1;
+    int32_t n2;
+    int32_t nboth;
+} fn3_edge;
+
+/* Store statistics (summarise_stored_items(), seqComparer.py:199-219, engine side). */
+typedef struct fn3_stats {
+    int64_t n_rows;          /* rows ever appended (including removed ones) */
+    int64_t n_live;          /* rows not removed */
+    int64_t n_invalid;       /* live rows stored as invalid */
+    int64_t store_words;     /* 32-bit words of row data resident in HBM (live + dead) */
+    int64_t store_bytes;     /* device bytes reserved for the store (chunks + headers) */
+    int64_t positions;       /* sum over live rows of |A|+|C|+|G|+|T|+|N|+|M| (canonical B_pair positions) */
+} fn3_stats;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+
+/* Replaces seqComparer.__init__'s in-RAM store (`self.seqProfile = {}`, :108).
+ * genome_length = len(reference) (:93); device = CUDA ordinal.  NULL on failure
+ * (no device, bad length); fn3_last_error(NULL) then holds the reason. */
+fn3_engine* fn3_create(int64_t genome_length, int32_t device);
+int         fn3_destroy(fn3_engine* e);
+int         fn3_abi_version(void);
+
+/* Text of the last error on this engine (or of the last failed fn3_create when e==NULL).
+ * The pointer stays valid until the next failing call on the same thread. */
+const char* fn3_last_error(fn3_engine* e);
+
+/* ---- store: persist / remove (seqComparer.py:119-134) --------------------------- */
+
+/* persist(obj, guid): append one sample; *out_row receives its row index (rows are
+ * dense, 0-based, never reused).  The double-delta form (patch + consensus, :503-548)
+ * is expanded by the caller before the call — the HBM store always holds expanded rows. */
+int fn3_append(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid,
+               int64_t* out_row);
+
+/* Bulk persist (server start-up reload, server.py:358-362): n samples, lists
+ * concatenated, off has 6*n+1 entries (sample i, list b = pos[off[6i+b] .. off[6i+b+1]) ),
+ * invalid[i] as above (may be NULL = none invalid).  Rows first_row .. first_row+n-1. */
+int fn3_append_bulk(fn3_engine* e, int64_t n, const int32_t* pos, const int64_t* off,
+                    const uint8_t* invalid, int64_t* out_first_row);
+
+/* remove(guid) (:125-134): tombstone the row; it never matches again. */
+int fn3_remove(fn3_engine* e, int64_t row);
+
+int fn3_stats_get(fn3_engine* e, fn3_stats* out);
+
+/* Copy a stored row back as the six plain lists (load(), :136-141, used by tests and by
+ * the sharded host layer to ship a query to other ranks).  pos_cap in int32 elements;
+ * FN3_ECAPACITY with *n_pos = required if too small.  *invalid: 1 invalid, 0 valid. */
+int fn3_row_get(fn3_engine* e, int64_t row, int32_t* pos, int64_t pos_cap, int32_t off[7],
+                int32_t* invalid, int64_t* n_pos);
+
+/* ---- the hot path --------------------------------------------------------------- */
+
+/* mcompare(guid, guids) (:149-172): stored row `query_row` (seq1) against the rows in
+ * `rows[0..n_rows)` (NULL = every row 0..n_rows_in_store-1), skipping the query itself
+ * (:166) and removed rows.  Survivors (dist <= ceiling) are written to out[0..*n_out) in
+ * no particular order (the reference's order is arbitrary too, :161).  An invalid
+ * query yields zero survivors (:438-442). */
+int fn3_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling,
+                   const int64_t* rows, int64_t n_rows,
+                   fn3_hit* out, int64_t cap, int64_t* n_out);
+
+/* Same, for a query that is NOT in the store (lists as in fn3_append): the sharded
+ * host layer uses it on the ranks that do not own the query row. */
+int fn3_lists_vs_all(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid,
+                     int32_t ceiling, const int64_t* rows, int64_t n_rows,
+                     fn3_hit* out, int64_t cap, int64_t* n_out);
+
+/* distmat(half, diagonal=False) (:174-197): every ordered pair (row1,row2), row1 != row2,
+ * of live rows in [row_begin,row_end) x [0,n_rows) — query rows are the block row this
+ * caller owns (multi-GPU: one block row set per rank).  upper_only != 0 keeps only
+ * row1 < row2 (`half=True` with guids ordered as rows).  `stride`/`phase`: only query
+ * rows r with r % stride == phase are taken (round-robin block-row ownership);
+ * stride=1, phase=0 = all. */
+int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only,
+                   int64_t row_begin, int64_t row_end, int64_t stride, int64_t phase,
+                   fn3_edge* out, int64_t cap, int64_t* n_out);
+
+/* countDifferences_byKey((k1,k2), cutoff) (:382-421) on two stored rows.
+ * *has_dist = 0 reproduces the reference's None distance (invalid sample or > ceiling). */
+int fn3_pair(fn3_engine* e, int64_t row1, int64_t row2, int32_t ceiling,
+             fn3_hit* out, int32_t* has_dist);
+
+/* setComparator1/2 + countDifferences (:338-352, :424-458) on two samples that are not
+ * in the store (the reference's tests assign _seq1/_seq2 directly, :1710-1711). */
+int fn3_pair_lists(fn3_engine* e,
+                   const int32_t* pos1, const int32_t off1[7], int32_t invalid1,
+                   const int32_t* pos2, const int32_t off2[7], int32_t invalid2,
+                   int32_t ceiling, fn3_hit* out, int32_t* has_dist);
+
+/* ---- ingest: compress() on the device (seqComparer.py:274-307) ---- */
+
+/* Upload the reference sequence (len = genome_length, bytes 'A','C','G','T') and the
+ * excluded positions (sorted, may be NULL/0) once; needed only by fn3_compress*. */
+int fn3_set_reference(fn3_engine* e, const char* reference, const int32_t* excluded,
+                      int64_t n_excluded);
+
+/* compress(sequence): byte-compare `sequence` (len = genome_length, any case-sensitive
+ * chars; '-' == 'N', :285) against the reference under the mask and return the six sorted
+ * lists plus the M characters (m_chars[i] belongs to M list entry i).  pos_cap in
+ * elements; FN3_ECAPACITY with *n_pos = required if too small.  No maxNs decision is
+ * taken here (the caller applies :301). */
+int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_cap,
+                 int32_t off[7], char* m_chars, int64_t m_cap, int64_t* n_pos);
+
+/* ---- measurement hooks (bench.py only; no effect on results) -------------------- */
+
+/* Run the one-vs-all DEVICE work for `query_row` `iters` times on the engine's stream
+ * with inputs already resident: each iteration = query-map build + compare kernel.
+ * ms_total[i] / ms_compare[i] receive CUDA-event times of the whole iteration and of
+ * the compare kernel alone; *n_hits the survivor count of the last iteration;
+ * *bytes_touched the bytes of row data + headers the compare kernel actually loaded in
+ * the last iteration (counted by an instrumented pass that is NOT timed), may be NULL.
+ * flush_l2 != 0 writes a >L2-sized scratch buffer between iterations (untimed). */
+int fn3_profile_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling, int32_t iters,
+                           int32_t flush_l2, float* ms_total, float* ms_compare,
+                           int64_t* n_hits, int64_t* bytes_touched);
+
+/* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
+int64_t fn3_launch_count(fn3_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FN3_H */

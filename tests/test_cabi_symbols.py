@@ -1,0 +1,62 @@
+"""not-gpu: libfn3.so loads on a CPU-only host, exports every symbol include/fn3.h declares, and refuses to
+create an engine without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fn3.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fn3_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("fn3_create", "fn3_destroy", "fn3_append", "fn3_append_bulk", "fn3_remove", "fn3_one_vs_all",
+                 "fn3_all_vs_all", "fn3_pair", "fn3_pair_lists", "fn3_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from findneighbour3_b200 import _native
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), "libfn3.so does not export %s" % name
+    assert set(_native.SIGNATURES) == set(declared_symbols())
+    assert lib.fn3_abi_version() == 1
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_device():
+    from findneighbour3_b200.engine import Engine, EngineError
+    with pytest.raises(EngineError) as ei:
+        Engine(1000, 0)
+    assert "no CUDA device" in str(ei.value) or "CPU" in str(ei.value)
+    from findneighbour3_b200.seqComparer import seqComparer
+    sc = seqComparer(reference="ACTG", maxNs=1e8, snpCeiling=20)
+    with pytest.raises(EngineError):
+        sc.persist(sc.compress("AAAA"), "x")
+
+
+def test_product_does_not_import_oracle():
+    """the shipped package must never import, load or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "findneighbour3_b200")
+    bad = re.compile(r"^\s*(from\s+\.*oracle|import\s+oracle)|libfn3_oracle|oracle/_build|fn3o_", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not bad.search(text), "%s reaches into oracle/" % f

@@ -1,0 +1,354 @@
+"""gpu: the CUDA path (through the C-ABI and through the drop-in seqComparer class) against
+ (a) the golden vectors produced by the unmodified reference, and
+ (b) the C oracle on seeded synthetic collections, bit-exact (integer work: no tolerance)."""
+import os
+
+import numpy as np
+import pytest
+
+from util import dict_from_json, golden, lists_from_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def libs_loaded():
+    from findneighbour3_b200 import _native
+    _native.load()
+
+
+def _sc(ref, maxNs, ceiling, excluded=(), **kw):
+    from findneighbour3_b200.seqComparer import seqComparer
+    return seqComparer(reference=ref, maxNs=maxNs, snpCeiling=ceiling, excludePositions=set(excluded), **kw)
+
+
+def hits_to_dict(hits):
+    return {int(h["row"]): (int(h["dist"]), int(h["n1"]), int(h["n2"]), int(h["nboth"])) for h in hits}
+
+
+# ---------------------------------------------------------------------------------------------
+# (a) golden vectors
+# ---------------------------------------------------------------------------------------------
+def test_compress_golden():
+    for case in golden("compress.json"):
+        sc = _sc(case["ref"], case["maxNs"], 20, case["excluded"])
+        got = sc.compress(case["seq"])
+        assert got == dict_from_json(case["got"]), case
+        if "uncompress" in case:
+            assert sc.uncompress(got) == case["uncompress"]
+
+
+def test_kat_count_differences():
+    n = 0
+    for case in golden("kat.json"):
+        if case["kind"] != "countDifferences":
+            continue
+        sc = _sc(case["ref"], case["maxNs"], case["snpCeiling"])
+        sc.setComparator1(case["seq1"])
+        sc.setComparator2(case["seq2"])
+        assert sc.countDifferences() == case["literal"], case
+        # and with _seq1/_seq2 assigned directly, as the reference's tests 16/17 do
+        sc._seq1 = sc.compress(case["seq1"])
+        sc._seq2 = sc.compress(case["seq2"])
+        assert sc.countDifferences() == case["literal"], case
+        n += 1
+    assert n >= 20
+
+
+def test_kat_mcompare_bykey_hash():
+    for case in golden("kat.json"):
+        if case["kind"] in ("mcompare", "mcompare_dist"):
+            sc = _sc(case["ref"], case["maxNs"], case["snpCeiling"])
+            for s in case["samples"]:
+                sc.persist(sc.compress(s), s)
+            res = sc.mcompare(case["query"])
+            assert len(res) == len(case["samples"]) - 1
+            if case["kind"] == "mcompare":
+                assert {r[1]: r[2:6] for r in res} == case["literal"]
+                by = {r[1]: r for r in res}
+                assert by["NNTG"][6:9] == [set(), {0, 1}, {0, 1}]
+            else:
+                assert {r[1]: r[2] for r in res} == case["literal"]
+            sub = sc.mcompare(case["query"], case["samples"][1:3])
+            assert len(sub) == 2
+        elif case["kind"] == "byKey":
+            sc = _sc(case["ref"], case["maxNs"], case["snpCeiling"])
+            with pytest.raises(KeyError):
+                sc.countDifferences_byKey(("k1", "k2"))
+            sc.persist(sc.compress(case["seq1"]), "k1")
+            sc.persist(sc.compress(case["seq2"]), "k2")
+            got = sc.countDifferences_byKey(("k1", "k2"), cutoff=None)
+            assert list(got[2:6]) == case["got"]
+            with pytest.raises(TypeError):
+                sc.countDifferences_byKey(["k1", "k2"])
+            with pytest.raises(TypeError):
+                sc.countDifferences_byKey(("k1", "k2", "k3"))
+        elif case["kind"] == "excluded_hash":
+            sc = _sc(case["ref"], 1e8, 1, case["excluded"])
+            assert sc.excluded_hash() == case["got"]
+        elif case["kind"] == "setStats":
+            sc = _sc(case["ref"], 1e8, 20)
+            c1, c2 = sc.compress(case["seq1"]), sc.compress(case["seq2"])
+            n1, n2, nall, rv1, rv2, rv = sc._setStats(c1[case["key"]], c2[case["key"]])
+            assert [n1, n2, nall, sorted(rv)] == case["got"]
+
+
+@pytest.mark.parametrize("ceiling", [20, 1000])
+def test_random_pairs_through_class(ceiling):
+    g = golden("random_pairs.json")
+    sc = _sc(g["ref"], g["maxNs"], ceiling, g["excluded"])
+    for i, s in enumerate(g["seqs"]):
+        sc.persist(sc.compress(s), i)
+    rows = []
+    for i in range(len(g["seqs"])):
+        for r in sc.mcompare(i):
+            if r[2] is not None:
+                rows.append([r[0], r[1], r[2], r[3], r[4], r[5]])
+                # the position sets must agree with the counts (reference: _setStats)
+                assert (len(r[6]), len(r[7]), len(r[8])) == (r[3], r[4], r[5])
+    assert sorted(rows) == g["results"][str(ceiling)]
+
+
+def _collection_engine(chunk_env=None):
+    from findneighbour3_b200.engine import Engine
+    g = golden("collection.json")
+    pos, off, inv = np.array(g["pos"], np.int32), np.array(g["off"], np.int64), np.array(g["invalid"], np.uint8)
+    eng = Engine(g["genome_length"], 0)
+    first = eng.append_bulk(pos, off, inv)
+    assert first == 0
+    return g, eng, pos, off, inv
+
+
+@pytest.mark.parametrize("ceiling", [12, 20, 250])
+def test_collection_one_vs_all_golden(ceiling):
+    g, eng, pos, off, inv = _collection_engine()
+    n = inv.size
+    for q in range(n):
+        got = hits_to_dict(eng.one_vs_all(q, ceiling))
+        want = {r[0]: tuple(r[1:]) for r in g["neighbours"][str(ceiling)][str(q)]}
+        assert got == want, (q, ceiling)
+    eng.close()
+
+
+@pytest.mark.parametrize("ceiling", [12, 250])
+def test_collection_all_vs_all_golden(ceiling):
+    g, eng, pos, off, inv = _collection_engine()
+    edges = eng.all_vs_all(ceiling, upper_only=False)
+    got = {(int(e["row1"]), int(e["row2"])): (int(e["dist"]), int(e["n1"]), int(e["n2"]), int(e["nboth"])) for e in edges}
+    want = {}
+    for q, rows in g["neighbours"][str(ceiling)].items():
+        for r in rows:
+            want[(int(q), r[0])] = tuple(r[1:])
+    assert got == want
+    upper = eng.all_vs_all(ceiling, upper_only=True)
+    got_u = {(int(e["row1"]), int(e["row2"])): int(e["dist"]) for e in upper}
+    assert got_u == {k: v[0] for k, v in want.items() if k[0] < k[1]}
+    # block-row ownership (multi-GPU sharding): the union over phases equals the whole
+    parts = {}
+    for phase in range(3):
+        for e in eng.all_vs_all(ceiling, upper_only=True, stride=3, phase=phase):
+            assert int(e["row1"]) % 3 == phase
+            parts[(int(e["row1"]), int(e["row2"]))] = int(e["dist"])
+    assert parts == got_u
+    eng.close()
+
+
+def test_collection_subset_remove_pair_rowget():
+    g, eng, pos, off, inv = _collection_engine()
+    want20 = {int(q): {r[0]: tuple(r[1:]) for r in rows} for q, rows in g["neighbours"]["20"].items()}
+    q = max(want20, key=lambda k: len(want20[k]))
+    rows = np.array(sorted(want20[q].keys())[:5] + [q, (q + 1) % inv.size], dtype=np.int64)
+    got = hits_to_dict(eng.one_vs_all(q, 20, rows))
+    assert got == {r: v for r, v in want20[q].items() if r in set(rows.tolist())}
+    # pair == one entry of one-vs-all; self pair is 0 for valid rows
+    r2 = sorted(want20[q])[0]
+    assert eng.pair(q, r2, 20) == want20[q][r2]
+    assert eng.pair(q, q, 20)[0] == 0
+    bad = int(np.flatnonzero(inv)[0])
+    assert eng.pair(q, bad, 20) is None and eng.pair(bad, q, 20) is None
+    assert len(eng.one_vs_all(bad, 20)) == 0
+    # row_get round trip
+    o = off[6 * q: 6 * q + 7]
+    p, f, i = eng.row_get(q)
+    assert not i and np.array_equal(p, pos[o[0]:o[6]]) and np.array_equal(f, (o - o[0]).astype(np.int32))
+    # lists_vs_all with the same content == one_vs_all (+ the stored twin at distance 0)
+    lv = hits_to_dict(eng.lists_vs_all(p, f, False, 20))
+    assert lv.pop(q)[0] == 0
+    assert lv == want20[q]
+    # remove a neighbour: it disappears; removing twice is silent; unknown row raises
+    eng.remove(r2)
+    eng.remove(r2)
+    got = hits_to_dict(eng.one_vs_all(q, 20))
+    assert got == {r: v for r, v in want20[q].items() if r != r2}
+    with pytest.raises(KeyError):
+        eng.remove(10 ** 6)
+    with pytest.raises(KeyError):
+        eng.one_vs_all(r2, 20)
+    st = eng.stats()
+    assert st["n_rows"] == inv.size and st["n_live"] == inv.size - 1
+    eng.close()
+
+
+def test_bad_input_is_rejected():
+    from findneighbour3_b200.engine import Engine
+    eng = Engine(100, 0)
+    off = np.array([0, 2, 2, 2, 2, 2, 2], np.int32)
+    with pytest.raises(ValueError):
+        eng.append(np.array([5, 5], np.int32), off)          # not strictly increasing
+    with pytest.raises(ValueError):
+        eng.append(np.array([5, 100], np.int32), off)        # out of range
+    assert eng.stats()["n_rows"] == 0
+    eng.close()
+
+
+def test_consensus_and_recompression_golden():
+    g = golden("consensus.json")
+    sc = _sc("ACTG", 1e8, 10)
+    assert sc.compressed_sequence_hash(sc.compress(g["hash"]["seq"])) == g["hash"]["literal"]
+    for case in g["consensus"]:
+        comp = [sc.compress(s) for s in case["seqs"]]
+        cons = sc.consensus(comp, case["cutoff"])
+        assert {k: sorted(v) for k, v in cons.items()} == case["got"]
+        assert sc.compressed_sequence_hash(cons) == case["hash"]
+    comp = [sc.compress(s) for s in g["consensus"][0]["seqs"]]
+    cons = sc.consensus(comp, 0.6)
+    for c, case in zip(comp, g["patch"]):
+        patch = sc.generate_patch(c, cons)
+        assert {k: sorted(v) for k, v in patch["+"].items()} == case["patch"]["+"]
+        assert {k: sorted(v) for k, v in patch["-"].items()} == case["patch"]["-"]
+        assert sc.apply_patch(patch, cons) == c
+    r = g["recompress"]
+    sc = _sc(r["ref"], 1e8, 20, snpCompressionCeiling=r["snpCompressionCeiling"])
+    for i, s in enumerate(r["seqs"]):
+        sc.persist(sc.compress(s), "g%d" % i)
+    before = {x[1]: x[2:6] for x in sc.mcompare("g0")}
+    assert before == r["mcompare_g0"]
+    launches = sc.engine.stats()["n_rows"]
+    visited = sc.compress_relative_to_consensus("g0", 0.8)
+    assert sorted(visited) == r["visited"]
+    assert sc.summarise_stored_items() == r["summary"]
+    assert sc.engine.stats()["n_rows"] == launches          # re-encoding as patches did not touch the device store
+    assert {x[1]: x[2:6] for x in sc.mcompare("g0")} == r["mcompare_g0"]
+    for i, s in enumerate(r["seqs"]):
+        assert sc.uncompress(sc.seqProfile["g%d" % i]) == s
+
+
+# ---------------------------------------------------------------------------------------------
+# (b) seeded synthetic collections vs the C oracle
+# ---------------------------------------------------------------------------------------------
+def _synthetic(n_anc, max_c, L, seed, **kw):
+    from findneighbour3_b200 import synth
+    excluded = synth.synthetic_mask(L, L // 15, 40, seed=seed + 100)
+    return synth.make_collection(n_anc, max_c, genome_length=L, seed=seed, excluded=excluded, **kw)
+
+
+@pytest.mark.parametrize("shape", ["tb_like", "high_nm", "tiny_genome", "long_runs"])
+def test_synthetic_vs_c_oracle(shape):
+    from findneighbour3_b200.engine import Engine
+    from oracle import c_oracle
+    if shape == "tb_like":        # config 1 shape at reduced genome length
+        coll = _synthetic(12, 25, 500000, 1, k1=500, s=3.0, n_blocks=20, n_mean=4000, rule="lss")
+        ceilings = (20, 250, 2 ** 31 - 1)
+    elif shape == "high_nm":      # config 4 shape: many N (lognormal) and IUPAC M, some invalid through maxNs
+        coll = _synthetic(6, 30, 400000, 4, k1=3000, s=5.0, n_blocks=40, n_mean=30000, m_mean=300, rule="any",
+                          n_lognormal_sigma=0.8, max_ns=60000, p_invalid=0.02)
+        ceilings = (20, 5000)
+    elif shape == "tiny_genome":  # genome shorter than one rank block / one run word
+        coll = _synthetic(5, 8, 31, 9, k1=3, s=1.0, n_blocks=2, n_mean=4, m_mean=1, rule="any", p_invalid=0.1)
+        ceilings = (0, 1, 20)
+    else:                         # runs much longer than the run-word limit and > maxNs-like sizes
+        coll = _synthetic(4, 10, 3000000, 12, k1=200, s=2.0, n_blocks=3, n_mean=120000, m_mean=20, rule="any")
+        ceilings = (20, 400)
+    eng = Engine(coll.genome_length, 0)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    rng = np.random.default_rng(0)
+    queries = rng.choice(coll.n, size=min(coll.n, 12), replace=False)
+    for ceiling in ceilings:
+        for q in queries:
+            got = hits_to_dict(eng.one_vs_all(int(q), ceiling))
+            want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, int(q), ceiling, nthreads=4)
+            assert got == want, (shape, ceiling, int(q))
+    eng.close()
+
+
+def test_incremental_insert_then_query_matches_bulk(monkeypatch):
+    """config 1 flow: persist one by one with a query after each insert; small store chunks force the arena
+    and the header table to roll over."""
+    from findneighbour3_b200.engine import Engine
+    from oracle import c_oracle
+    monkeypatch.setenv("FN3_CHUNK_MB", "1")
+    monkeypatch.setenv("FN3_HDR_SHIFT", "4")
+    coll = _synthetic(6, 20, 300000, 21, k1=400, s=3.0, n_blocks=10, n_mean=3000)
+    eng = Engine(coll.genome_length, 0)
+    for i in range(coll.n):
+        p, o, inv = coll.lists(i)
+        assert eng.append(p, o, inv) == i
+        if i % 7 == 3 or i == coll.n - 1:
+            sub = coll.subset(np.arange(i + 1))
+            want = c_oracle.one_vs_all(sub.pos, sub.off, sub.invalid, i, 20)
+            assert hits_to_dict(eng.one_vs_all(i, 20)) == want
+    st = eng.stats()
+    assert st["n_rows"] == coll.n and st["store_bytes"] > (1 << 20)
+    eng.close()
+
+
+def test_properties_at_scale():
+    """size-independent properties on a TB-sized genome: symmetry of the distance, zero self distance,
+    hits at a low ceiling are a subset of hits at a higher one with identical values, monotone counts."""
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.engine import Engine
+    coll = synth.make_collection(40, 50, seed=5, excluded=synth.synthetic_mask(synth.TB_LENGTH, synth.TB_EXCLUDED,
+                                                                               synth.TB_EXCLUDED_RUNS))
+    eng = Engine(coll.genome_length, 0)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    rng = np.random.default_rng(1)
+    valid = np.flatnonzero(coll.invalid == 0)
+    for q in rng.choice(valid, size=10, replace=False):
+        q = int(q)
+        lo = hits_to_dict(eng.one_vs_all(q, 12))
+        hi = hits_to_dict(eng.one_vs_all(q, 250))
+        assert set(lo) <= set(hi)
+        for r, v in lo.items():
+            assert hi[r] == v and v[0] <= 12
+        assert eng.pair(q, q, 0)[0] == 0
+        for r in list(hi)[:20]:
+            back = eng.pair(r, q, 250)
+            assert back is not None and back[0] == hi[r][0]
+        same_family = np.flatnonzero((coll.family == coll.family[q]) & (coll.invalid == 0))
+        assert len(hi) >= 1 and set(hi) <= set(same_family.tolist())
+    eng.close()
+
+
+def test_threads_append_while_querying():
+    """persist runs outside the server's write semaphore (findNeighbour3-server.py:513-516): appends from one
+    thread while another thread queries must neither crash nor corrupt earlier rows."""
+    import threading
+    from findneighbour3_b200.engine import Engine
+    from oracle import c_oracle
+    coll = _synthetic(4, 25, 200000, 33, k1=300, s=3.0, n_blocks=8, n_mean=2000)
+    eng = Engine(coll.genome_length, 0)
+    half = coll.n // 2
+    first = coll.subset(np.arange(half))
+    eng.append_bulk(first.pos, first.off, first.invalid)
+    want = {q: c_oracle.one_vs_all(first.pos, first.off, first.invalid, q, 20) for q in range(0, half, 5)}
+    errors = []
+
+    def writer():
+        try:
+            for i in range(half, coll.n):
+                p, o, inv = coll.lists(i)
+                eng.append(p, o, inv)
+        except Exception as ex:      # pragma: no cover
+            errors.append(ex)
+
+    t = threading.Thread(target=writer)
+    t.start()
+    for _ in range(3):
+        for q in want:
+            got = {r: v for r, v in hits_to_dict(eng.one_vs_all(q, 20)).items() if r < half}
+            assert got == want[q]
+    t.join()
+    assert not errors
+    full = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, 0, 20)
+    assert hits_to_dict(eng.one_vs_all(0, 20)) == full
+    eng.close()

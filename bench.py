@@ -1,0 +1,432 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the masked pairwise SNV distance path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--samples S] [--ceiling C]
+
+Workload (config.workload): BASELINE.json configs[1] — a 50 000-sample synthetic M. tuberculosis-shaped
+collection (1 000 ancestors x 50, L = 4 411 532, TB-exclude-shaped mask, ~480 variant + ~4 000 blocky N
+positions per sample, 1 % invalid), one new-sample one-vs-all neighbour query per step at snpCeiling 20.
+With N GPUs every rank holds its OWN 50 000-sample shard (weak scaling: the collection grows with N) and
+every query is compared against all shards.
+
+  value     pairwise comparisons/s, device-resident: the K query samples are already rows of the HBM store;
+            a step = query-map build + compare kernel, timed with CUDA events on the engine's stream, L2
+            flushed (256 MiB write, untimed) before every step; max over ranks.
+  e2e       the same metric through the C-ABI a user of the reference class would sit on
+            (persist -> fn3_append, mcompare -> fn3_one_vs_all) with HOST buffers: every step copies the new
+            sample's packed lists host->device and the neighbour records device->host; wall clock, max over ranks.
+  roofline  dominant kernel = k_compare.  achieved = algorithmic bytes / mean CUDA-event duration of the
+            compare launch, algorithmic bytes = sum over compared candidates of B_pair = 4*(|A|+|C|+|G|+|T|+|N|+|M|)+32
+            (SURVEY.md §8(d)).  Early exit and N-run coding make the kernel touch far fewer bytes than that,
+            so `frac` can exceed 1; `touched_*` and `fullscan` (ceiling = 2^31-1: no pair may exit early,
+            every stored byte is streamed) are reported beside it.  See DESIGN.md §6.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pairwise SNV comparisons/sec (one-vs-all, 50k-sample TB collection per GPU, snpCeiling 20)"
+UNIT = "comparisons/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=50000, help="samples per GPU shard")
+    ap.add_argument("--ceiling", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of k_compare from the committed ncu capture, if any (profiles/traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm), sm_mhz_max_seen=max(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+COMMON_ANC = 20      # families every rank can regenerate quickly: the new samples are their relatives
+
+
+def _mask():
+    from findneighbour3_b200 import synth
+    return synth.synthetic_mask(synth.TB_LENGTH, synth.TB_EXCLUDED, synth.TB_EXCLUDED_RUNS)
+
+
+def make_common():
+    from findneighbour3_b200 import synth
+    return synth.make_collection(COMMON_ANC, 50, seed=777, excluded=_mask())
+
+
+def make_shard(samples, rank, common):
+    """rank's shard of `samples` samples; rank 0's shard ends with the `common` families."""
+    from findneighbour3_b200 import synth
+    max_c = 50
+    n_anc = max(1, samples // max_c)
+    if rank == 0:
+        own = max(0, n_anc - COMMON_ANC)
+        if own == 0:
+            return common
+        return synth.concat(synth.make_collection(own, max_c, seed=2, excluded=_mask()), common)
+    return synth.make_collection(n_anc, max_c, seed=2 + 1000 * rank, excluded=_mask())
+
+
+def make_queries(common, count, seed=12345):
+    """`count` newly sequenced samples: relatives (0-3 extra SNVs) of random valid samples of the common
+    families — identical on every rank."""
+    from findneighbour3_b200 import synth
+    rng = np.random.default_rng(seed)
+    valid = np.flatnonzero(common.invalid == 0)
+    out = []
+    for k in range(count):
+        i = int(rng.choice(valid))
+        out.append(synth.new_sample_like(common, i, int(rng.integers(0, 4)), seed=seed + k))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU legs (oracle = test/bench infrastructure; never on the product path)
+# ----------------------------------------------------------------------------------------------------
+def cpu_python_port(coll, queries, ceiling, budget_s):
+    """the reference's algorithm (Python set algebra, single thread — the class the server imports is
+    single-threaded and GIL-bound) on a bounded sample: the query against the first `m` stored samples."""
+    from oracle import seqcomparer_port as port
+    from findneighbour3_b200 import packing
+    m = min(coll.n, 1500)
+    store = {i: coll.as_dict(i) for i in range(coll.n - m, coll.n)}     # includes the queries' own families
+    pairs, t_used, nq = 0, 0.0, 0
+    for (p, o, inv) in queries:
+        store["q"] = {"invalid": 1} if inv else packing.unpack_lists(p, o, None)
+        t0 = time.perf_counter()
+        port.mcompare(store, {}, "q", ceiling)
+        t_used += time.perf_counter() - t0
+        pairs += m
+        nq += 1
+        if t_used > budget_s:
+            break
+    return {"value": pairs / t_used, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d queries x last %d candidates of the shard, oracle/seqcomparer_port.py "
+                      "(Python-set restatement of seqComparer.mcompare), %.1f s" % (nq, m, t_used)}
+
+
+def cpu_c_oracle(coll, queries, ceiling, budget_s, threads):
+    from oracle import c_oracle
+    sub = coll
+    t_used, pairs, nq = 0.0, 0, 0
+    # the query is appended as the last row of a private copy of the store arrays
+    for (p, o, inv) in queries:
+        pos = np.concatenate([sub.pos, p])
+        off = np.concatenate([sub.off, sub.off[-1] + o[1:].astype(np.int64)])
+        invalid = np.concatenate([sub.invalid, np.array([1 if inv else 0], np.uint8)])
+        t0 = time.perf_counter()
+        c_oracle.one_vs_all(pos, off, invalid, sub.n, ceiling, nthreads=threads)
+        t_used += time.perf_counter() - t0
+        pairs += sub.n
+        nq += 1
+        if t_used > budget_s:
+            break
+    return {"value": pairs / t_used, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d queries x all %d candidates, oracle/fn3_oracle.c (C restatement, %d pthreads), %.1f s"
+                      % (nq, sub.n, threads, t_used)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, timed on this host.
+    The reference is pure Python and cannot travel to the GPU box, so its restatement (oracle port) runs."""
+    if rank != 0:
+        return
+    common = make_common()
+    coll = make_shard(min(args.samples, 5000), 0, common)
+    queries = make_queries(common, max(args.steps + args.warmup, 4))
+    budget = max(5.0, min(90.0, args.cpu_seconds * 3))
+    # warm-up steps then timed steps; a step = one query against a bounded candidate sample
+    from oracle import seqcomparer_port as port
+    from findneighbour3_b200 import packing
+    m = min(coll.n, 1500)
+    store = {i: coll.as_dict(i) for i in range(coll.n - m, coll.n)}     # includes the queries' own families
+    for (p, o, inv) in queries[:min(args.warmup, 1)]:
+        store["q"] = {"invalid": 1} if inv else packing.unpack_lists(p, o, None)
+        port.mcompare(store, {}, "q", args.ceiling)
+    t_used, steps = 0.0, 0
+    for (p, o, inv) in queries[args.warmup:args.warmup + args.steps]:
+        store["q"] = {"invalid": 1} if inv else packing.unpack_lists(p, o, None)
+        t0 = time.perf_counter()
+        port.mcompare(store, {}, "q", args.ceiling)
+        t_used += time.perf_counter() - t0
+        steps += 1
+        if t_used > budget:
+            break
+    value = steps * m / t_used
+    sample = ("%d steps, each one query x %d candidates (bounded sample of the 50k workload), single thread: "
+              "Python-set restatement of seqComparer.mcompare (oracle/seqcomparer_port.py)" % (steps, m))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_used / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "configs[1]: one-vs-all over a synthetic TB collection, snpCeiling %d" % args.ceiling,
+                       "candidates_per_step": m, "genome_length": coll.genome_length},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host_cpus": os.cpu_count()}
+    try:
+        line["cpu_baseline_native"] = cpu_c_oracle(coll, queries[:3], args.ceiling, 10.0, os.cpu_count() or 1)
+    except Exception as ex:       # pragma: no cover
+        line["cpu_baseline_native"] = {"error": str(ex)}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    from findneighbour3_b200.engine import Engine
+
+    t_gen = time.time()
+    common = make_common()
+    coll = make_shard(args.samples, rank, common)
+    eng = Engine(coll.genome_length, local)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    K, W = args.steps, args.warmup
+    queries = make_queries(common, 2 * (K + W))      # the same new samples on every rank
+    t_gen = time.time() - t_gen
+
+    # ---- leg 1: device-resident value ------------------------------------------------------------
+    resident = [eng.append(p, o, inv) for (p, o, inv) in queries[:K + W]]
+    n_rows = eng.stats()["n_rows"]
+    bytes_canon_all = int(coll.bytes_canonical()[coll.invalid == 0].sum())
+    for (p, o, inv) in queries[:K + W]:
+        if not inv:
+            bytes_canon_all += 4 * int(o[6]) + 32
+    sampler = ClockSampler(local)
+    barrier()
+    eng.profile_queries(resident[:W], args.ceiling, flush_l2=True)
+    barrier()
+    sampler.start()
+    launches0 = eng.launch_count()
+    prof = eng.profile_queries(resident[W:], args.ceiling, flush_l2=True)
+    launches = eng.launch_count() - launches0 - K      # minus the untimed L2-flush launches
+    barrier()
+    warm = eng.profile_queries(resident[W:], args.ceiling, flush_l2=False)
+    full = eng.profile_queries(resident[W:W + min(K, 20)], 2 ** 31 - 1, flush_l2=True, count_bytes=True)
+    touched = eng.profile_queries(resident[W:W + min(K, 20)], args.ceiling, flush_l2=False, count_bytes=True)
+    barrier()
+    clocks = sampler.stop()
+    t_dev = float(prof["ms_build"].sum() + prof["ms_compare"].sum()) / 1e3
+    t_dev = max_over_ranks(t_dev)
+    comps_per_step = sum_over_ranks(float(n_rows - 1))          # every other row of every shard
+    value = comps_per_step * K / t_dev
+    t_warm = max_over_ranks(float(warm["ms_build"].sum() + warm["ms_compare"].sum()) / 1e3)
+
+    peak, peak_src = peaks()
+    cmp_ms = float(prof["ms_compare"].mean())
+    st = eng.stats()
+    store_bytes_rows = 4 * st["store_words"] + 32 * st["n_rows"]
+    achieved = bytes_canon_all / (cmp_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {
+        "bound": "hbm", "kernel": "k_compare", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None if not traffic else traffic.get("k_compare_bytes_per_launch"),
+        "launch_ms": cmp_ms,
+        "algorithmic_bytes_per_launch": bytes_canon_all,
+        "store_bytes_per_launch": store_bytes_rows,
+        "touched_bytes_per_launch": float(touched["bytes_touched"].mean()),
+        "touched_GBps": float(touched["bytes_touched"].mean()) / (cmp_ms * 1e-3) / 1e9,
+        "note": "frac uses SURVEY §8(d) canonical B_pair bytes; early exit + N-run coding let the kernel skip most "
+                "of them (touched_bytes_per_launch), so frac > 1 is expected here; `fullscan` is the same kernel "
+                "with early exit impossible",
+    }
+    full_ms = float(full["ms_compare"].mean())
+    roofline["fullscan"] = {
+        "ceiling": 2 ** 31 - 1, "launch_ms": full_ms,
+        "achieved_canonical": bytes_canon_all / (full_ms * 1e-3) / 1e9,
+        "frac_canonical": bytes_canon_all / (full_ms * 1e-3) / 1e9 / peak,
+        "touched_bytes_per_launch": float(full["bytes_touched"].mean()),
+        "achieved_touched": float(full["bytes_touched"].mean()) / (full_ms * 1e-3) / 1e9,
+        "frac_touched": float(full["bytes_touched"].mean()) / (full_ms * 1e-3) / 1e9 / peak,
+        "comparisons_per_s": (n_rows - 1) / (full_ms * 1e-3),
+    }
+
+    # ---- leg 2: end to end through the C-ABI with host buffers -----------------------------------
+    fresh = queries[K + W:]
+    ceiling = args.ceiling
+
+    def e2e_step(sample):
+        p, o, inv = sample
+        row = eng.append(p, o, inv)                 # persist: pack -> pinned staging -> H2D
+        return eng.one_vs_all(row, ceiling)         # mcompare: build + compare -> D2H of the neighbour records
+
+    lat = []
+    for s in fresh[:W]:
+        e2e_step(s)
+    st0 = eng.stats()
+    barrier()
+    t0 = time.perf_counter()
+    n_neighbours = 0
+    for s in fresh[W:W + K]:
+        t1 = time.perf_counter()
+        hits = e2e_step(s)
+        lat.append(time.perf_counter() - t1)
+        n_neighbours += len(hits)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    st1 = eng.stats()
+    t_e2e = max_over_ranks(t_e2e)
+    e2e_comps = sum_over_ranks(float(sum(range(st0["n_rows"], st0["n_rows"] + K))))   # store grows by one per step
+    e2e = {"value": e2e_comps / t_e2e, "unit": UNIT,
+           "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) / K,
+           "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) / K,
+           "ms_per_step": 1e3 * t_e2e / K,
+           "p50_ms": 1e3 * statistics.median(lat), "p95_ms": 1e3 * sorted(lat)[int(0.95 * (len(lat) - 1))],
+           "neighbours_per_query": n_neighbours / K,
+           "call": "fn3_append + fn3_one_vs_all via ctypes (seqComparer.persist + mcompare sit on these)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 50,000 synthetic TB sequences per GPU, one new-sample one-vs-all query "
+                               "per step, snpCeiling %d" % ceiling,
+                   "samples_per_gpu": int(coll.n), "genome_length": int(coll.genome_length),
+                   "positions_per_sample_mean": float(coll.positions_per_sample()[coll.invalid == 0].mean()),
+                   "l2": "flushed (256 MiB write) before every timed step; store %.0f MB > L2" % (store_bytes_rows / 1e6),
+                   "parallelism": "candidate shards x%d, no data-path collective in `value`" % world},
+        "value_warm_l2": comps_per_step * K / t_warm,
+        "one_vs_all_p50_ms_device": float(np.median(prof["ms_build"] + prof["ms_compare"])),
+        "one_vs_all_p50_ms_e2e": e2e["p50_ms"],
+        "build_ms": float(prof["ms_build"].mean()), "compare_ms": cmp_ms,
+        "neighbours_per_query": float(prof["n_hits"].mean()),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum_over_ranks(float(launches))),
+        "roofline": roofline, "host_cpus": os.cpu_count(), "setup_s": t_gen,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_python_port(coll, fresh[W:], ceiling, args.cpu_seconds)
+            line["cpu_baseline_native"] = cpu_c_oracle(coll, fresh[W:W + 4], ceiling, args.cpu_seconds,
+                                                       os.cpu_count() or 1)
+        except Exception as ex:   # pragma: no cover
+            line["cpu_baseline"] = {"error": str(ex)}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,7 +29,8 @@ class Edge(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_live", C.c_int64), ("n_invalid", C.c_int64),
-                ("store_words", C.c_int64), ("store_bytes", C.c_int64), ("positions", C.c_int64)]
+                ("store_words", C.c_int64), ("store_bytes", C.c_int64), ("positions", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 _i32p = C.POINTER(C.c_int32)
@@ -59,7 +60,7 @@ SIGNATURES = {
                                  C.POINTER(Hit), _i32p]),
     "fn3_set_reference": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64]),
     "fn3_compress": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64, _i32p, C.c_char_p, C.c_int64, _i64p]),
-    "fn3_profile_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i64p, _i64p]),
+    "fn3_profile_queries": (C.c_int, [_vp, _i64p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i64p, _i64p]),
     "fn3_launch_count": (C.c_int64, [_vp]),
 }
 

@@ -480,10 +480,14 @@ struct fn3_engine {
     long long map_stride = 0, rank_stride = 0, n_blk = 0; int rank_ctas = 0;
     uint8_t* qmap = nullptr; RankBlk* qrank = nullptr; uint3* partial = nullptr;
     QuerySlot* d_slots = nullptr; QuerySlot* h_slots = nullptr;   // h_slots pinned
+    // survivor buffer: one allocation = [32-byte counter block | records], mirrored in pinned host memory so
+    // that the counter and the first records come back in ONE device-to-host copy
+    unsigned char* d_outbuf = nullptr; unsigned char* h_outbuf = nullptr;
     EdgeRec* d_out = nullptr; long long out_cap = 0;
     unsigned long long* d_count = nullptr;   // [0] hit counter, [1] touched bytes
-    unsigned long long* h_count = nullptr;   // pinned [2]
-    EdgeRec* h_out = nullptr; long long h_out_cap = 0;           // pinned
+    unsigned long long* h_count = nullptr;
+    EdgeRec* h_out = nullptr; long long h_out_cap = 0;
+    std::atomic<long long> h2d_bytes{0}, d2h_bytes{0};
     long long* d_rows = nullptr; long long d_rows_cap = 0;
     long long* h_rows = nullptr; long long h_rows_cap = 0;       // pinned
     // scratch rows for samples that are not stored (pair_lists / lists_vs_all)
@@ -531,13 +535,18 @@ extern "C" const char* fn3_last_error(fn3_engine* e) {
 
 extern "C" int64_t fn3_launch_count(fn3_engine* e) { return e ? e->launches.load() : 0; }
 
+#define FN3_OUT_HDR 32
+#define FN3_FIRST_HITS 256      // records fetched together with the counter
+
 static int ensure_out(fn3_engine* e, long long cap) {
     if (cap <= e->out_cap) return FN3_OK;
     long long want = std::max<long long>(cap, e->out_cap * 2);
     want = std::max<long long>(want, 4096);
-    if (e->d_out) cudaFree(e->d_out);
-    e->d_out = nullptr; e->out_cap = 0;
-    CU(e, cudaMalloc(&e->d_out, (size_t)want * sizeof(EdgeRec)));
+    if (e->d_outbuf) { cudaStreamSynchronize(e->q_stream); cudaFree(e->d_outbuf); }
+    e->d_outbuf = nullptr; e->out_cap = 0;
+    CU(e, cudaMalloc(&e->d_outbuf, FN3_OUT_HDR + (size_t)want * sizeof(EdgeRec)));
+    e->d_count = reinterpret_cast<unsigned long long*>(e->d_outbuf);
+    e->d_out = reinterpret_cast<EdgeRec*>(e->d_outbuf + FN3_OUT_HDR);
     e->out_cap = want;
     return FN3_OK;
 }
@@ -546,9 +555,11 @@ static int ensure_hout(fn3_engine* e, long long cap) {
     if (cap <= e->h_out_cap) return FN3_OK;
     long long want = std::max<long long>(cap, e->h_out_cap * 2);
     want = std::max<long long>(want, 4096);
-    if (e->h_out) cudaFreeHost(e->h_out);
-    e->h_out = nullptr; e->h_out_cap = 0;
-    CU(e, cudaHostAlloc(&e->h_out, (size_t)want * sizeof(EdgeRec), cudaHostAllocDefault));
+    if (e->h_outbuf) cudaFreeHost(e->h_outbuf);
+    e->h_outbuf = nullptr; e->h_out_cap = 0;
+    CU(e, cudaHostAlloc(&e->h_outbuf, FN3_OUT_HDR + (size_t)want * sizeof(EdgeRec), cudaHostAllocDefault));
+    e->h_count = reinterpret_cast<unsigned long long*>(e->h_outbuf);
+    e->h_out = reinterpret_cast<EdgeRec*>(e->h_outbuf + FN3_OUT_HDR);
     e->h_out_cap = want;
     return FN3_OK;
 }
@@ -646,8 +657,11 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
     if ((s = cudaMalloc(&e->partial, (size_t)e->rank_ctas * e->n_slots * sizeof(uint3))) != cudaSuccess) return fail("cudaMalloc(partial)", s);
     if ((s = cudaMalloc(&e->d_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS)) != cudaSuccess) return fail("cudaMalloc(slots)", s);
     if ((s = cudaHostAlloc(&e->h_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(slots)", s);
-    if ((s = cudaMalloc(&e->d_count, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(count)", s);
-    if ((s = cudaHostAlloc(&e->h_count, 2 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(count)", s);
+    if (ensure_out(e, 4096) != FN3_OK || ensure_hout(e, 4096) != FN3_OK) {
+        set_err(nullptr, FN3_ENOMEM, "fn3_create: survivor buffers: %s", e->err.c_str());
+        fn3_destroy(e);
+        return nullptr;
+    }
     if ((s = cudaMalloc(&e->d_scratch_hdr, 2 * sizeof(RowHdr))) != cudaSuccess) return fail("cudaMalloc(scratch hdr)", s);
     if ((s = cudaMemset(e->qmap, 0, (size_t)e->map_stride * e->n_slots)) != cudaSuccess) return fail("cudaMemset", s);
     e->store_bytes = 0;
@@ -662,7 +676,7 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     for (auto p : e->data_chunks) cudaFree(p);
     for (auto p : e->hdr_chunks) cudaFree(p);
     cudaFree(e->qmap); cudaFree(e->qrank); cudaFree(e->partial); cudaFree(e->d_slots);
-    cudaFree(e->d_out); cudaFree(e->d_count); cudaFree(e->d_rows); cudaFree(e->d_scratch);
+    cudaFree(e->d_outbuf); cudaFree(e->d_rows); cudaFree(e->d_scratch);
     cudaFree(e->d_scratch_hdr); cudaFree(e->d_flush);
     cudaFree(e->d_refmask); cudaFree(e->d_seq); cudaFree(e->d_mchars); cudaFree(e->d_cpos);
     cudaFree(e->d_ccounts); cudaFree(e->d_ctotals);
@@ -672,8 +686,7 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->h_mchars) cudaFreeHost(e->h_mchars);
     if (e->in_stream) cudaStreamDestroy(e->in_stream);
     if (e->h_slots) cudaFreeHost(e->h_slots);
-    if (e->h_count) cudaFreeHost(e->h_count);
-    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->h_outbuf) cudaFreeHost(e->h_outbuf);
     if (e->h_rows) cudaFreeHost(e->h_rows);
     if (e->stage) cudaFreeHost(e->stage);
     if (e->stage_hdr) cudaFreeHost(e->stage_hdr);
@@ -822,6 +835,7 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
             w += need;
         }
         CU(e, cudaMemcpyAsync(dbase, e->stage, batch_words * 4, cudaMemcpyHostToDevice, e->copy_stream));
+        e->h2d_bytes += (long long)batch_words * 4 + (j - i) * (long long)sizeof(RowHdr);
         // headers: may straddle header chunks
         long long r = i;
         while (r < j) {
@@ -899,6 +913,7 @@ extern "C" int fn3_stats_get(fn3_engine* e, fn3_stats* out) {
     std::lock_guard<std::mutex> g(e->store_mu);
     out->n_rows = e->n_rows; out->n_live = e->n_live; out->n_invalid = e->n_invalid;
     out->store_words = e->store_words; out->store_bytes = e->store_bytes; out->positions = e->positions;
+    out->h2d_bytes = e->h2d_bytes.load(); out->d2h_bytes = e->d2h_bytes.load();
     return FN3_OK;
 }
 
@@ -945,14 +960,19 @@ static void fill_hdr_table(fn3_engine* e, HdrTable& t) {   // store_mu held
 }
 
 // enqueue: slots upload + map clear + scatter + rank build for `ns` slots (h_slots filled by caller)
-static int enqueue_query_build(fn3_engine* e, int ns) {
+// (`resident` != nullptr: the slots are already on the device — measurement hook)
+static int enqueue_query_build(fn3_engine* e, int ns, const QuerySlot* resident = nullptr) {
     cudaStream_t st = e->q_stream;
-    CU(e, cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(QuerySlot) * ns, cudaMemcpyHostToDevice, st));
+    const QuerySlot* d_slots = resident ? resident : e->d_slots;
+    if (!resident) {
+        CU(e, cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(QuerySlot) * ns, cudaMemcpyHostToDevice, st));
+        e->h2d_bytes += (long long)sizeof(QuerySlot) * ns;
+    }
     CU(e, cudaMemsetAsync(e->qmap, 0, (size_t)e->map_stride * ns, st));
     uint32_t maxw = 1;
     for (int s = 0; s < ns; ++s) maxw = std::max(maxw, e->h_slots[s].hdr.end[5]);
     dim3 gs((unsigned)std::min<uint32_t>((maxw + 255) / 256, 1024u), (unsigned)ns);
-    k_scatter_query<<<gs, 256, 0, st>>>(e->d_slots, e->qmap, e->map_stride, e->pos_bits);
+    k_scatter_query<<<gs, 256, 0, st>>>(d_slots, e->qmap, e->map_stride, e->pos_bits);
     dim3 gr((unsigned)e->rank_ctas, (unsigned)ns);
     k_rank_a<<<gr, 1024, 0, st>>>(e->qmap, e->qrank, e->partial, e->map_stride, e->rank_stride, e->n_blk, e->rank_ctas);
     k_rank_b<<<gr, 1024, 0, st>>>(e->qrank, e->partial, e->rank_stride, e->n_blk, e->rank_ctas);
@@ -962,11 +982,11 @@ static int enqueue_query_build(fn3_engine* e, int ns) {
 }
 
 static int enqueue_compare(fn3_engine* e, const HdrTable& ht, const long long* d_rows, long long row_begin, long long n,
-                           int ns, int ceiling, bool count_bytes) {
+                           int ns, int ceiling, bool count_bytes, const QuerySlot* resident = nullptr) {
     if (n <= 0) return FN3_OK;
     CompareParams p;
     p.hdr = ht; p.rows = d_rows; p.row_begin = row_begin; p.n = n;
-    p.qmap = e->qmap; p.qrank = e->qrank; p.slots = e->d_slots;
+    p.qmap = e->qmap; p.qrank = e->qrank; p.slots = resident ? resident : e->d_slots;
     p.map_stride = e->map_stride; p.rank_stride = e->rank_stride; p.rank_last = e->n_blk - 1;
     p.out = e->d_out; p.out_count = e->d_count; p.touched = e->d_count + 1; p.out_cap = e->out_cap;
     p.ceiling = ceiling; p.pos_bits = e->pos_bits;
@@ -1010,6 +1030,7 @@ static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const in
         uint32_t* dst = e->d_scratch + (which ? e->scratch_words / 2 : 0);
         h.data = (unsigned long long)(uintptr_t)dst;
         CU(e, cudaMemcpyAsync(dst, e->stage, need * 4, cudaMemcpyHostToDevice, e->q_stream));
+        e->h2d_bytes += (long long)need * 4;
         CU(e, cudaStreamSynchronize(e->q_stream));
     }
     *out = h;
@@ -1032,18 +1053,19 @@ static int run_one_vs_all(fn3_engine* e, int ceiling, const int64_t* rows, int64
             e->h_rows[i] = rows[i];
         }
         CU(e, cudaMemcpyAsync(e->d_rows, e->h_rows, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, e->q_stream));
+        e->h2d_bytes += n * (long long)sizeof(long long);
         d_rows = e->d_rows;
     }
     if ((rc = ensure_out(e, n))) return rc;
-    if ((rc = ensure_hout(e, std::min<long long>(n, 4096)))) return rc;
-    CU(e, cudaMemsetAsync(e->d_count, 0, 2 * sizeof(unsigned long long), e->q_stream));
+    CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
     if ((rc = enqueue_query_build(e, 1))) return rc;
     if ((rc = enqueue_compare(e, ht, d_rows, 0, n, 1, ceiling, false))) return rc;
-    // one D2H for the counter and the first records; a second one only for long neighbour lists
-    const long long first = std::min<long long>(std::min<long long>(n, e->h_out_cap), 4096);
-    CU(e, cudaMemcpyAsync(e->h_count, e->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->q_stream));
-    CU(e, cudaMemcpyAsync(e->h_out, e->d_out, (size_t)first * sizeof(EdgeRec), cudaMemcpyDeviceToHost, e->q_stream));
+    // ONE device-to-host copy brings the counter and the first records; a second one only for long lists
+    const long long first = std::min<long long>(n, FN3_FIRST_HITS);
+    CU(e, cudaMemcpyAsync(e->h_outbuf, e->d_outbuf, FN3_OUT_HDR + (size_t)first * sizeof(EdgeRec), cudaMemcpyDeviceToHost,
+                          e->q_stream));
     CU(e, cudaStreamSynchronize(e->q_stream));
+    e->d2h_bytes += FN3_OUT_HDR + first * (long long)sizeof(EdgeRec);
     const long long cnt = (long long)e->h_count[0];
     *n_out = cnt;
     if (cnt > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld hits, %lld needed", (long long)cap, cnt);
@@ -1051,6 +1073,7 @@ static int run_one_vs_all(fn3_engine* e, int ceiling, const int64_t* rows, int64
         if ((rc = ensure_hout(e, cnt))) return rc;
         CU(e, cudaMemcpyAsync(e->h_out, e->d_out, (size_t)cnt * sizeof(EdgeRec), cudaMemcpyDeviceToHost, e->q_stream));
         CU(e, cudaStreamSynchronize(e->q_stream));
+        e->d2h_bytes += cnt * (long long)sizeof(EdgeRec);
     }
     for (long long i = 0; i < cnt; ++i) {
         const EdgeRec& r = e->h_out[i];
@@ -1176,15 +1199,17 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
             }
         }
         const long long cbegin = upper_only ? min_row + 1 : 0;
-        CU(e, cudaMemsetAsync(e->d_count, 0, 2 * sizeof(unsigned long long), e->q_stream));
+        CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
         if ((rc = enqueue_query_build(e, ns))) return rc;
         if ((rc = enqueue_compare(e, ht, nullptr, cbegin, n_store - cbegin, ns, ceiling, false))) return rc;
-        CU(e, cudaMemcpyAsync(e->h_count, e->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->q_stream));
+        CU(e, cudaMemcpyAsync(e->h_count, e->d_count, FN3_OUT_HDR, cudaMemcpyDeviceToHost, e->q_stream));
         CU(e, cudaStreamSynchronize(e->q_stream));
+        e->d2h_bytes += FN3_OUT_HDR;
         const long long cnt = (long long)e->h_count[0];
         if (cnt > 0) {
             if (total + cnt <= cap)
                 CU(e, cudaMemcpy(out + total, e->d_out, (size_t)cnt * sizeof(EdgeRec), cudaMemcpyDeviceToHost));
+            e->d2h_bytes += cnt * (long long)sizeof(EdgeRec);
             total += cnt;
         }
     }
@@ -1280,47 +1305,84 @@ extern "C" int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, i
 
 // ---- measurement hook ----------------------------------------------------------------------
 
-extern "C" int fn3_profile_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling, int32_t iters, int32_t flush_l2,
-                                      float* ms_total, float* ms_compare, int64_t* n_hits, int64_t* bytes_touched) {
-    if (!e || iters < 1) return set_err(e, FN3_EARG, "fn3_profile_one_vs_all: bad arguments");
+extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int32_t n, int32_t ceiling, int32_t flush_l2,
+                                   float* ms_build, float* ms_compare, int64_t* n_hits, int64_t* bytes_touched) {
+    if (!e || !query_rows || n < 1) return set_err(e, FN3_EARG, "fn3_profile_queries: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
-    RowHdr qh; int rc;
-    if ((rc = stored_hdr(e, query_row, &qh, "fn3_profile_one_vs_all"))) return rc;
     HdrTable ht; long long n_store;
     snapshot_store(e, ht, n_store);
-    QuerySlot& s = e->h_slots[0];
-    s.hdr = qh; s.row = query_row; s.skip_le = -1; s.exclude = query_row; s.pad = 0;
+    int rc;
     if ((rc = ensure_out(e, n_store))) return rc;
     if (flush_l2 && !e->d_flush) {
         e->flush_n = (256ll << 20) / 16;
         CU(e, cudaMalloc(&e->d_flush, (size_t)e->flush_n * 16));
     }
     cudaStream_t st = e->q_stream;
-    for (int it = 0; it < iters; ++it) {
+    std::vector<cudaEvent_t> evs((size_t)n * 3, nullptr);
+    for (auto& ev : evs) CU(e, cudaEventCreate(&ev));
+    unsigned long long* d_pc = nullptr;                       // per-step counters: [hits, touched, -, -]
+    CU(e, cudaMalloc(&d_pc, (size_t)n * FN3_OUT_HDR));
+    CU(e, cudaMemsetAsync(d_pc, 0, (size_t)n * FN3_OUT_HDR, st));
+    unsigned long long* saved = e->d_count;
+    // all query slots go to the device in one copy; then the whole batch is queued without any host
+    // synchronisation, events bracketing each step's pieces
+    std::vector<QuerySlot> hs((size_t)n);
+    uint32_t maxw = 1;
+    for (int it = 0; it < n; ++it) {
+        RowHdr qh;
+        if ((rc = stored_hdr(e, query_rows[it], &qh, "fn3_profile_queries"))) break;
+        QuerySlot& s = hs[(size_t)it];
+        s.hdr = qh; s.row = query_rows[it]; s.skip_le = -1; s.exclude = query_rows[it]; s.pad = 0;
+        maxw = std::max(maxw, qh.end[5]);
+    }
+    QuerySlot* d_ps = nullptr;
+    if (rc == FN3_OK) {
+        CU(e, cudaMalloc(&d_ps, (size_t)n * sizeof(QuerySlot)));
+        CU(e, cudaMemcpyAsync(d_ps, hs.data(), (size_t)n * sizeof(QuerySlot), cudaMemcpyHostToDevice, st));
+        CU(e, cudaStreamSynchronize(st));
+        e->h_slots[0].hdr.end[5] = maxw;      // sizes the scatter grid
+    }
+    for (int it = 0; it < n && rc == FN3_OK; ++it) {
         if (flush_l2) { k_fill<<<e->sm_count * 4, 512, 0, st>>>(e->d_flush, e->flush_n, (uint32_t)it); e->launches += 1; }
-        CU(e, cudaMemsetAsync(e->d_count, 0, 2 * sizeof(unsigned long long), st));
-        CU(e, cudaEventRecord(e->ev[0], st));
-        if ((rc = enqueue_query_build(e, 1))) return rc;
-        CU(e, cudaEventRecord(e->ev[1], st));
-        if ((rc = enqueue_compare(e, ht, nullptr, 0, n_store, 1, ceiling, false))) return rc;
-        CU(e, cudaEventRecord(e->ev[2], st));
-        CU(e, cudaStreamSynchronize(st));
-        float a = 0, b = 0;
-        CU(e, cudaEventElapsedTime(&a, e->ev[0], e->ev[2]));
-        CU(e, cudaEventElapsedTime(&b, e->ev[1], e->ev[2]));
-        if (ms_total) ms_total[it] = a;
-        if (ms_compare) ms_compare[it] = b;
+        e->d_count = d_pc + (size_t)it * (FN3_OUT_HDR / sizeof(unsigned long long));
+        cudaEventRecord(evs[(size_t)it * 3 + 0], st);
+        if ((rc = enqueue_query_build(e, 1, d_ps + it))) break;
+        cudaEventRecord(evs[(size_t)it * 3 + 1], st);
+        if ((rc = enqueue_compare(e, ht, nullptr, 0, n_store, 1, ceiling, false, d_ps + it))) break;
+        cudaEventRecord(evs[(size_t)it * 3 + 2], st);
     }
-    CU(e, cudaMemcpy(e->h_count, e->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    if (n_hits) *n_hits = (int64_t)e->h_count[0];
-    if (bytes_touched) {
-        CU(e, cudaMemsetAsync(e->d_count, 0, 2 * sizeof(unsigned long long), st));
-        if ((rc = enqueue_query_build(e, 1))) return rc;
-        if ((rc = enqueue_compare(e, ht, nullptr, 0, n_store, 1, ceiling, true))) return rc;
-        CU(e, cudaMemcpyAsync(e->h_count, e->d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CU(e, cudaStreamSynchronize(st));
-        *bytes_touched = (int64_t)e->h_count[1];
+    e->d_count = saved;
+    cudaError_t sync = cudaStreamSynchronize(st);
+    std::vector<unsigned long long> pc((size_t)n * 4, 0);
+    if (rc == FN3_OK && sync == cudaSuccess) {
+        for (int it = 0; it < n; ++it) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, evs[(size_t)it * 3 + 0], evs[(size_t)it * 3 + 1]);
+            cudaEventElapsedTime(&b, evs[(size_t)it * 3 + 1], evs[(size_t)it * 3 + 2]);
+            if (ms_build) ms_build[it] = a;
+            if (ms_compare) ms_compare[it] = b;
+        }
+        cudaMemcpy(pc.data(), d_pc, (size_t)n * FN3_OUT_HDR, cudaMemcpyDeviceToHost);
+        if (n_hits) for (int it = 0; it < n; ++it) n_hits[it] = (int64_t)pc[(size_t)it * 4];
     }
+    if (rc == FN3_OK && sync == cudaSuccess && bytes_touched) {
+        // instrumented, untimed pass: bytes of headers + row data each compare launch actually loads
+        cudaMemsetAsync(d_pc, 0, (size_t)n * FN3_OUT_HDR, st);
+        for (int it = 0; it < n && rc == FN3_OK; ++it) {
+            e->d_count = d_pc + (size_t)it * (FN3_OUT_HDR / sizeof(unsigned long long));
+            if ((rc = enqueue_query_build(e, 1, d_ps + it))) break;
+            if ((rc = enqueue_compare(e, ht, nullptr, 0, n_store, 1, ceiling, true, d_ps + it))) break;
+        }
+        e->d_count = saved;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(pc.data(), d_pc, (size_t)n * FN3_OUT_HDR, cudaMemcpyDeviceToHost);
+        for (int it = 0; it < n; ++it) bytes_touched[it] = (int64_t)pc[(size_t)it * 4 + 1];
+    }
+    cudaFree(d_ps);
+    for (auto ev : evs) cudaEventDestroy(ev);
+    cudaFree(d_pc);
+    if (rc != FN3_OK) return rc;
+    if (sync != cudaSuccess) return set_err(e, FN3_ECUDA, "fn3_profile_queries: %s", cudaGetErrorString(sync));
     return FN3_OK;
 }

@@ -233,17 +233,19 @@ class Engine:
         return (hit.dist, hit.n1, hit.n2, hit.nboth)
 
     # -- measurement ----------------------------------------------------------------------
-    def profile_one_vs_all(self, query_row, ceiling, iters=10, flush_l2=False, count_bytes=True):
-        ms_total = np.zeros(iters, dtype=np.float32)
-        ms_cmp = np.zeros(iters, dtype=np.float32)
-        n_hits = C.c_int64(0)
-        touched = C.c_int64(0)
-        rc = self._lib.fn3_profile_one_vs_all(self._h, int(query_row), int(ceiling), int(iters), 1 if flush_l2 else 0,
-                                              _ptr(ms_total, _f32p), _ptr(ms_cmp, _f32p), C.byref(n_hits),
-                                              C.byref(touched) if count_bytes else None)
+    def profile_queries(self, query_rows, ceiling, flush_l2=False, count_bytes=False):
+        """device-only timing of one-vs-all for each stored row in query_rows (bench.py's `value` leg)."""
+        q = np.ascontiguousarray(query_rows, dtype=np.int64)
+        n = q.size
+        ms_build = np.zeros(n, dtype=np.float32)
+        ms_cmp = np.zeros(n, dtype=np.float32)
+        n_hits = np.zeros(n, dtype=np.int64)
+        touched = np.zeros(n, dtype=np.int64) if count_bytes else None
+        rc = self._lib.fn3_profile_queries(self._h, _ptr(q, _i64p), n, int(ceiling), 1 if flush_l2 else 0,
+                                           _ptr(ms_build, _f32p), _ptr(ms_cmp, _f32p), _ptr(n_hits, _i64p),
+                                           _ptr(touched, _i64p))
         self._check(rc)
-        return {"ms_total": ms_total, "ms_compare": ms_cmp, "n_hits": n_hits.value,
-                "bytes_touched": touched.value if count_bytes else None}
+        return {"ms_build": ms_build, "ms_compare": ms_cmp, "n_hits": n_hits, "bytes_touched": touched}
 
     def launch_count(self):
         return int(self._lib.fn3_launch_count(self._h))

@@ -13,9 +13,8 @@ Same constructor, methods, return shapes and exception types as the reference cl
   * the host keeps the reference-format dict of every sample (needed by load(), uncompress(),
     the MSA code and MongoDB pickling — SURVEY.md §8(b) "Ownership").
 
-Deliberate deviations (documented in INTEGRATION.md): a malformed object is rejected at
-persist() time instead of at the first comparison; `compress_relative_to_consensus` compares
-guids by value where the reference uses `is not` (:588).
+Deliberate deviation (documented in INTEGRATION.md): a malformed object is rejected at
+persist() time instead of at the first comparison.
 """
 import hashlib
 import json
@@ -521,7 +520,14 @@ class seqComparer():
         visited_sequences = [self.seqProfile[guid]]
         found = self.neighbours(guid, None, self.snpCompressionCeiling)
         for other in self.seqProfile.keys():
-            if other != guid and other in found and found[other][0] < self.snpCompressionCeiling:
+            if other == guid:
+                # the reference skips the seed by IDENTITY (`result[1] is not guid`, :588): an equal but distinct
+                # string object passes the test and the seed is visited twice (its self distance is 0)
+                if other is not guid and not packing.is_invalid(self.seqProfile[other]) \
+                        and 0 < self.snpCompressionCeiling:
+                    visited_sequences.append(self.seqProfile[other])
+                    visited_guids.append(other)
+            elif other in found and found[other][0] < self.snpCompressionCeiling:
                 visited_sequences.append(self.seqProfile[other])
                 visited_guids.append(other)
         if len(visited_sequences) > 1:

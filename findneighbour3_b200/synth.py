@@ -17,6 +17,7 @@ Excluded positions are dropped exactly as compress() does (src/seqComparer.py:29
 Everything is numpy; a 50 000-sample TB collection takes a few tens of seconds.
 """
 from dataclasses import dataclass
+from functools import lru_cache
 
 import numpy as np
 
@@ -74,9 +75,20 @@ class Collection:
         return Collection(self.genome_length, pos, off, self.invalid[idx].copy(), self.family[idx].copy())
 
 
+@lru_cache(maxsize=4)
 def random_reference(length, seed=962):
-    """uint8 codes 0..3 (A,C,G,T): seeded stand-in for the missing NC_000962 FASTA."""
-    return np.random.default_rng(seed).integers(0, 4, size=length, dtype=np.uint8)
+    """uint8 codes 0..3 (A,C,G,T): seeded stand-in for the missing NC_000962 FASTA (read-only, cached)."""
+    ref = np.random.default_rng(seed).integers(0, 4, size=length, dtype=np.uint8)
+    ref.setflags(write=False)
+    return ref
+
+
+def concat(a, b):
+    """two Collections over the same genome -> one (b's samples after a's)."""
+    assert a.genome_length == b.genome_length
+    off = np.concatenate([a.off, a.off[-1] + b.off[1:]])
+    return Collection(a.genome_length, np.concatenate([a.pos, b.pos]), off, np.concatenate([a.invalid, b.invalid]),
+                      np.concatenate([a.family, b.family + (int(a.family.max()) + 1 if a.n else 0)]))
 
 
 def reference_string(ref_codes):

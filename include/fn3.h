@@ -81,6 +81,8 @@ typedef struct fn3_stats {
     int64_t store_words;     /* 32-bit words of row data resident in HBM (live + dead) */
     int64_t store_bytes;     /* device bytes reserved for the store (chunks + headers) */
     int64_t positions;       /* sum over live rows of |A|+|C|+|G|+|T|+|N|+|M| (canonical B_pair positions) */
+    int64_t h2d_bytes;       /* bytes copied host->device by this engine since creation */
+    int64_t d2h_bytes;       /* bytes copied device->host by this engine since creation */
 } fn3_stats;
 
 /* ---- life cycle ------------------------------------------------------------------ */
@@ -177,16 +179,15 @@ int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_
 
 /* ---- measurement hooks (bench.py only; no effect on results) -------------------- */
 
-/* Run the one-vs-all DEVICE work for `query_row` `iters` times on the engine's stream
- * with inputs already resident: each iteration = query-map build + compare kernel.
- * ms_total[i] / ms_compare[i] receive CUDA-event times of the whole iteration and of
- * the compare kernel alone; *n_hits the survivor count of the last iteration;
- * *bytes_touched the bytes of row data + headers the compare kernel actually loaded in
- * the last iteration (counted by an instrumented pass that is NOT timed), may be NULL.
- * flush_l2 != 0 writes a >L2-sized scratch buffer between iterations (untimed). */
-int fn3_profile_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling, int32_t iters,
-                           int32_t flush_l2, float* ms_total, float* ms_compare,
-                           int64_t* n_hits, int64_t* bytes_touched);
+/* Run the one-vs-all DEVICE work (query-map build + compare kernel, inputs already resident in HBM) once
+ * for each of the n stored rows in query_rows, queued back to back on the engine's stream with no host
+ * synchronisation in between.  ms_build[i] / ms_compare[i] receive the CUDA-event times of step i's
+ * query-map build (memset + scatter + rank) and of its compare kernel; n_hits[i] its survivor count;
+ * bytes_touched[i] (may be NULL) the bytes of headers + row data the compare kernel of step i actually
+ * loaded, counted by a separate instrumented pass that is NOT timed.  flush_l2 != 0 writes a 256 MiB
+ * scratch buffer before each step (outside the timed events) so that every step starts with a cold L2. */
+int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int32_t n, int32_t ceiling, int32_t flush_l2,
+                        float* ms_build, float* ms_compare, int64_t* n_hits, int64_t* bytes_touched);
 
 /* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 int64_t fn3_launch_count(fn3_engine* e);

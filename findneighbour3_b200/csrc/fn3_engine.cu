@@ -12,8 +12,9 @@
 //   row data   : 32-bit words, 16-byte aligned per row:  [A | C | G | T | Nruns | Mruns]
 //                A..T = sorted int32 positions; runs = (len-1) << pos_bits | start
 //   row header : 32 B (one sector): device pointer + 6 cumulative list ends
-//   query map  : uint8 code per genome position (0 ref,1..4 ACGT,5 N,6 M), L2-resident
-//   query rank : per 32 positions {maskDef, maskU, maskM, cumDef, cumU, cumM, 0, 0} (32 B)
+//   query      : compact, staged in SHARED memory by every compare CTA: bitmap of touched 32-position
+//                blocks + prefix counts (uint2 per 1024 positions) and one 32-byte entry per touched block
+//                {maskDef, maskU, maskB0, maskB1, maskM, cumDef, cumU, cumM}
 //
 // No CPU path exists in this file: every distance is produced by k_compare on the device.
 
@@ -41,12 +42,14 @@ struct __align__(32) RowHdr {
 };
 static_assert(sizeof(RowHdr) == 32, "RowHdr must be one 32-byte sector");
 
-struct __align__(32) RankBlk {
-    uint32_t mDef, mU, mM;     // bit i: position 32*b+i of the query is ACGT-nonref / N-or-M / M
-    uint32_t cDef, cU, cM;     // number of such positions strictly below 32*b
-    uint32_t pad0, pad1;
+// The query, compacted.  Positions are grouped in blocks of 32.  `bmpref[w]` holds, for
+// blocks 32w..32w+31, .x = bit per block "the query is non-reference / N / M somewhere in this block" and
+// .y = number of such (touched) blocks below block 32w.  Entry i describes the i-th touched block:
+struct __align__(32) QEntry {
+    uint32_t mDef, mU, mB0, mB1;   // per position: ACGT-nonref / N-or-M / base code bit 0 / bit 1 (A0 C1 G2 T3)
+    uint32_t mM, cDef, cU, cM;     // per position: M ; number of Def / U / M positions below this block
 };
-static_assert(sizeof(RankBlk) == 32, "RankBlk must be one 32-byte sector");
+static_assert(sizeof(QEntry) == 32, "QEntry must be one 32-byte sector");
 
 struct __align__(32) EdgeRec {   // device-side survivor record (== fn3_edge)
     long long row1, row2;
@@ -70,23 +73,30 @@ struct QuerySlot {             // one query of a tile
     long long pad;
 };
 
+struct QueryState {            // device arrays holding the compact form of up to n_slots queries
+    uint2* bmpref;             // slot s at bmpref + s*nw
+    QEntry* ent;               // slot s at ent + s*ent_stride
+    uint4* info;               // slot s: {nE, |V_q|, |U_q|, |M_q|}
+    uint32_t* bm_scratch;      // slot s at bm_scratch + s*2*nw (build kernel, only when the bitmap exceeds smem)
+    long long ent_stride;
+    int nw;                    // 32-block words: ceil(n_blk / 32)
+    int n_blk;                 // blocks incl. the end sentinel block
+};
+
 struct CompareParams {
     HdrTable hdr;
+    QueryState qs;
     const long long* rows;     // optional explicit candidate list
     long long row_begin;       // else candidates row_begin .. row_begin+n-1
     long long n;
-    const uint8_t* qmap;       // slot s at qmap + s*map_stride
-    const RankBlk* qrank;      // slot s at qrank + s*rank_stride
     const QuerySlot* slots;    // device array [n_slots]
-    long long map_stride;      // bytes
-    long long rank_stride;     // RankBlk entries
-    long long rank_last;       // index of the totals entry inside a slot's rank array
     EdgeRec* out;
     unsigned long long* out_count;
     unsigned long long* touched;   // instrumented variant only
     long long out_cap;
     int ceiling;
     int pos_bits;
+    int filter_len;            // V words examined per thread by the early-exit filter (0 = no filter)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -94,130 +104,139 @@ struct CompareParams {
 // ------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ uint4 ld_stream_v4(const uint32_t* p) {
-    // candidate row data is read exactly once per comparison: keep it out of L1 so that the
-    // query map / rank gathers own the L1.
+    // candidate row data is read once per comparison: do not let it displace anything in L1
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 
-__device__ __forceinline__ void ld_rank(const RankBlk* p, uint4& a, uint2& b) {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    a = __ldg(q);
-    b = __ldg(reinterpret_cast<const uint2*>(q + 1));
+__device__ __forceinline__ uint32_t lowmask(uint32_t k) { return (1u << k) - 1u; }    // k in 0..31
+
+// block-wide exclusive scan of one value per thread (blockDim.x <= 1024, multiple of 32); returns the
+// exclusive prefix, *total receives the block total.  `ws` = 33 words of shared scratch.
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* ws, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();                       // ws may still be read from a previous call
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t a = lane < nwarp ? ws[lane] : 0u, i2 = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, i2, o); if (lane >= o) i2 += t; }
+        ws[lane] = i2 - a;
+        if (lane == 31) ws[32] = i2;
+    }
+    __syncthreads();
+    *total = ws[32];
+    return ws[warp] + inc - v;
 }
 
-// number of set bits of m at bit positions < k   (k in 0..31)
-__device__ __forceinline__ uint32_t below(uint32_t m, uint32_t k) { return __popc(m & ((1u << k) - 1u)); }
-
 // ------------------------------------------------------------------------------------------
-// query build: scatter the query's row into the code map, then derive the rank structure
+// query build: ONE CTA turns the query's own row into {bmpref, entries} — no genome-sized pass
 // ------------------------------------------------------------------------------------------
 
-__global__ void k_scatter_query(const QuerySlot* __restrict__ slots, uint8_t* __restrict__ qmap,
-                                long long map_stride, int pos_bits) {
-    const QuerySlot& qs = slots[blockIdx.y];
-    const uint32_t* d = reinterpret_cast<const uint32_t*>(qs.hdr.data);
-    if (d == nullptr) return;
-    uint8_t* map = qmap + (long long)blockIdx.y * map_stride;
-    const uint32_t e0 = qs.hdr.end[0], e1 = qs.hdr.end[1], e2 = qs.hdr.end[2], e3 = qs.hdr.end[3],
-                   e4 = qs.hdr.end[4], e5 = qs.hdr.end[5];
+#define FN3_BUILD_THREADS 1024
+
+template <bool BM_SMEM>
+__global__ void __launch_bounds__(FN3_BUILD_THREADS) k_build_query(const QuerySlot* __restrict__ slots,
+                                                                    const QueryState qs, int pos_bits) {
+    extern __shared__ uint32_t dyn[];
+    __shared__ uint32_t ws[33];
+    const int slot = blockIdx.x;
+    const QuerySlot& q = slots[slot];
+    const int nw = qs.nw;
+    uint2* __restrict__ bmpref = qs.bmpref + (long long)slot * nw;
+    QEntry* __restrict__ ent = qs.ent + (long long)slot * qs.ent_stride;
+    uint32_t* bm = BM_SMEM ? dyn : qs.bm_scratch + (long long)slot * 2 * nw;      // touched-block bitmap
+    uint32_t* pf = bm + nw;                                                       // prefix per word
+    const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(q.hdr.data);
+    const uint32_t e0 = q.hdr.end[0], e1 = q.hdr.end[1], e2 = q.hdr.end[2], e3 = q.hdr.end[3],
+                   e4 = q.hdr.end[4], e5 = d ? q.hdr.end[5] : 0u;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < e5; i += gridDim.x * blockDim.x) {
-        uint32_t w = d[i];
+    const int tid = threadIdx.x;
+
+    for (int w = tid; w < nw; w += FN3_BUILD_THREADS) bm[w] = 0u;
+    __syncthreads();
+    // 1. which blocks does the query touch
+    for (uint32_t i = tid; i < e5; i += FN3_BUILD_THREADS) {
+        const uint32_t w = d[i];
         if (i < e3) {
-            uint8_t code = 1 + (i >= e0) + (i >= e1) + (i >= e2);
-            map[w] = code;
+            const uint32_t blk = w >> 5;
+            atomicOr(&bm[blk >> 5], 1u << (blk & 31u));
         } else {
-            uint8_t code = (i < e4) ? 5 : 6;
-            uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u);
-            for (uint32_t j = 0; j < len; ++j) map[s + j] = code;
+            const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u);
+            for (uint32_t blk = s >> 5; blk <= ((s + len - 1u) >> 5); ++blk) atomicOr(&bm[blk >> 5], 1u << (blk & 31u));
         }
     }
-}
-
-// pass A: 32 positions per thread -> masks + CTA-local exclusive counts; CTA totals to `partial`
-__global__ void __launch_bounds__(1024) k_rank_a(const uint8_t* __restrict__ qmap, RankBlk* __restrict__ qrank,
-                                                 uint3* __restrict__ partial, long long map_stride,
-                                                 long long rank_stride, long long n_blk, int ctas_per_slot) {
-    const int slot = blockIdx.y;
-    const uint8_t* map = qmap + (long long)slot * map_stride;
-    RankBlk* rank = qrank + (long long)slot * rank_stride;
-    const long long b = (long long)blockIdx.x * 1024 + threadIdx.x;
-    uint32_t mD = 0, mU = 0, mM = 0;
-    if (b < n_blk) {
-        const uint4* src = reinterpret_cast<const uint4*>(map + b * 32);
-        uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
-        uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t c = (w[k] >> (8 * j)) & 0xffu;
-                uint32_t bit = 1u << (k * 4 + j);
-                if (c - 1u < 4u) mD |= bit;
-                if (c >= 5u) mU |= bit;
-                if (c == 6u) mM |= bit;
+    __threadfence_block();
+    __syncthreads();
+    // 2. prefix of touched-block counts per word -> bmpref
+    const int chunk = (nw + FN3_BUILD_THREADS - 1) / FN3_BUILD_THREADS;
+    const int lo = min(nw, tid * chunk), hi = min(nw, lo + chunk);
+    uint32_t local = 0;
+    for (int w = lo; w < hi; ++w) local += __popc(bm[w]);
+    uint32_t nE;
+    uint32_t run = block_exscan(local, ws, &nE);
+    for (int w = lo; w < hi; ++w) { const uint32_t b = bm[w]; pf[w] = run; bmpref[w] = make_uint2(b, run); run += __popc(b); }
+    // 3. clear the entries (incl. the sentinel)
+    {
+        uint4* z = reinterpret_cast<uint4*>(ent);
+        for (uint32_t i = tid; i < 2u * (nE + 1u); i += FN3_BUILD_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __threadfence_block();
+    __syncthreads();
+    // 4. per-position masks
+    for (uint32_t i = tid; i < e5; i += FN3_BUILD_THREADS) {
+        const uint32_t w = d[i];
+        if (i < e3) {
+            const uint32_t blk = w >> 5, wi = blk >> 5, bit = blk & 31u;
+            QEntry* en = ent + (pf[wi] + __popc(bm[wi] & lowmask(bit)));
+            const uint32_t pb = 1u << (w & 31u);
+            const uint32_t base = (i >= e0) + (i >= e1) + (i >= e2);
+            atomicOr(&en->mDef, pb);
+            if (base & 1u) atomicOr(&en->mB0, pb);
+            if (base & 2u) atomicOr(&en->mB1, pb);
+        } else {
+            const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u), e = s + len;
+            for (uint32_t blk = s >> 5; blk <= ((e - 1u) >> 5); ++blk) {
+                const uint32_t b0 = blk << 5;
+                const uint32_t from = s > b0 ? s - b0 : 0u, to = min(e - b0, 32u);        // [from,to) inside the block
+                const uint32_t m = (to >= 32u ? 0xffffffffu : lowmask(to)) & ~lowmask(from);
+                const uint32_t wi = blk >> 5, bit = blk & 31u;
+                QEntry* en = ent + (pf[wi] + __popc(bm[wi] & lowmask(bit)));
+                atomicOr(&en->mU, m);
+                if (i >= e4) atomicOr(&en->mM, m);
             }
         }
     }
-    uint32_t cD = __popc(mD), cU = __popc(mU), cM = __popc(mM);
-    // inclusive warp scan
-    uint32_t sD = cD, sU = cU, sM = cM;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t tD = __shfl_up_sync(0xffffffffu, sD, o), tU = __shfl_up_sync(0xffffffffu, sU, o),
-                 tM = __shfl_up_sync(0xffffffffu, sM, o);
-        if (lane >= o) { sD += tD; sU += tU; sM += tM; }
-    }
-    __shared__ uint32_t wD[32], wU[32], wM[32];
-    if (lane == 31) { wD[warp] = sD; wU[warp] = sU; wM[warp] = sM; }
+    __threadfence_block();
     __syncthreads();
-    if (warp == 0) {
-        uint32_t aD = wD[lane], aU = wU[lane], aM = wM[lane];
-        uint32_t iD = aD, iU = aU, iM = aM;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t tD = __shfl_up_sync(0xffffffffu, iD, o), tU = __shfl_up_sync(0xffffffffu, iU, o),
-                     tM = __shfl_up_sync(0xffffffffu, iM, o);
-            if (lane >= o) { iD += tD; iU += tU; iM += tM; }
-        }
-        wD[lane] = iD - aD; wU[lane] = iU - aU; wM[lane] = iM - aM;   // exclusive warp offsets
-        if (lane == 31) partial[slot * ctas_per_slot + blockIdx.x] = make_uint3(iD, iU, iM);
+    // 5. running counts over the entries; the sentinel entry nE receives the totals
+    const uint32_t echunk = (nE + FN3_BUILD_THREADS - 1) / FN3_BUILD_THREADS;
+    const uint32_t elo = min(nE, tid * echunk), ehi = min(nE, elo + echunk);
+    uint32_t sD = 0, sU = 0, sM = 0;
+    for (uint32_t i = elo; i < ehi; ++i) {
+        sD += __popc(__ldcg(&ent[i].mDef)); sU += __popc(__ldcg(&ent[i].mU)); sM += __popc(__ldcg(&ent[i].mM));
     }
-    __syncthreads();
-    if (b < n_blk) {
-        uint4 a = make_uint4(mD, mU, mM, wD[warp] + sD - cD);
-        uint4 c = make_uint4(wU[warp] + sU - cU, wM[warp] + sM - cM, 0u, 0u);
-        uint4* dst = reinterpret_cast<uint4*>(rank + b);
-        dst[0] = a; dst[1] = c;
+    uint32_t tD, tU, tM;
+    uint32_t rD = block_exscan(sD, ws, &tD), rU = block_exscan(sU, ws, &tU), rM = block_exscan(sM, ws, &tM);
+    for (uint32_t i = elo; i < ehi; ++i) {
+        const uint32_t a = __popc(__ldcg(&ent[i].mDef)), b = __popc(__ldcg(&ent[i].mU)), c = __popc(__ldcg(&ent[i].mM));
+        ent[i].cDef = rD; ent[i].cU = rU; ent[i].cM = rM;
+        rD += a; rU += b; rM += c;
     }
-}
-
-// pass B: add the sum of all preceding CTAs' totals
-__global__ void __launch_bounds__(1024) k_rank_b(RankBlk* __restrict__ qrank, const uint3* __restrict__ partial,
-                                                 long long rank_stride, long long n_blk, int ctas_per_slot) {
-    const int slot = blockIdx.y;
-    if (blockIdx.x == 0) return;
-    RankBlk* rank = qrank + (long long)slot * rank_stride;
-    const uint3* part = partial + slot * ctas_per_slot;
-    uint32_t aD = 0, aU = 0, aM = 0;
-    for (int i = threadIdx.x; i < (int)blockIdx.x; i += 1024) { uint3 p = part[i]; aD += p.x; aU += p.y; aM += p.z; }
-    __shared__ uint32_t sD[32], sU[32], sM[32];
-    aD = __reduce_add_sync(0xffffffffu, aD); aU = __reduce_add_sync(0xffffffffu, aU); aM = __reduce_add_sync(0xffffffffu, aM);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sD[warp] = aD; sU[warp] = aU; sM[warp] = aM; }
-    __syncthreads();
-    uint32_t tD = __reduce_add_sync(0xffffffffu, sD[lane]), tU = __reduce_add_sync(0xffffffffu, sU[lane]),
-             tM = __reduce_add_sync(0xffffffffu, sM[lane]);
-    const long long b = (long long)blockIdx.x * 1024 + threadIdx.x;
-    if (b < n_blk) { rank[b].cDef += tD; rank[b].cU += tU; rank[b].cM += tM; }
+    if (tid == 0) {
+        ent[nE].cDef = tD; ent[nE].cU = tU; ent[nE].cM = tM;
+        qs.info[slot] = make_uint4(nE, tD, tU, tM);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
-// the compare kernel: one warp per (query slot, candidate row)
+// the compare kernel
 // ------------------------------------------------------------------------------------------
 //
 // Streaming identity (SURVEY.md §8 "Spec"), with V = definite non-reference positions,
@@ -226,88 +245,184 @@ __global__ void __launch_bounds__(1024) k_rank_b(RankBlk* __restrict__ qrank, co
 //   dist  = S1 + |V_q| - |V_c n V_q| - |U_c n V_q|
 //   n1    = |U_q|,  n2 = |N_c| + |M_q| - |N_c n M_q|,  nboth = n1 + |N_c| - |N_c n U_q|
 // S1 alone is a lower bound of dist, so a pair leaves as soon as S1 > ceiling.
+//
+// Each CTA first stages the query's compact structure in shared memory (QSMEM) — every later
+// lookup is an LDS, never an L2 gather.  Work unit = a group of 32 candidates per warp:
+//   phase A (one THREAD per candidate): header + the first `filter_len` V words; a candidate
+//            whose first words already give S1 > ceiling is done (this is ~all unrelated pairs);
+//   phase B (one WARP per surviving candidate): coalesced 128-bit streaming of the whole row,
+//            warp-reduced tallies, survivors compacted into the neighbour buffer.
+// Lane l of group g takes candidate g + l*G (G = number of groups) so that consecutive rows
+// — relatives are inserted together — land in different warps.
 
-template <bool COUNT>
-__global__ void __launch_bounds__(256) k_compare(const CompareParams p) {
+struct QView {                  // where the staged query lives (shared or global)
+    const uint2* bmpref;
+    const uint4* ent;           // two uint4 per entry
+};
+
+// V element: returns mismatch flag (bit0) | query-is-Def flag (bit1)
+__device__ __forceinline__ uint32_t look_v(const QView& qv, uint32_t p, uint32_t b) {
+    const uint32_t blk = p >> 5;
+    const uint2 bp = qv.bmpref[blk >> 5];
+    const uint32_t bit = blk & 31u;
+    if (!((bp.x >> bit) & 1u)) return 1u;                       // query is reference all over this block
+    const uint4 a = qv.ent[2u * (bp.y + __popc(bp.x & lowmask(bit)))];
+    const uint32_t k = p & 31u;
+    const uint32_t D = (a.x >> k) & 1u, U = (a.y >> k) & 1u;
+    const uint32_t qb = ((a.z >> k) & 1u) | (((a.w >> k) & 1u) << 1);
+    const uint32_t mism = (U ^ 1u) & ((D ^ 1u) | (uint32_t)(qb != b));
+    return mism | (D << 1);
+}
+
+// number of query positions of each kind strictly below x (Def, U, M)
+__device__ __forceinline__ void rank3(const QView& qv, uint32_t x, uint32_t& rD, uint32_t& rU, uint32_t& rM, bool want_um) {
+    const uint32_t blk = x >> 5;
+    const uint2 bp = qv.bmpref[blk >> 5];
+    const uint32_t bit = blk & 31u;
+    const uint32_t idx = bp.y + __popc(bp.x & lowmask(bit));
+    const bool touched = (bp.x >> bit) & 1u;
+    const uint4 b = qv.ent[2u * idx + 1u];                      // {mM, cDef, cU, cM}
+    rD = b.y; rU = b.z; rM = b.w;
+    if (touched) {
+        const uint4 a = qv.ent[2u * idx];                       // {mDef, mU, mB0, mB1}
+        const uint32_t lm = lowmask(x & 31u);
+        rD += __popc(a.x & lm);
+        if (want_um) { rU += __popc(a.y & lm); rM += __popc(b.x & lm); }
+    }
+}
+
+#define FN3_CMP_BLOCK 256
+
+template <bool COUNT, bool QSMEM>
+__global__ void __launch_bounds__(FN3_CMP_BLOCK) k_compare(const CompareParams p) {
+    extern __shared__ uint4 qsm[];
     const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const int slot = blockIdx.y;
     const QuerySlot qs = p.slots[slot];
     if (qs.hdr.data == 0ull) return;                       // invalid query: no distances at all
-    const uint8_t* __restrict__ qmap = p.qmap + (long long)slot * p.map_stride;
-    const RankBlk* __restrict__ qrank = p.qrank + (long long)slot * p.rank_stride;
-    const uint32_t nVq = qrank[p.rank_last].cDef, nUq = qrank[p.rank_last].cU, nMq = qrank[p.rank_last].cM;
+    const int nw = p.qs.nw;
+    const uint4 info = p.qs.info[slot];
+    const uint32_t nE = info.x, nVq = info.y, nUq = info.z, nMq = info.w;
+    QView qv;
+    {
+        const uint2* g_bp = p.qs.bmpref + (long long)slot * nw;
+        const uint4* g_en = reinterpret_cast<const uint4*>(p.qs.ent + (long long)slot * p.qs.ent_stride);
+        if (QSMEM) {
+            // stage: [bmpref (nw x 8 B, padded to 16) | entries ((nE+1) x 32 B)]
+            const int n_bp4 = (nw + 1) / 2;
+            const uint4* src = reinterpret_cast<const uint4*>(g_bp);
+            for (int i = threadIdx.x; i < n_bp4; i += blockDim.x) qsm[i] = __ldg(src + i);
+            const int n_en4 = 2 * ((int)nE + 1);
+            for (int i = threadIdx.x; i < n_en4; i += blockDim.x) qsm[n_bp4 + i] = __ldg(g_en + i);
+            __syncthreads();
+            qv.bmpref = reinterpret_cast<const uint2*>(qsm);
+            qv.ent = qsm + n_bp4;
+        } else {
+            qv.bmpref = g_bp;
+            qv.ent = g_en;
+        }
+    }
     const int k = p.ceiling;
     const int pos_bits = p.pos_bits;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
     const long long hmask = (1ll << p.hdr.shift) - 1;
+    const long long G = (p.n + 31) >> 5;                   // candidate groups
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     unsigned long long touched = 0;
 
-    for (long long i = warp0; i < p.n; i += nwarps) {
-        const long long row = p.rows ? p.rows[i] : p.row_begin + i;
-        if (row == qs.exclude || row <= qs.skip_le) continue;
-        const uint4* hp = reinterpret_cast<const uint4*>(p.hdr.chunk[row >> p.hdr.shift] + (row & hmask));
-        const uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
-        if (COUNT) touched += 32;
-        const unsigned long long daddr = ((unsigned long long)h0.y << 32) | h0.x;
-        if (daddr == 0ull) continue;                       // invalid or removed candidate
-        const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(daddr);
-        const uint32_t e0 = h0.z, e1 = h0.w, e2 = h1.x, e3 = h1.y, e4 = h1.z, e5 = h1.w;
-
-        int S1 = 0;                                        // warp-uniform running mismatch count
-        int qdefV = 0, qdefU = 0, nNc = 0, nNU = 0, nNM = 0;   // per-lane partials
-        bool dead = false;
-        for (uint32_t base = 0; base < e5; base += 128) {
-            const uint32_t idx = base + lane * 4;
-            uint4 w4 = make_uint4(0, 0, 0, 0);
-            if (idx < e5) { w4 = ld_stream_v4(d + idx); if (COUNT) touched += 16; }
-            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-            int mism = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t ii = idx + j;
-                if (ii < e3) {
-                    const uint32_t b = 1u + (ii >= e0) + (ii >= e1) + (ii >= e2);
-                    const uint32_t q = __ldg(qmap + w[j]);
-                    mism += (q < 5u) & (q != b);
-                    qdefV += (q - 1u < 4u);
-                } else if (ii < e5) {
-                    const uint32_t s = w[j] & pmask;
-                    const uint32_t len = (pos_bits >= 32) ? 1u : ((w[j] >> pos_bits) + 1u);
-                    const uint32_t e = s + len;
-                    uint4 a0, a1; uint2 b0, b1;
-                    ld_rank(qrank + (s >> 5), a0, b0);
-                    ld_rank(qrank + (e >> 5), a1, b1);
-                    const uint32_t ks = s & 31u, ke = e & 31u;
-                    qdefU += (int)(a1.w + below(a1.x, ke)) - (int)(a0.w + below(a0.x, ks));
-                    if (ii < e4) {                          // an N run of the candidate
-                        nNc += (int)len;
-                        nNU += (int)(b1.x + below(a1.y, ke)) - (int)(b0.x + below(a0.y, ks));
-                        nNM += (int)(b1.y + below(a1.z, ke)) - (int)(b0.y + below(a0.z, ks));
-                    }
-                }
-            }
-            if (base < e3) {                                // warp-uniform: this step touched V words
-                S1 += __reduce_add_sync(0xffffffffu, mism);
-                if (S1 > k) { dead = true; break; }
+    for (long long g = warp0; g < G; g += nwarps) {
+        // ---- phase A: one thread per candidate -------------------------------------------
+        const long long ci = g + (long long)lane * G;
+        long long row = -1;
+        uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+        bool pass = false;
+        if (ci < p.n) {
+            row = p.rows ? p.rows[ci] : p.row_begin + ci;
+            if (row != qs.exclude && row > qs.skip_le) {
+                const uint4* hp = reinterpret_cast<const uint4*>(p.hdr.chunk[row >> p.hdr.shift] + (row & hmask));
+                h0 = __ldg(hp); h1 = __ldg(hp + 1);
+                if (COUNT) touched += 32;
+                pass = (h0.x | h0.y) != 0u;                // data pointer 0: invalid or removed candidate
             }
         }
-        if (dead) continue;
-        qdefV = __reduce_add_sync(0xffffffffu, qdefV);
-        qdefU = __reduce_add_sync(0xffffffffu, qdefU);
-        const int dist = S1 + (int)nVq - qdefV - qdefU;
-        if (dist > k) continue;
-        nNc = __reduce_add_sync(0xffffffffu, nNc);
-        nNU = __reduce_add_sync(0xffffffffu, nNU);
-        nNM = __reduce_add_sync(0xffffffffu, nNM);
-        if (lane == 0) {
-            const unsigned long long at = atomicAdd(p.out_count, 1ull);
-            if ((long long)at < p.out_cap) {
-                EdgeRec r;
-                r.row1 = qs.row; r.row2 = row; r.dist = dist;
-                r.n1 = (int)nUq; r.n2 = nNc + (int)nMq - nNM; r.nboth = (int)nUq + nNc - nNU;
-                p.out[at] = r;
+        if (pass && p.filter_len > 0) {
+            const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
+            const uint32_t e0 = h0.z, e1 = h0.w, e2 = h1.x, e3 = h1.y;
+            const uint32_t lim = min(e3, (uint32_t)p.filter_len);
+            int S = 0;
+            for (uint32_t i = 0; i < lim && S <= k; i += 4) {
+                const uint4 w4 = ld_stream_v4(d + i);
+                if (COUNT) touched += 16;
+                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t ii = i + j;
+                    if (ii < lim) S += look_v(qv, w[j], (ii >= e0) + (ii >= e1) + (ii >= e2)) & 1u;
+                }
+            }
+            pass = S <= k;
+        }
+        // ---- phase B: one warp per surviving candidate -----------------------------------
+        uint32_t alive = __ballot_sync(0xffffffffu, pass);
+        while (alive) {
+            const int src = __ffs(alive) - 1;
+            alive &= alive - 1u;
+            const uint32_t dlo = __shfl_sync(0xffffffffu, h0.x, src), dhi = __shfl_sync(0xffffffffu, h0.y, src);
+            const uint32_t e0 = __shfl_sync(0xffffffffu, h0.z, src), e1 = __shfl_sync(0xffffffffu, h0.w, src);
+            const uint32_t e2 = __shfl_sync(0xffffffffu, h1.x, src), e3 = __shfl_sync(0xffffffffu, h1.y, src);
+            const uint32_t e4 = __shfl_sync(0xffffffffu, h1.z, src), e5 = __shfl_sync(0xffffffffu, h1.w, src);
+            const long long crow = __shfl_sync(0xffffffffu, row, src);
+            const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(((unsigned long long)dhi << 32) | dlo);
+
+            int S1 = 0;                                    // warp-uniform running mismatch count
+            int qdefV = 0, qdefU = 0, nNc = 0, nNU = 0, nNM = 0;   // per-lane partials
+            bool dead = false;
+            for (uint32_t base = 0; base < e5; base += 128) {
+                const uint32_t idx = base + lane * 4;
+                uint4 w4 = make_uint4(0, 0, 0, 0);
+                if (idx < e5) { w4 = ld_stream_v4(d + idx); if (COUNT) touched += 16; }
+                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+                int mism = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t ii = idx + j;
+                    if (ii < e3) {
+                        const uint32_t r = look_v(qv, w[j], (ii >= e0) + (ii >= e1) + (ii >= e2));
+                        mism += r & 1u;
+                        qdefV += r >> 1;
+                    } else if (ii < e5) {
+                        const uint32_t s = w[j] & pmask;
+                        const uint32_t len = (pos_bits >= 32) ? 1u : ((w[j] >> pos_bits) + 1u);
+                        const bool isN = ii < e4;
+                        uint32_t aD, aU, aM, bD, bU, bM;
+                        rank3(qv, s, aD, aU, aM, isN);
+                        rank3(qv, s + len, bD, bU, bM, isN);
+                        qdefU += (int)(bD - aD);
+                        if (isN) { nNc += (int)len; nNU += (int)(bU - aU); nNM += (int)(bM - aM); }
+                    }
+                }
+                if (base < e3) {                            // warp-uniform: this step touched V words
+                    S1 += __reduce_add_sync(0xffffffffu, mism);
+                    if (S1 > k) { dead = true; break; }
+                }
+            }
+            if (dead) continue;
+            qdefV = __reduce_add_sync(0xffffffffu, qdefV);
+            qdefU = __reduce_add_sync(0xffffffffu, qdefU);
+            const int dist = S1 + (int)nVq - qdefV - qdefU;
+            if (dist > k) continue;
+            nNc = __reduce_add_sync(0xffffffffu, nNc);
+            nNU = __reduce_add_sync(0xffffffffu, nNU);
+            nNM = __reduce_add_sync(0xffffffffu, nNM);
+            if (lane == 0) {
+                const unsigned long long at = atomicAdd(p.out_count, 1ull);
+                if ((long long)at < p.out_cap) {
+                    EdgeRec r;
+                    r.row1 = qs.row; r.row2 = crow; r.dist = dist;
+                    r.n1 = (int)nUq; r.n2 = nNc + (int)nMq - nNM; r.nboth = (int)nUq + nNc - nNU;
+                    p.out[at] = r;
+                }
             }
         }
     }
@@ -317,7 +432,6 @@ __global__ void __launch_bounds__(256) k_compare(const CompareParams p) {
         if (lane == 0) atomicAdd(p.touched, touched);
     }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // ingest: compress() on the device (seqComparer.py:274-307)
@@ -467,6 +581,7 @@ struct fn3_engine {
     std::vector<RowHdr> h_hdr;              // host mirror (published rows)
     std::vector<uint8_t> h_flags;           // bit0 invalid, bit1 removed
     std::vector<uint32_t> h_npos;           // canonical position count per row
+    std::vector<uint32_t> h_nblk;           // number of 32-position blocks the row touches (sizes query staging)
     long long n_rows = 0;                   // published
     long long n_live = 0, n_invalid = 0;
     long long store_words = 0, store_bytes = 0, positions = 0;
@@ -477,8 +592,10 @@ struct fn3_engine {
 
     // query state
     int n_slots = 8;
-    long long map_stride = 0, rank_stride = 0, n_blk = 0; int rank_ctas = 0;
-    uint8_t* qmap = nullptr; RankBlk* qrank = nullptr; uint3* partial = nullptr;
+    QueryState qstate;                     // device arrays of the compact queries (n_slots of them)
+    int max_smem = 0;                      // opt-in dynamic shared memory per CTA
+    int stage_limit = 0;                   // = max_smem, or 0 to force the global-memory query variants
+    uint32_t slot_blocks[FN3_MAX_SLOTS];   // touched-block count of the query in each slot (sizes the staging)
     QuerySlot* d_slots = nullptr; QuerySlot* h_slots = nullptr;   // h_slots pinned
     // survivor buffer: one allocation = [32-byte counter block | records], mirrored in pinned host memory so
     // that the counter and the first records come back in ONE device-to-host copy
@@ -647,14 +764,24 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
     for (int i = 0; i < 4; ++i)
         if ((s = cudaEventCreate(&e->ev[i])) != cudaSuccess) return fail("cudaEventCreate", s);
 
-    // query state: map padded so that rank block n_blk-1 (the totals entry) reads zeros
-    e->n_blk = (genome_length + 31) / 32 + 1;
-    e->map_stride = ((e->n_blk * 32 + 255) / 256) * 256;
-    e->rank_stride = e->n_blk;
-    e->rank_ctas = (int)((e->n_blk + 1023) / 1024);
-    if ((s = cudaMalloc(&e->qmap, (size_t)e->map_stride * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(qmap)", s);
-    if ((s = cudaMalloc(&e->qrank, (size_t)e->rank_stride * sizeof(RankBlk) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(qrank)", s);
-    if ((s = cudaMalloc(&e->partial, (size_t)e->rank_ctas * e->n_slots * sizeof(uint3))) != cudaSuccess) return fail("cudaMalloc(partial)", s);
+    // query state (compact form); the last block is the end sentinel for rank(L)
+    {
+        QueryState& q = e->qstate;
+        memset(&q, 0, sizeof q);
+        q.n_blk = (int)((genome_length + 31) / 32 + 1);
+        q.nw = (q.n_blk + 31) / 32;
+        q.nw = (q.nw + 1) & ~1;                                  // even: 16-byte staging copies
+        q.ent_stride = (long long)q.n_blk + 1;
+        if ((s = cudaMalloc(&q.bmpref, (size_t)q.nw * sizeof(uint2) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(bmpref)", s);
+        if ((s = cudaMalloc(&q.ent, (size_t)q.ent_stride * sizeof(QEntry) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(entries)", s);
+        if ((s = cudaMalloc(&q.info, sizeof(uint4) * FN3_MAX_SLOTS)) != cudaSuccess) return fail("cudaMalloc(info)", s);
+        if ((s = cudaMalloc(&q.bm_scratch, (size_t)q.nw * 2 * sizeof(uint32_t) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(bm)", s);
+        e->max_smem = (int)prop.sharedMemPerBlockOptin;
+        e->stage_limit = env_ll("FN3_FORCE_GLOBAL_QUERY", 0) ? 0 : e->max_smem;   // tests: exercise the non-staged variants
+        cudaFuncSetAttribute(k_compare<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
+        cudaFuncSetAttribute(k_compare<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
+        cudaFuncSetAttribute(k_build_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
+    }
     if ((s = cudaMalloc(&e->d_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS)) != cudaSuccess) return fail("cudaMalloc(slots)", s);
     if ((s = cudaHostAlloc(&e->h_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(slots)", s);
     if (ensure_out(e, 4096) != FN3_OK || ensure_hout(e, 4096) != FN3_OK) {
@@ -663,7 +790,6 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         return nullptr;
     }
     if ((s = cudaMalloc(&e->d_scratch_hdr, 2 * sizeof(RowHdr))) != cudaSuccess) return fail("cudaMalloc(scratch hdr)", s);
-    if ((s = cudaMemset(e->qmap, 0, (size_t)e->map_stride * e->n_slots)) != cudaSuccess) return fail("cudaMemset", s);
     e->store_bytes = 0;
     return e;
 }
@@ -675,7 +801,8 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     for (auto p : e->data_chunks) cudaFree(p);
     for (auto p : e->hdr_chunks) cudaFree(p);
-    cudaFree(e->qmap); cudaFree(e->qrank); cudaFree(e->partial); cudaFree(e->d_slots);
+    cudaFree(e->qstate.bmpref); cudaFree(e->qstate.ent); cudaFree(e->qstate.info); cudaFree(e->qstate.bm_scratch);
+    cudaFree(e->d_slots);
     cudaFree(e->d_outbuf); cudaFree(e->d_rows); cudaFree(e->d_scratch);
     cudaFree(e->d_scratch_hdr); cudaFree(e->d_flush);
     cudaFree(e->d_refmask); cudaFree(e->d_seq); cudaFree(e->d_mchars); cudaFree(e->d_cpos);
@@ -700,8 +827,12 @@ extern "C" int fn3_destroy(fn3_engine* e) {
 // ---- packing: six plain lists -> row words ------------------------------------------------
 
 // validates one sample; returns number of row words (0 for invalid), or -1 with error set
-static long long row_words_needed(fn3_engine* e, const int32_t* pos, const long long off[7], int invalid) {
+// *nblk receives an upper bound of the number of distinct 32-position blocks the sample touches
+static long long row_words_needed(fn3_engine* e, const int32_t* pos, const long long off[7], int invalid,
+                                  uint32_t* nblk = nullptr) {
+    if (nblk) *nblk = 0;
     if (invalid) return 0;
+    long long blocks = 0;
     for (int b = 0; b < 6; ++b)
         if (off[b + 1] < off[b]) { set_err(e, FN3_EARG, "list offsets must be non-decreasing"); return -1; }
     long long words = off[4] - off[0];
@@ -716,6 +847,7 @@ static long long row_words_needed(fn3_engine* e, const int32_t* pos, const long 
             if (i && p[i] <= p[i - 1]) {
                 set_err(e, FN3_EARG, "positions must be strictly increasing within a list"); return -1;
             }
+            if (!i || (p[i] >> 5) != (p[i - 1] >> 5)) ++blocks;
             if (b >= 4) {
                 if (i && p[i] == p[i - 1] + 1 && run_len < (long long)e->max_run) ++run_len;
                 else { ++runs; run_len = 1; }
@@ -724,6 +856,7 @@ static long long row_words_needed(fn3_engine* e, const int32_t* pos, const long 
         if (b >= 4) words += runs;
     }
     if (words >= (1ll << 31)) { set_err(e, FN3_EARG, "sample too large"); return -1; }
+    if (nblk) *nblk = (uint32_t)blocks;
     return words;
 }
 
@@ -792,10 +925,11 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
     CU(e, cudaSetDevice(e->device));
     // pass 1: validate + size
     std::vector<long long> words((size_t)n);
+    std::vector<uint32_t> nblks((size_t)n);
     for (long long i = 0; i < n; ++i) {
         long long o[7];
         for (int b = 0; b < 7; ++b) o[b] = off6[6 * i + b];
-        long long w = row_words_needed(e, pos, o, invalid ? invalid[i] : 0);
+        long long w = row_words_needed(e, pos, o, invalid ? invalid[i] : 0, &nblks[(size_t)i]);
         if (w < 0) return FN3_EARG;
         words[(size_t)i] = w;
     }
@@ -856,6 +990,7 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
             e->h_flags.push_back(inv ? 1 : 0);
             const uint32_t np = inv ? 0u : (uint32_t)(off6[6 * r2 + 6] - off6[6 * r2]);
             e->h_npos.push_back(np);
+            e->h_nblk.push_back(nblks[(size_t)r2]);
             e->positions += np;
             e->n_live++; if (inv) e->n_invalid++;
         }
@@ -959,7 +1094,7 @@ static void fill_hdr_table(fn3_engine* e, HdrTable& t) {   // store_mu held
     t.shift = e->hdr_shift;
 }
 
-// enqueue: slots upload + map clear + scatter + rank build for `ns` slots (h_slots filled by caller)
+// enqueue: slots upload + ONE build kernel for `ns` slots (h_slots + slot_blocks filled by the caller)
 // (`resident` != nullptr: the slots are already on the device — measurement hook)
 static int enqueue_query_build(fn3_engine* e, int ns, const QuerySlot* resident = nullptr) {
     cudaStream_t st = e->q_stream;
@@ -968,47 +1103,66 @@ static int enqueue_query_build(fn3_engine* e, int ns, const QuerySlot* resident 
         CU(e, cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(QuerySlot) * ns, cudaMemcpyHostToDevice, st));
         e->h2d_bytes += (long long)sizeof(QuerySlot) * ns;
     }
-    CU(e, cudaMemsetAsync(e->qmap, 0, (size_t)e->map_stride * ns, st));
-    uint32_t maxw = 1;
-    for (int s = 0; s < ns; ++s) maxw = std::max(maxw, e->h_slots[s].hdr.end[5]);
-    dim3 gs((unsigned)std::min<uint32_t>((maxw + 255) / 256, 1024u), (unsigned)ns);
-    k_scatter_query<<<gs, 256, 0, st>>>(d_slots, e->qmap, e->map_stride, e->pos_bits);
-    dim3 gr((unsigned)e->rank_ctas, (unsigned)ns);
-    k_rank_a<<<gr, 1024, 0, st>>>(e->qmap, e->qrank, e->partial, e->map_stride, e->rank_stride, e->n_blk, e->rank_ctas);
-    k_rank_b<<<gr, 1024, 0, st>>>(e->qrank, e->partial, e->rank_stride, e->n_blk, e->rank_ctas);
-    e->launches += 3;
+    const size_t bm_bytes = (size_t)e->qstate.nw * 2 * sizeof(uint32_t);
+    if (bm_bytes + 1024 <= (size_t)e->stage_limit)
+        k_build_query<true><<<ns, FN3_BUILD_THREADS, bm_bytes, st>>>(d_slots, e->qstate, e->pos_bits);
+    else
+        k_build_query<false><<<ns, FN3_BUILD_THREADS, 0, st>>>(d_slots, e->qstate, e->pos_bits);
+    e->launches += 1;
     CU(e, cudaGetLastError());
     return FN3_OK;
+}
+
+// the early-exit filter looks at this many leading V words per candidate (0 = filter off)
+static int filter_len_for(int ceiling) {
+    if (ceiling < 0) return 4;
+    if (ceiling >= 56) return 0;                 // the filter cannot reject cheaply: stream every row in phase B
+    return ((ceiling + 1 + 7 + 3) / 4) * 4;
 }
 
 static int enqueue_compare(fn3_engine* e, const HdrTable& ht, const long long* d_rows, long long row_begin, long long n,
                            int ns, int ceiling, bool count_bytes, const QuerySlot* resident = nullptr) {
     if (n <= 0) return FN3_OK;
     CompareParams p;
-    p.hdr = ht; p.rows = d_rows; p.row_begin = row_begin; p.n = n;
-    p.qmap = e->qmap; p.qrank = e->qrank; p.slots = resident ? resident : e->d_slots;
-    p.map_stride = e->map_stride; p.rank_stride = e->rank_stride; p.rank_last = e->n_blk - 1;
+    p.hdr = ht; p.qs = e->qstate; p.rows = d_rows; p.row_begin = row_begin; p.n = n;
+    p.slots = resident ? resident : e->d_slots;
     p.out = e->d_out; p.out_count = e->d_count; p.touched = e->d_count + 1; p.out_cap = e->out_cap;
-    p.ceiling = ceiling; p.pos_bits = e->pos_bits;
-    const long long warps_per_cta = 8;
-    long long ctas = (n + warps_per_cta - 1) / warps_per_cta;
-    const long long max_ctas = (long long)e->sm_count * 8;
+    p.ceiling = ceiling; p.pos_bits = e->pos_bits; p.filter_len = filter_len_for(ceiling);
+    // shared-memory staging of the query: bmpref + (touched blocks + 1) entries, sized for the largest slot
+    uint32_t blocks = 0;
+    for (int s = 0; s < ns; ++s) blocks = std::max(blocks, e->slot_blocks[s]);
+    blocks = std::min<uint32_t>(blocks, (uint32_t)e->qstate.n_blk);
+    const size_t smem = (size_t)e->qstate.nw * sizeof(uint2) + ((size_t)blocks + 1) * sizeof(QEntry);
+    const bool in_smem = smem + 1024 <= (size_t)e->stage_limit;
+    const long long groups = (n + 31) / 32;
+    const long long warps_per_cta = FN3_CMP_BLOCK / 32;
+    long long ctas = (groups + warps_per_cta - 1) / warps_per_cta;
+    long long per_sm = 4;                                         // 64 registers x 256 threads
+    if (in_smem) per_sm = std::max<long long>(1, std::min<long long>(per_sm, (long long)(228 * 1024) / (long long)(smem + 1024)));
+    const long long max_ctas = (long long)e->sm_count * per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
     dim3 g((unsigned)ctas, (unsigned)ns);
-    if (count_bytes) k_compare<true><<<g, 256, 0, e->q_stream>>>(p);
-    else k_compare<false><<<g, 256, 0, e->q_stream>>>(p);
+    if (in_smem) {
+        if (count_bytes) k_compare<true, true><<<g, FN3_CMP_BLOCK, smem, e->q_stream>>>(p);
+        else k_compare<false, true><<<g, FN3_CMP_BLOCK, smem, e->q_stream>>>(p);
+    } else {
+        if (count_bytes) k_compare<true, false><<<g, FN3_CMP_BLOCK, 0, e->q_stream>>>(p);
+        else k_compare<false, false><<<g, FN3_CMP_BLOCK, 0, e->q_stream>>>(p);
+    }
     e->launches += 1;
     CU(e, cudaGetLastError());
     return FN3_OK;
 }
 
 // upload a non-stored sample into scratch slot `which` (0/1); returns its header
-static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const int32_t off[7], int invalid, RowHdr* out) {
+static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const int32_t off[7], int invalid, RowHdr* out,
+                          uint32_t* nblk = nullptr) {
     RowHdr h; memset(&h, 0, sizeof h);
+    if (nblk) *nblk = 0;
     if (invalid) { *out = h; return FN3_OK; }
     long long o[7];
     for (int b = 0; b < 7; ++b) o[b] = off[b];
-    long long w = row_words_needed(e, pos, o, 0);
+    long long w = row_words_needed(e, pos, o, 0, nblk);
     if (w < 0) return FN3_EARG;
     size_t need = ((size_t)w + 3) & ~(size_t)3; if (need == 0) need = 4;
     // scratch holds two samples: [0, half) and [half, 2*half)
@@ -1089,11 +1243,12 @@ static int snapshot_store(fn3_engine* e, HdrTable& ht, long long& n_store) {
     return FN3_OK;
 }
 
-static int stored_hdr(fn3_engine* e, long long row, RowHdr* h, const char* who) {
+static int stored_hdr(fn3_engine* e, long long row, RowHdr* h, const char* who, uint32_t* nblk = nullptr) {
     std::lock_guard<std::mutex> g(e->store_mu);
     if (row < 0 || row >= e->n_rows) return set_err(e, FN3_ENOTFOUND, "%s: row %lld does not exist", who, row);
     if (e->h_flags[(size_t)row] & 2) return set_err(e, FN3_ENOTFOUND, "%s: row %lld was removed", who, row);
     *h = e->h_hdr[(size_t)row];
+    if (nblk) *nblk = e->h_nblk[(size_t)row];
     return FN3_OK;
 }
 
@@ -1103,7 +1258,7 @@ extern "C" int fn3_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling,
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
     RowHdr qh; int rc;
-    if ((rc = stored_hdr(e, query_row, &qh, "fn3_one_vs_all"))) return rc;
+    if ((rc = stored_hdr(e, query_row, &qh, "fn3_one_vs_all", &e->slot_blocks[0]))) return rc;
     HdrTable ht; long long n_store;
     snapshot_store(e, ht, n_store);
     QuerySlot& s = e->h_slots[0];
@@ -1117,7 +1272,7 @@ extern "C" int fn3_lists_vs_all(fn3_engine* e, const int32_t* pos, const int32_t
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
     RowHdr qh; int rc;
-    if ((rc = upload_scratch(e, 0, pos, off, invalid, &qh))) return rc;
+    if ((rc = upload_scratch(e, 0, pos, off, invalid, &qh, &e->slot_blocks[0]))) return rc;
     HdrTable ht; long long n_store;
     snapshot_store(e, ht, n_store);
     QuerySlot& s = e->h_slots[0];
@@ -1130,7 +1285,7 @@ extern "C" int fn3_pair(fn3_engine* e, int64_t row1, int64_t row2, int32_t ceili
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
     RowHdr qh, ch; int rc;
-    if ((rc = stored_hdr(e, row1, &qh, "fn3_pair"))) return rc;
+    if ((rc = stored_hdr(e, row1, &qh, "fn3_pair", &e->slot_blocks[0]))) return rc;
     if ((rc = stored_hdr(e, row2, &ch, "fn3_pair"))) return rc;
     HdrTable ht; long long n_store;
     snapshot_store(e, ht, n_store);
@@ -1150,7 +1305,7 @@ extern "C" int fn3_pair_lists(fn3_engine* e, const int32_t* pos1, const int32_t 
     CU(e, cudaSetDevice(e->device));
     *has_dist = 0;
     RowHdr qh, ch; int rc;
-    if ((rc = upload_scratch(e, 0, pos1, off1, invalid1, &qh))) return rc;
+    if ((rc = upload_scratch(e, 0, pos1, off1, invalid1, &qh, &e->slot_blocks[0]))) return rc;
     if ((rc = upload_scratch(e, 1, pos2, off2, invalid2, &ch))) return rc;
     if (qh.data == 0ull || ch.data == 0ull) return FN3_OK;   // either invalid: None (:438-442)
     // scratch header table: one chunk holding the candidate header at row 0
@@ -1195,6 +1350,7 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
                 const long long r = qrows[t0 + s];
                 QuerySlot& qs = e->h_slots[s];
                 qs.hdr = e->h_hdr[(size_t)r]; qs.row = r; qs.exclude = r; qs.skip_le = upper_only ? r : -1; qs.pad = 0;
+                e->slot_blocks[s] = e->h_nblk[(size_t)r];
                 min_row = std::min(min_row, r);
             }
         }
@@ -1331,17 +1487,18 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     uint32_t maxw = 1;
     for (int it = 0; it < n; ++it) {
         RowHdr qh;
-        if ((rc = stored_hdr(e, query_rows[it], &qh, "fn3_profile_queries"))) break;
+        uint32_t nb = 0;
+        if ((rc = stored_hdr(e, query_rows[it], &qh, "fn3_profile_queries", &nb))) break;
         QuerySlot& s = hs[(size_t)it];
         s.hdr = qh; s.row = query_rows[it]; s.skip_le = -1; s.exclude = query_rows[it]; s.pad = 0;
-        maxw = std::max(maxw, qh.end[5]);
+        maxw = std::max(maxw, nb);
     }
     QuerySlot* d_ps = nullptr;
     if (rc == FN3_OK) {
         CU(e, cudaMalloc(&d_ps, (size_t)n * sizeof(QuerySlot)));
         CU(e, cudaMemcpyAsync(d_ps, hs.data(), (size_t)n * sizeof(QuerySlot), cudaMemcpyHostToDevice, st));
         CU(e, cudaStreamSynchronize(st));
-        e->h_slots[0].hdr.end[5] = maxw;      // sizes the scatter grid
+        e->slot_blocks[0] = maxw;             // sizes the shared-memory staging of every step
     }
     for (int it = 0; it < n && rc == FN3_OK; ++it) {
         if (flush_l2) { k_fill<<<e->sm_count * 4, 512, 0, st>>>(e->d_flush, e->flush_n, (uint32_t)it); e->launches += 1; }

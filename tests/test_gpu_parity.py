@@ -242,10 +242,15 @@ def _synthetic(n_anc, max_c, L, seed, **kw):
     return synth.make_collection(n_anc, max_c, genome_length=L, seed=seed, excluded=excluded, **kw)
 
 
-@pytest.mark.parametrize("shape", ["tb_like", "high_nm", "tiny_genome", "long_runs"])
-def test_synthetic_vs_c_oracle(shape):
+@pytest.mark.parametrize("staged", [True, False])
+@pytest.mark.parametrize("shape", ["tb_like", "high_nm", "tiny_genome", "long_runs", "scattered_n"])
+def test_synthetic_vs_c_oracle(shape, staged, monkeypatch):
+    """staged=False forces the kernels' global-memory query variants (what a query touching more blocks than
+    fit in shared memory, or a genome whose block bitmap exceeds it, would use)."""
     from findneighbour3_b200.engine import Engine
     from oracle import c_oracle
+    if not staged:
+        monkeypatch.setenv("FN3_FORCE_GLOBAL_QUERY", "1")
     if shape == "tb_like":        # config 1 shape at reduced genome length
         coll = _synthetic(12, 25, 500000, 1, k1=500, s=3.0, n_blocks=20, n_mean=4000, rule="lss")
         ceilings = (20, 250, 2 ** 31 - 1)
@@ -256,6 +261,10 @@ def test_synthetic_vs_c_oracle(shape):
     elif shape == "tiny_genome":  # genome shorter than one rank block / one run word
         coll = _synthetic(5, 8, 31, 9, k1=3, s=1.0, n_blocks=2, n_mean=4, m_mean=1, rule="any", p_invalid=0.1)
         ceilings = (0, 1, 20)
+    elif shape == "scattered_n":  # i.i.d. N (the reference generator's model): tens of thousands of touched blocks,
+        # more than shared memory can stage -> the engine itself falls back to the global-memory variant
+        coll = _synthetic(3, 8, 4000000, 15, k1=300, s=2.0, n_blocks=60000, n_mean=60000, m_mean=50, rule="any")
+        ceilings = (20, 400)
     else:                         # runs much longer than the run-word limit and > maxNs-like sizes
         coll = _synthetic(4, 10, 3000000, 12, k1=200, s=2.0, n_blocks=3, n_mean=120000, m_mean=20, rule="any")
         ceilings = (20, 400)

@@ -25,9 +25,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -43,8 +41,8 @@ UNIT = "comparisons/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=50000, help="samples per GPU shard")
     ap.add_argument("--ceiling", type=int, default=20)
@@ -75,55 +73,68 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed regions (NVML, every 2 ms, own thread);
+    the equivalent of the profiling recipe's nvidia-smi clocks line without its start-up delay."""
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.h = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap ordinals: match by PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id
+            dom = torch.cuda.get_device_properties(index).pci_domain_id
+            dev = torch.cuda.get_device_properties(index).pci_device_id
+            busid = "%08X:%02X:%02X.0" % (dom, bus, dev)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(busid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        if self.h is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self.thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
-                    continue
-                try:
-                    sm.append(float(f[0]))
-                    mx.append(float(f[1]))
-                except ValueError:
-                    continue
-                for name, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm), sm_mhz_max_seen=max(sm))
-        out["reasons"] = sorted(reasons)
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        if self.samples:
+            out.update(sm_mhz=statistics.median(self.samples), samples=len(self.samples),
+                       sm_mhz_min=min(self.samples), sm_mhz_max_seen=max(self.samples))
+        out["reasons"] = sorted(self.reasons)
         return out
 
 
@@ -324,7 +335,6 @@ def main():
     full = eng.profile_queries(resident[W:W + min(K, 20)], 2 ** 31 - 1, flush_l2=True, count_bytes=True)
     touched = eng.profile_queries(resident[W:W + min(K, 20)], args.ceiling, flush_l2=False, count_bytes=True)
     barrier()
-    clocks = sampler.stop()
     t_dev = float(prof["ms_build"].sum() + prof["ms_compare"].sum()) / 1e3
     t_dev = max_over_ranks(t_dev)
     comps_per_step = sum_over_ranks(float(n_rows - 1))          # every other row of every shard
@@ -385,6 +395,7 @@ def main():
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()
     st1 = eng.stats()
     t_e2e = max_over_ranks(t_e2e)
     e2e_comps = sum_over_ranks(float(sum(range(st0["n_rows"], st0["n_rows"] + K))))   # store grows by one per step

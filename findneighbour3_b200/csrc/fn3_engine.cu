@@ -778,9 +778,16 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         if ((s = cudaMalloc(&q.bm_scratch, (size_t)q.nw * 2 * sizeof(uint32_t) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(bm)", s);
         e->max_smem = (int)prop.sharedMemPerBlockOptin;
         e->stage_limit = env_ll("FN3_FORCE_GLOBAL_QUERY", 0) ? 0 : e->max_smem;   // tests: exercise the non-staged variants
-        cudaFuncSetAttribute(k_compare<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
-        cudaFuncSetAttribute(k_compare<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
-        cudaFuncSetAttribute(k_build_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem);
+        // opt in to the full shared memory for the kernels that stage the query (minus their static part)
+        const void* staged[3] = {(const void*)k_compare<false, true>, (const void*)k_compare<true, true>,
+                                 (const void*)k_build_query<true>};
+        for (int i = 0; i < 3; ++i) {
+            cudaFuncAttributes fa;
+            if ((s = cudaFuncGetAttributes(&fa, staged[i])) != cudaSuccess) return fail("cudaFuncGetAttributes", s);
+            if ((s = cudaFuncSetAttribute(staged[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          e->max_smem - (int)fa.sharedSizeBytes)) != cudaSuccess)
+                return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", s);
+        }
     }
     if ((s = cudaMalloc(&e->d_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS)) != cudaSuccess) return fail("cudaMalloc(slots)", s);
     if ((s = cudaHostAlloc(&e->h_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(slots)", s);
@@ -912,7 +919,9 @@ static int ensure_hdr_chunk(fn3_engine* e, long long row) {
         size_t bytes = sizeof(RowHdr) << e->hdr_shift;
         cudaError_t s = cudaMalloc(&p, bytes);
         if (s != cudaSuccess) return set_err(e, FN3_ENOMEM, "cudaMalloc of a header chunk failed: %s", cudaGetErrorString(s));
-        cudaMemset(p, 0, bytes);
+        // same stream as the header copies that follow (the legacy default stream does not order against it)
+        s = cudaMemsetAsync(p, 0, bytes, e->copy_stream);
+        if (s != cudaSuccess) return set_err(e, FN3_ECUDA, "cudaMemsetAsync of a header chunk failed: %s", cudaGetErrorString(s));
         e->hdr_chunks.push_back(p);
         e->store_bytes += (long long)bytes;
     }
@@ -1409,7 +1418,8 @@ extern "C" int fn3_set_reference(fn3_engine* e, const char* reference, const int
         memset(e->h_seq, 0, (size_t)e->Lpad);
     }
     CU(e, cudaMemcpy(e->d_refmask, rm.data(), (size_t)e->Lpad, cudaMemcpyHostToDevice));
-    CU(e, cudaMemset(e->d_seq, 0, (size_t)e->Lpad));
+    CU(e, cudaMemsetAsync(e->d_seq, 0, (size_t)e->Lpad, e->in_stream));
+    CU(e, cudaStreamSynchronize(e->in_stream));
     return FN3_OK;
 }
 

@@ -42,6 +42,15 @@ struct __align__(32) RowHdr {
 };
 static_assert(sizeof(RowHdr) == 32, "RowHdr must be one 32-byte sector");
 
+// What the header table holds per row: the header plus a copy of the row's first V words, so that the
+// early-exit filter needs ONE contiguous 160-byte read per candidate and no dependent second access.
+#define FN3_HEAD_WORDS 32
+struct __align__(32) RowHead {
+    RowHdr hdr;
+    uint32_t first[FN3_HEAD_WORDS];   // row words 0 .. min(end[3], 32)-1 (A,C,G,T positions), zero padded
+};
+static_assert(sizeof(RowHead) == 160, "RowHead must be 160 bytes");
+
 // The query, compacted.  Positions are grouped in blocks of 32.  `bmpref[w]` holds, for
 // blocks 32w..32w+31, .x = bit per block "the query is non-reference / N / M somewhere in this block" and
 // .y = number of such (touched) blocks below block 32w.  Entry i describes the i-th touched block:
@@ -61,7 +70,7 @@ static_assert(sizeof(EdgeRec) == sizeof(fn3_edge), "EdgeRec/fn3_edge mismatch");
 #define FN3_MAX_SLOTS 16
 
 struct HdrTable {
-    const RowHdr* chunk[FN3_MAX_HDR_CHUNKS];
+    const RowHead* chunk[FN3_MAX_HDR_CHUNKS];
     int shift;                 // rows per chunk = 1 << shift
 };
 
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(FN3_BUILD_THREADS) k_build_query(const QuerySl
 }
 
 // ------------------------------------------------------------------------------------------
-// the compare kernel
+// the compare kernel (k_query)
 // ------------------------------------------------------------------------------------------
 //
 // Streaming identity (SURVEY.md §8 "Spec"), with V = definite non-reference positions,
@@ -246,16 +255,20 @@ __global__ void __launch_bounds__(FN3_BUILD_THREADS) k_build_query(const QuerySl
 //   n1    = |U_q|,  n2 = |N_c| + |M_q| - |N_c n M_q|,  nboth = n1 + |N_c| - |N_c n U_q|
 // S1 alone is a lower bound of dist, so a pair leaves as soon as S1 > ceiling.
 //
-// Each CTA first stages the query's compact structure in shared memory (QSMEM) — every later
-// lookup is an LDS, never an L2 gather.  Work unit = a group of 32 candidates per warp:
-//   phase A (one THREAD per candidate): header + the first `filter_len` V words; a candidate
-//            whose first words already give S1 > ceiling is done (this is ~all unrelated pairs);
-//   phase B (one WARP per surviving candidate): coalesced 128-bit streaming of the whole row,
-//            warp-reduced tallies, survivors compacted into the neighbour buffer.
-// Lane l of group g takes candidate g + l*G (G = number of groups) so that consecutive rows
-// — relatives are inserted together — land in different warps.
+// ONE launch per one-vs-all query.  Every CTA first builds the query's compact structure in its own
+// SHARED memory straight from the query's row (QMODE 1: ~1 us of block-local work, no global traffic
+// beyond re-reading the ~4 KB row) — every later lookup is an LDS, never an L2 gather.  Queries whose
+// structure exceeds shared memory use the copy k_build_query left in global memory (QMODE 0).
+//   FILTER variant (small ceilings): one THREAD per candidate reads the candidate's 160-byte row head
+//     (header + first 32 V words, contiguous, L2-resident across queries); a candidate whose first words
+//     already give S1 > ceiling is done — that is ~every unrelated pair.  Survivors are then streamed
+//     one WARP per candidate.  Lane l of group g takes candidate g + l*G so that consecutive rows
+//     (relatives are inserted together) land in different warps.
+//   STREAM variant (large ceilings): one WARP per candidate from the start, next header prefetched.
+// Row streaming: coalesced 128-bit loads, next chunk in flight while the current one is tallied,
+// __reduce_add_sync tallies, survivors compacted into the neighbour buffer with one atomic each.
 
-struct QView {                  // where the staged query lives (shared or global)
+struct QView {                  // where the query structure lives (shared or global)
     const uint2* bmpref;
     const uint4* ent;           // two uint4 per entry
 };
@@ -291,139 +304,288 @@ __device__ __forceinline__ void rank3(const QView& qv, uint32_t x, uint32_t& rD,
     }
 }
 
-#define FN3_CMP_BLOCK 256
+// three exclusive block scans sharing their barriers; ws = 3*33 words
+__device__ __forceinline__ void block_exscan3(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t* ws,
+                                              uint32_t& ta, uint32_t& tb, uint32_t& tc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t ia = a, ib = b, ic = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t x = __shfl_up_sync(0xffffffffu, ia, o), y = __shfl_up_sync(0xffffffffu, ib, o), z = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) { ia += x; ib += y; ic += z; }
+    }
+    __syncthreads();
+    if (lane == 31) { ws[warp] = ia; ws[33 + warp] = ib; ws[66 + warp] = ic; }
+    __syncthreads();
+    if (warp < 3) {
+        uint32_t* w = ws + 33 * warp;
+        uint32_t v = lane < nwarp ? w[lane] : 0u, i2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, i2, o); if (lane >= o) i2 += t; }
+        w[lane] = i2 - v;
+        if (lane == 31) w[32] = i2;
+    }
+    __syncthreads();
+    ta = ws[32]; tb = ws[65]; tc = ws[98];
+    a = ws[warp] + ia - a; b = ws[33 + warp] + ib - b; c = ws[66 + warp] + ic - c;
+}
 
-template <bool COUNT, bool QSMEM>
-__global__ void __launch_bounds__(FN3_CMP_BLOCK) k_compare(const CompareParams p) {
-    extern __shared__ uint4 qsm[];
+// Build the query's compact structure in shared memory from its row.  sm_bp: nw uint2, sm_en: (cap+1) QEntry.
+// Returns totals (|V_q|,|U_q|,|M_q|) in tot[3].  All threads of the CTA must call.
+__device__ __forceinline__ void build_query_smem(const QuerySlot& q, int nw, int pos_bits, uint2* sm_bp, QEntry* sm_en,
+                                                 uint32_t* ws, uint32_t tot[3]) {
+    const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(q.hdr.data);
+    const uint32_t e0 = q.hdr.end[0], e1 = q.hdr.end[1], e2 = q.hdr.end[2], e3 = q.hdr.end[3],
+                   e4 = q.hdr.end[4], e5 = q.hdr.end[5];
+    const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    {
+        uint4* z = reinterpret_cast<uint4*>(sm_bp);
+        for (int i = tid; i < nw / 2; i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < e5; i += nt) {                   // 1. touched blocks
+        const uint32_t w = __ldg(d + i);
+        if (i < e3) {
+            const uint32_t blk = w >> 5;
+            atomicOr(&sm_bp[blk >> 5].x, 1u << (blk & 31u));
+        } else {
+            const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u);
+            for (uint32_t blk = s >> 5; blk <= ((s + len - 1u) >> 5); ++blk) atomicOr(&sm_bp[blk >> 5].x, 1u << (blk & 31u));
+        }
+    }
+    __syncthreads();
+    const int chunk = (nw + nt - 1) / nt;                        // 2. prefix of touched-block counts
+    const int lo = min(nw, tid * chunk), hi = min(nw, lo + chunk);
+    uint32_t local = 0;
+    for (int w = lo; w < hi; ++w) local += __popc(sm_bp[w].x);
+    uint32_t nE;
+    uint32_t run = block_exscan(local, ws, &nE);
+    for (int w = lo; w < hi; ++w) { const uint32_t b = sm_bp[w].x; sm_bp[w].y = run; run += __popc(b); }
+    {
+        uint4* z = reinterpret_cast<uint4*>(sm_en);              // 3. clear entries incl. the sentinel
+        for (uint32_t i = tid; i < 2u * (nE + 1u); i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < e5; i += nt) {                   // 4. per-position masks
+        const uint32_t w = __ldg(d + i);
+        if (i < e3) {
+            const uint32_t blk = w >> 5;
+            const uint2 bp = sm_bp[blk >> 5];
+            QEntry* en = sm_en + (bp.y + __popc(bp.x & lowmask(blk & 31u)));
+            const uint32_t pb = 1u << (w & 31u);
+            const uint32_t base = (i >= e0) + (i >= e1) + (i >= e2);
+            atomicOr(&en->mDef, pb);
+            if (base & 1u) atomicOr(&en->mB0, pb);
+            if (base & 2u) atomicOr(&en->mB1, pb);
+        } else {
+            const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u), e = s + len;
+            for (uint32_t blk = s >> 5; blk <= ((e - 1u) >> 5); ++blk) {
+                const uint32_t b0 = blk << 5;
+                const uint32_t from = s > b0 ? s - b0 : 0u, to = min(e - b0, 32u);
+                const uint32_t m = (to >= 32u ? 0xffffffffu : lowmask(to)) & ~lowmask(from);
+                const uint2 bp = sm_bp[blk >> 5];
+                QEntry* en = sm_en + (bp.y + __popc(bp.x & lowmask(blk & 31u)));
+                atomicOr(&en->mU, m);
+                if (i >= e4) atomicOr(&en->mM, m);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t echunk = (nE + nt - 1) / nt;                  // 5. running counts
+    const uint32_t elo = min(nE, tid * echunk), ehi = min(nE, elo + echunk);
+    uint32_t sD = 0, sU = 0, sM = 0;
+    for (uint32_t i = elo; i < ehi; ++i) { sD += __popc(sm_en[i].mDef); sU += __popc(sm_en[i].mU); sM += __popc(sm_en[i].mM); }
+    uint32_t tD, tU, tM;
+    block_exscan3(sD, sU, sM, ws, tD, tU, tM);
+    for (uint32_t i = elo; i < ehi; ++i) {
+        const uint32_t a = __popc(sm_en[i].mDef), b = __popc(sm_en[i].mU), c = __popc(sm_en[i].mM);
+        sm_en[i].cDef = sD; sm_en[i].cU = sU; sm_en[i].cM = sM;
+        sD += a; sU += b; sM += c;
+    }
+    if (tid == 0) { sm_en[nE].cDef = tD; sm_en[nE].cU = tU; sm_en[nE].cM = tM; }
+    __syncthreads();
+    tot[0] = tD; tot[1] = tU; tot[2] = tM;
+}
+
+struct Tally { int S1, qdefV, qdefU, nNc, nNU, nNM; bool dead; };
+
+// One warp streams one candidate row against the query (all 32 lanes must call).
+template <bool COUNT>
+__device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __restrict__ d, uint32_t e0, uint32_t e1,
+                                            uint32_t e2, uint32_t e3, uint32_t e4, uint32_t e5, int k, int pos_bits,
+                                            uint32_t pmask, int lane, unsigned long long& touched) {
+    Tally t; t.S1 = 0; t.qdefV = 0; t.qdefU = 0; t.nNc = 0; t.nNU = 0; t.nNM = 0; t.dead = false;
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if ((uint32_t)lane * 4u < e5) { cur = ld_stream_v4(d + lane * 4); if (COUNT) touched += 16; }
+    for (uint32_t base = 0; base < e5; base += 128) {
+        const uint32_t idx = base + lane * 4;
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (idx + 128u < e5) { nxt = ld_stream_v4(d + idx + 128); if (COUNT) touched += 16; }   // next chunk in flight
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+        int mism = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t ii = idx + j;
+            if (ii < e3) {
+                const uint32_t r = look_v(qv, w[j], (ii >= e0) + (ii >= e1) + (ii >= e2));
+                mism += r & 1u;
+                t.qdefV += r >> 1;
+            } else if (ii < e5) {
+                const uint32_t s = w[j] & pmask;
+                const uint32_t len = (pos_bits >= 32) ? 1u : ((w[j] >> pos_bits) + 1u);
+                const bool isN = ii < e4;
+                uint32_t aD, aU, aM, bD, bU, bM;
+                rank3(qv, s, aD, aU, aM, isN);
+                rank3(qv, s + len, bD, bU, bM, isN);
+                t.qdefU += (int)(bD - aD);
+                if (isN) { t.nNc += (int)len; t.nNU += (int)(bU - aU); t.nNM += (int)(bM - aM); }
+            }
+        }
+        if (base < e3) {                                        // warp-uniform: this step touched V words
+            t.S1 += __reduce_add_sync(0xffffffffu, mism);
+            if (t.S1 > k) { t.dead = true; break; }
+        }
+        cur = nxt;
+    }
+    return t;
+}
+
+__device__ __forceinline__ void emit_if_close(const CompareParams& p, const Tally& t0, int k, uint32_t nVq, uint32_t nUq,
+                                              uint32_t nMq, long long qrow, long long crow, int lane) {
+    if (t0.dead) return;
+    const int qdefV = __reduce_add_sync(0xffffffffu, t0.qdefV);
+    const int qdefU = __reduce_add_sync(0xffffffffu, t0.qdefU);
+    const int dist = t0.S1 + (int)nVq - qdefV - qdefU;
+    if (dist > k) return;
+    const int nNc = __reduce_add_sync(0xffffffffu, t0.nNc);
+    const int nNU = __reduce_add_sync(0xffffffffu, t0.nNU);
+    const int nNM = __reduce_add_sync(0xffffffffu, t0.nNM);
+    if (lane == 0) {
+        const unsigned long long at = atomicAdd(p.out_count, 1ull);
+        if ((long long)at < p.out_cap) {
+            EdgeRec r;
+            r.row1 = qrow; r.row2 = crow; r.dist = dist;
+            r.n1 = (int)nUq; r.n2 = nNc + (int)nMq - nNM; r.nboth = (int)nUq + nNc - nNU;
+            p.out[at] = r;
+        }
+    }
+}
+
+#define FN3_Q_THREADS 512
+
+// QMODE 0: query structure in global memory (built by k_build_query); 1: built here in shared memory
+template <bool COUNT, int QMODE, bool FILTER>
+__global__ void __launch_bounds__(FN3_Q_THREADS, 2) k_query(const CompareParams p) {
+    extern __shared__ __align__(128) uint4 qsm[];
+    __shared__ uint32_t ws[99];
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.y;
     const QuerySlot qs = p.slots[slot];
     if (qs.hdr.data == 0ull) return;                       // invalid query: no distances at all
     const int nw = p.qs.nw;
-    const uint4 info = p.qs.info[slot];
-    const uint32_t nE = info.x, nVq = info.y, nUq = info.z, nMq = info.w;
+    uint32_t nVq, nUq, nMq;
     QView qv;
-    {
-        const uint2* g_bp = p.qs.bmpref + (long long)slot * nw;
-        const uint4* g_en = reinterpret_cast<const uint4*>(p.qs.ent + (long long)slot * p.qs.ent_stride);
-        if (QSMEM) {
-            // stage: [bmpref (nw x 8 B, padded to 16) | entries ((nE+1) x 32 B)]
-            const int n_bp4 = (nw + 1) / 2;
-            const uint4* src = reinterpret_cast<const uint4*>(g_bp);
-            for (int i = threadIdx.x; i < n_bp4; i += blockDim.x) qsm[i] = __ldg(src + i);
-            const int n_en4 = 2 * ((int)nE + 1);
-            for (int i = threadIdx.x; i < n_en4; i += blockDim.x) qsm[n_bp4 + i] = __ldg(g_en + i);
-            __syncthreads();
-            qv.bmpref = reinterpret_cast<const uint2*>(qsm);
-            qv.ent = qsm + n_bp4;
-        } else {
-            qv.bmpref = g_bp;
-            qv.ent = g_en;
-        }
+    if (QMODE == 1) {
+        uint2* sm_bp = reinterpret_cast<uint2*>(qsm);
+        QEntry* sm_en = reinterpret_cast<QEntry*>(qsm + nw / 2);
+        uint32_t tot[3];
+        build_query_smem(qs, nw, p.pos_bits, sm_bp, sm_en, ws, tot);
+        nVq = tot[0]; nUq = tot[1]; nMq = tot[2];
+        qv.bmpref = sm_bp;
+        qv.ent = reinterpret_cast<const uint4*>(sm_en);
+    } else {
+        const uint4 info = p.qs.info[slot];
+        nVq = info.y; nUq = info.z; nMq = info.w;
+        qv.bmpref = p.qs.bmpref + (long long)slot * nw;
+        qv.ent = reinterpret_cast<const uint4*>(p.qs.ent + (long long)slot * p.qs.ent_stride);
     }
     const int k = p.ceiling;
     const int pos_bits = p.pos_bits;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
     const long long hmask = (1ll << p.hdr.shift) - 1;
-    const long long G = (p.n + 31) >> 5;                   // candidate groups
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     unsigned long long touched = 0;
 
-    for (long long g = warp0; g < G; g += nwarps) {
-        // ---- phase A: one thread per candidate -------------------------------------------
-        const long long ci = g + (long long)lane * G;
-        long long row = -1;
-        uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
-        bool pass = false;
-        if (ci < p.n) {
-            row = p.rows ? p.rows[ci] : p.row_begin + ci;
-            if (row != qs.exclude && row > qs.skip_le) {
-                const uint4* hp = reinterpret_cast<const uint4*>(p.hdr.chunk[row >> p.hdr.shift] + (row & hmask));
-                h0 = __ldg(hp); h1 = __ldg(hp + 1);
-                if (COUNT) touched += 32;
-                pass = (h0.x | h0.y) != 0u;                // data pointer 0: invalid or removed candidate
-            }
-        }
-        if (pass && p.filter_len > 0) {
-            const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
-            const uint32_t e0 = h0.z, e1 = h0.w, e2 = h1.x, e3 = h1.y;
-            const uint32_t lim = min(e3, (uint32_t)p.filter_len);
-            int S = 0;
-            for (uint32_t i = 0; i < lim && S <= k; i += 4) {
-                const uint4 w4 = ld_stream_v4(d + i);
-                if (COUNT) touched += 16;
-                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+    if (FILTER) {
+        const long long G = (p.n + 31) >> 5;               // candidate groups of 32
+        for (long long g = warp0; g < G; g += nwarps) {
+            // ---- phase A: one thread per candidate, on the candidate's row head ---------------
+            const long long ci = g + (long long)lane * G;
+            long long row = -1;
+            uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+            bool pass = false;
+            if (ci < p.n) {
+                row = p.rows ? p.rows[ci] : p.row_begin + ci;
+                if (row != qs.exclude && row > qs.skip_le) {
+                    const uint4* hp = reinterpret_cast<const uint4*>(p.hdr.chunk[row >> p.hdr.shift] + (row & hmask));
+                    h0 = __ldg(hp); h1 = __ldg(hp + 1);
+                    if (COUNT) touched += 32;
+                    if ((h0.x | h0.y) != 0u) {             // data pointer 0: invalid or removed candidate
+                        const uint32_t e0 = h0.z, e1 = h0.w, e2 = h1.x, e3 = h1.y;
+                        const uint32_t lim = min(e3, (uint32_t)p.filter_len);
+                        uint4 f[FN3_HEAD_WORDS / 4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t ii = i + j;
-                    if (ii < lim) S += look_v(qv, w[j], (ii >= e0) + (ii >= e1) + (ii >= e2)) & 1u;
-                }
-            }
-            pass = S <= k;
-        }
-        // ---- phase B: one warp per surviving candidate -----------------------------------
-        uint32_t alive = __ballot_sync(0xffffffffu, pass);
-        while (alive) {
-            const int src = __ffs(alive) - 1;
-            alive &= alive - 1u;
-            const uint32_t dlo = __shfl_sync(0xffffffffu, h0.x, src), dhi = __shfl_sync(0xffffffffu, h0.y, src);
-            const uint32_t e0 = __shfl_sync(0xffffffffu, h0.z, src), e1 = __shfl_sync(0xffffffffu, h0.w, src);
-            const uint32_t e2 = __shfl_sync(0xffffffffu, h1.x, src), e3 = __shfl_sync(0xffffffffu, h1.y, src);
-            const uint32_t e4 = __shfl_sync(0xffffffffu, h1.z, src), e5 = __shfl_sync(0xffffffffu, h1.w, src);
-            const long long crow = __shfl_sync(0xffffffffu, row, src);
-            const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(((unsigned long long)dhi << 32) | dlo);
-
-            int S1 = 0;                                    // warp-uniform running mismatch count
-            int qdefV = 0, qdefU = 0, nNc = 0, nNU = 0, nNM = 0;   // per-lane partials
-            bool dead = false;
-            for (uint32_t base = 0; base < e5; base += 128) {
-                const uint32_t idx = base + lane * 4;
-                uint4 w4 = make_uint4(0, 0, 0, 0);
-                if (idx < e5) { w4 = ld_stream_v4(d + idx); if (COUNT) touched += 16; }
-                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-                int mism = 0;
+                        for (int j = 0; j < FN3_HEAD_WORDS / 4; ++j) {
+                            f[j] = make_uint4(0, 0, 0, 0);
+                            if ((uint32_t)(4 * j) < lim) { f[j] = __ldg(hp + 2 + j); if (COUNT) touched += 16; }
+                        }
+                        int S = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t ii = idx + j;
-                    if (ii < e3) {
-                        const uint32_t r = look_v(qv, w[j], (ii >= e0) + (ii >= e1) + (ii >= e2));
-                        mism += r & 1u;
-                        qdefV += r >> 1;
-                    } else if (ii < e5) {
-                        const uint32_t s = w[j] & pmask;
-                        const uint32_t len = (pos_bits >= 32) ? 1u : ((w[j] >> pos_bits) + 1u);
-                        const bool isN = ii < e4;
-                        uint32_t aD, aU, aM, bD, bU, bM;
-                        rank3(qv, s, aD, aU, aM, isN);
-                        rank3(qv, s + len, bD, bU, bM, isN);
-                        qdefU += (int)(bD - aD);
-                        if (isN) { nNc += (int)len; nNU += (int)(bU - aU); nNM += (int)(bM - aM); }
+                        for (int j = 0; j < FN3_HEAD_WORDS / 4; ++j) {
+                            const uint32_t w[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t ii = 4 * j + i;
+                                if (ii < lim && S <= k) S += look_v(qv, w[i], (ii >= e0) + (ii >= e1) + (ii >= e2)) & 1u;
+                            }
+                        }
+                        pass = S <= k;
                     }
                 }
-                if (base < e3) {                            // warp-uniform: this step touched V words
-                    S1 += __reduce_add_sync(0xffffffffu, mism);
-                    if (S1 > k) { dead = true; break; }
+            }
+            // ---- phase B: one warp per surviving candidate -----------------------------------
+            uint32_t alive = __ballot_sync(0xffffffffu, pass);
+            while (alive) {
+                const int src = __ffs(alive) - 1;
+                alive &= alive - 1u;
+                const uint32_t dlo = __shfl_sync(0xffffffffu, h0.x, src), dhi = __shfl_sync(0xffffffffu, h0.y, src);
+                const uint32_t e0 = __shfl_sync(0xffffffffu, h0.z, src), e1 = __shfl_sync(0xffffffffu, h0.w, src);
+                const uint32_t e2 = __shfl_sync(0xffffffffu, h1.x, src), e3 = __shfl_sync(0xffffffffu, h1.y, src);
+                const uint32_t e4 = __shfl_sync(0xffffffffu, h1.z, src), e5 = __shfl_sync(0xffffffffu, h1.w, src);
+                const long long crow = __shfl_sync(0xffffffffu, row, src);
+                const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)dhi << 32) | dlo);
+                const Tally t = stream_row<COUNT>(qv, d, e0, e1, e2, e3, e4, e5, k, pos_bits, pmask, lane, touched);
+                emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, crow, lane);
+            }
+        }
+    } else {
+        // one warp per candidate; the next candidate's header is requested before the current row is streamed
+        long long i = warp0;
+        long long row = -1;
+        uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+        auto fetch = [&](long long ci, long long& r, uint4& a, uint4& b) {
+            a = make_uint4(0, 0, 0, 0); b = a; r = -1;
+            if (ci < p.n) {
+                r = p.rows ? p.rows[ci] : p.row_begin + ci;
+                if (r != qs.exclude && r > qs.skip_le) {
+                    const uint4* hp = reinterpret_cast<const uint4*>(p.hdr.chunk[r >> p.hdr.shift] + (r & hmask));
+                    a = __ldg(hp); b = __ldg(hp + 1);
+                    if (COUNT && lane == 0) touched += 32;
                 }
             }
-            if (dead) continue;
-            qdefV = __reduce_add_sync(0xffffffffu, qdefV);
-            qdefU = __reduce_add_sync(0xffffffffu, qdefU);
-            const int dist = S1 + (int)nVq - qdefV - qdefU;
-            if (dist > k) continue;
-            nNc = __reduce_add_sync(0xffffffffu, nNc);
-            nNU = __reduce_add_sync(0xffffffffu, nNU);
-            nNM = __reduce_add_sync(0xffffffffu, nNM);
-            if (lane == 0) {
-                const unsigned long long at = atomicAdd(p.out_count, 1ull);
-                if ((long long)at < p.out_cap) {
-                    EdgeRec r;
-                    r.row1 = qs.row; r.row2 = crow; r.dist = dist;
-                    r.n1 = (int)nUq; r.n2 = nNc + (int)nMq - nNM; r.nboth = (int)nUq + nNc - nNU;
-                    p.out[at] = r;
-                }
+        };
+        fetch(i, row, h0, h1);
+        while (i < p.n) {
+            long long nrow; uint4 n0, n1;
+            fetch(i + nwarps, nrow, n0, n1);
+            if ((h0.x | h0.y) != 0u) {
+                const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
+                const Tally t = stream_row<COUNT>(qv, d, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, k, pos_bits, pmask, lane, touched);
+                emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, row, lane);
             }
+            i += nwarps; row = nrow; h0 = n0; h1 = n1;
         }
     }
     if (COUNT) {
@@ -577,7 +739,7 @@ struct fn3_engine {
     std::vector<size_t> data_chunk_cap;     // words
     size_t cur_used = 0;                    // words used in the last chunk
     int hdr_shift = 20;
-    std::vector<RowHdr*> hdr_chunks;        // device
+    std::vector<RowHead*> hdr_chunks;       // device: header + first V words per row
     std::vector<RowHdr> h_hdr;              // host mirror (published rows)
     std::vector<uint8_t> h_flags;           // bit0 invalid, bit1 removed
     std::vector<uint32_t> h_npos;           // canonical position count per row
@@ -588,13 +750,14 @@ struct fn3_engine {
 
     // staging
     uint32_t* stage = nullptr; size_t stage_words = 0;     // pinned
-    RowHdr* stage_hdr = nullptr; size_t stage_hdr_n = 0;   // pinned
+    RowHead* stage_hdr = nullptr; size_t stage_hdr_n = 0;  // pinned
 
     // query state
     int n_slots = 8;
     QueryState qstate;                     // device arrays of the compact queries (n_slots of them)
     int max_smem = 0;                      // opt-in dynamic shared memory per CTA
     int stage_limit = 0;                   // = max_smem, or 0 to force the global-memory query variants
+    int q_static_smem = 0;                 // static shared memory of k_query
     uint32_t slot_blocks[FN3_MAX_SLOTS];   // touched-block count of the query in each slot (sizes the staging)
     QuerySlot* d_slots = nullptr; QuerySlot* h_slots = nullptr;   // h_slots pinned
     // survivor buffer: one allocation = [32-byte counter block | records], mirrored in pinned host memory so
@@ -609,7 +772,7 @@ struct fn3_engine {
     long long* h_rows = nullptr; long long h_rows_cap = 0;       // pinned
     // scratch rows for samples that are not stored (pair_lists / lists_vs_all)
     uint32_t* d_scratch = nullptr; size_t scratch_words = 0;
-    RowHdr* d_scratch_hdr = nullptr;         // [2]
+    RowHead* d_scratch_hdr = nullptr;        // [2]
     uint4* d_flush = nullptr; long long flush_n = 0;
     // ingest (fn3_compress)
     std::mutex ingest_mu;
@@ -713,7 +876,7 @@ static int ensure_stage(fn3_engine* e, size_t words, size_t hdrs) {
         want = std::max<size_t>(want, 1024);
         if (e->stage_hdr) cudaFreeHost(e->stage_hdr);
         e->stage_hdr = nullptr; e->stage_hdr_n = 0;
-        CU(e, cudaHostAlloc(&e->stage_hdr, want * sizeof(RowHdr), cudaHostAllocDefault));
+        CU(e, cudaHostAlloc(&e->stage_hdr, want * sizeof(RowHead), cudaHostAllocDefault));
         e->stage_hdr_n = want;
     }
     return FN3_OK;
@@ -770,7 +933,7 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         memset(&q, 0, sizeof q);
         q.n_blk = (int)((genome_length + 31) / 32 + 1);
         q.nw = (q.n_blk + 31) / 32;
-        q.nw = (q.nw + 1) & ~1;                                  // even: 16-byte staging copies
+        q.nw = (q.nw + 3) & ~3;                                  // entries start 32-byte aligned behind bmpref
         q.ent_stride = (long long)q.n_blk + 1;
         if ((s = cudaMalloc(&q.bmpref, (size_t)q.nw * sizeof(uint2) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(bmpref)", s);
         if ((s = cudaMalloc(&q.ent, (size_t)q.ent_stride * sizeof(QEntry) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(entries)", s);
@@ -779,11 +942,14 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         e->max_smem = (int)prop.sharedMemPerBlockOptin;
         e->stage_limit = env_ll("FN3_FORCE_GLOBAL_QUERY", 0) ? 0 : e->max_smem;   // tests: exercise the non-staged variants
         // opt in to the full shared memory for the kernels that stage the query (minus their static part)
-        const void* staged[3] = {(const void*)k_compare<false, true>, (const void*)k_compare<true, true>,
+        const void* staged[5] = {(const void*)k_query<false, 1, false>, (const void*)k_query<false, 1, true>,
+                                 (const void*)k_query<true, 1, false>, (const void*)k_query<true, 1, true>,
                                  (const void*)k_build_query<true>};
-        for (int i = 0; i < 3; ++i) {
+        e->q_static_smem = 0;
+        for (int i = 0; i < 5; ++i) {
             cudaFuncAttributes fa;
             if ((s = cudaFuncGetAttributes(&fa, staged[i])) != cudaSuccess) return fail("cudaFuncGetAttributes", s);
+            if (i < 4) e->q_static_smem = std::max(e->q_static_smem, (int)fa.sharedSizeBytes);
             if ((s = cudaFuncSetAttribute(staged[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           e->max_smem - (int)fa.sharedSizeBytes)) != cudaSuccess)
                 return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", s);
@@ -796,7 +962,7 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         fn3_destroy(e);
         return nullptr;
     }
-    if ((s = cudaMalloc(&e->d_scratch_hdr, 2 * sizeof(RowHdr))) != cudaSuccess) return fail("cudaMalloc(scratch hdr)", s);
+    if ((s = cudaMalloc(&e->d_scratch_hdr, 2 * sizeof(RowHead))) != cudaSuccess) return fail("cudaMalloc(scratch hdr)", s);
     e->store_bytes = 0;
     return e;
 }
@@ -891,6 +1057,14 @@ static void pack_row(const fn3_engine* e, const int32_t* pos, const long long of
     }
 }
 
+// header + copy of the first V words (the early-exit filter's contiguous read)
+static void fill_head(RowHead& hd, const RowHdr& h, const uint32_t* words) {
+    hd.hdr = h;
+    const uint32_t nv = h.data ? std::min<uint32_t>(h.end[3], FN3_HEAD_WORDS) : 0u;
+    for (uint32_t i = 0; i < nv; ++i) hd.first[i] = words[i];
+    for (uint32_t i = nv; i < FN3_HEAD_WORDS; ++i) hd.first[i] = 0u;
+}
+
 // reserve `words` (rounded up to 4) in the arena; returns device pointer
 static int arena_alloc(fn3_engine* e, size_t words, uint32_t** out) {
     size_t need = (words + 3) & ~(size_t)3;
@@ -915,8 +1089,8 @@ static int ensure_hdr_chunk(fn3_engine* e, long long row) {
     const long long c = row >> e->hdr_shift;
     if (c >= FN3_MAX_HDR_CHUNKS) return set_err(e, FN3_ECAPACITY, "store is full (%lld rows)", row);
     while ((long long)e->hdr_chunks.size() <= c) {
-        RowHdr* p = nullptr;
-        size_t bytes = sizeof(RowHdr) << e->hdr_shift;
+        RowHead* p = nullptr;
+        size_t bytes = sizeof(RowHead) << e->hdr_shift;
         cudaError_t s = cudaMalloc(&p, bytes);
         if (s != cudaSuccess) return set_err(e, FN3_ENOMEM, "cudaMalloc of a header chunk failed: %s", cudaGetErrorString(s));
         // same stream as the header copies that follow (the legacy default stream does not order against it)
@@ -963,7 +1137,7 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
         for (long long r = i; r < j; ++r) {
             long long o[7];
             for (int b = 0; b < 7; ++b) o[b] = off6[6 * r + b];
-            RowHdr& h = e->stage_hdr[r - i];
+            RowHdr h;
             const bool inv = invalid && invalid[r];
             size_t need = ((size_t)words[(size_t)r] + 3) & ~(size_t)3;
             if (need == 0) need = 4;
@@ -975,10 +1149,11 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
                 for (size_t z = (size_t)words[(size_t)r]; z < need; ++z) e->stage[w + z] = 0;
                 h.data = (unsigned long long)(uintptr_t)(dbase + w);
             }
+            fill_head(e->stage_hdr[r - i], h, e->stage + w);
             w += need;
         }
         CU(e, cudaMemcpyAsync(dbase, e->stage, batch_words * 4, cudaMemcpyHostToDevice, e->copy_stream));
-        e->h2d_bytes += (long long)batch_words * 4 + (j - i) * (long long)sizeof(RowHdr);
+        e->h2d_bytes += (long long)batch_words * 4 + (j - i) * (long long)sizeof(RowHead);
         // headers: may straddle header chunks
         long long r = i;
         while (r < j) {
@@ -988,14 +1163,14 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
             const long long in_chunk = row & ((1ll << e->hdr_shift) - 1);
             const long long take = std::min<long long>(j - r, (1ll << e->hdr_shift) - in_chunk);
             CU(e, cudaMemcpyAsync(e->hdr_chunks[(size_t)(row >> e->hdr_shift)] + in_chunk, e->stage_hdr + (r - i),
-                                  (size_t)take * sizeof(RowHdr), cudaMemcpyHostToDevice, e->copy_stream));
+                                  (size_t)take * sizeof(RowHead), cudaMemcpyHostToDevice, e->copy_stream));
             r += take;
         }
         CU(e, cudaStreamSynchronize(e->copy_stream));
         // publish host mirror
         for (long long r2 = i; r2 < j; ++r2) {
             const bool inv = invalid && invalid[r2];
-            e->h_hdr.push_back(e->stage_hdr[r2 - i]);
+            e->h_hdr.push_back(e->stage_hdr[r2 - i].hdr);
             e->h_flags.push_back(inv ? 1 : 0);
             const uint32_t np = inv ? 0u : (uint32_t)(off6[6 * r2 + 6] - off6[6 * r2]);
             e->h_npos.push_back(np);
@@ -1103,60 +1278,69 @@ static void fill_hdr_table(fn3_engine* e, HdrTable& t) {   // store_mu held
     t.shift = e->hdr_shift;
 }
 
-// enqueue: slots upload + ONE build kernel for `ns` slots (h_slots + slot_blocks filled by the caller)
-// (`resident` != nullptr: the slots are already on the device — measurement hook)
-static int enqueue_query_build(fn3_engine* e, int ns, const QuerySlot* resident = nullptr) {
+// the early-exit filter looks at this many leading V words of each candidate's row head (0 = STREAM variant)
+static int filter_len_for(int ceiling) {
+    if (ceiling < 0) return 4;
+    if (ceiling > 24) return 0;                  // 32 head words cannot push S1 past the ceiling reliably
+    return std::min(FN3_HEAD_WORDS, ((ceiling + 1 + 7 + 3) / 4) * 4);
+}
+
+template <bool COUNT, int QMODE>
+static void launch_query(bool filter, dim3 g, size_t smem, cudaStream_t st, const CompareParams& p) {
+    if (filter) k_query<COUNT, QMODE, true><<<g, FN3_Q_THREADS, smem, st>>>(p);
+    else k_query<COUNT, QMODE, false><<<g, FN3_Q_THREADS, smem, st>>>(p);
+}
+
+// enqueue one query tile: `ns` slots (h_slots + slot_blocks filled by the caller, or `resident` slots that
+// already live on the device — measurement hook) against candidates rows[0..n) / row_begin..row_begin+n-1.
+// Normally ONE kernel (k_query builds the query structure in shared memory itself); queries too large for
+// shared memory take k_build_query + the global-memory variant.  `split` (measurement hook) receives an event
+// recorded between the optional build kernel and k_query.
+static int enqueue_query(fn3_engine* e, const HdrTable& ht, const long long* d_rows, long long row_begin, long long n,
+                         int ns, int ceiling, bool count_bytes, const QuerySlot* resident = nullptr,
+                         cudaEvent_t split = nullptr) {
     cudaStream_t st = e->q_stream;
     const QuerySlot* d_slots = resident ? resident : e->d_slots;
     if (!resident) {
         CU(e, cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(QuerySlot) * ns, cudaMemcpyHostToDevice, st));
         e->h2d_bytes += (long long)sizeof(QuerySlot) * ns;
     }
-    const size_t bm_bytes = (size_t)e->qstate.nw * 2 * sizeof(uint32_t);
-    if (bm_bytes + 1024 <= (size_t)e->stage_limit)
-        k_build_query<true><<<ns, FN3_BUILD_THREADS, bm_bytes, st>>>(d_slots, e->qstate, e->pos_bits);
-    else
-        k_build_query<false><<<ns, FN3_BUILD_THREADS, 0, st>>>(d_slots, e->qstate, e->pos_bits);
-    e->launches += 1;
-    CU(e, cudaGetLastError());
-    return FN3_OK;
-}
-
-// the early-exit filter looks at this many leading V words per candidate (0 = filter off)
-static int filter_len_for(int ceiling) {
-    if (ceiling < 0) return 4;
-    if (ceiling >= 56) return 0;                 // the filter cannot reject cheaply: stream every row in phase B
-    return ((ceiling + 1 + 7 + 3) / 4) * 4;
-}
-
-static int enqueue_compare(fn3_engine* e, const HdrTable& ht, const long long* d_rows, long long row_begin, long long n,
-                           int ns, int ceiling, bool count_bytes, const QuerySlot* resident = nullptr) {
-    if (n <= 0) return FN3_OK;
-    CompareParams p;
-    p.hdr = ht; p.qs = e->qstate; p.rows = d_rows; p.row_begin = row_begin; p.n = n;
-    p.slots = resident ? resident : e->d_slots;
-    p.out = e->d_out; p.out_count = e->d_count; p.touched = e->d_count + 1; p.out_cap = e->out_cap;
-    p.ceiling = ceiling; p.pos_bits = e->pos_bits; p.filter_len = filter_len_for(ceiling);
-    // shared-memory staging of the query: bmpref + (touched blocks + 1) entries, sized for the largest slot
     uint32_t blocks = 0;
     for (int s = 0; s < ns; ++s) blocks = std::max(blocks, e->slot_blocks[s]);
     blocks = std::min<uint32_t>(blocks, (uint32_t)e->qstate.n_blk);
     const size_t smem = (size_t)e->qstate.nw * sizeof(uint2) + ((size_t)blocks + 1) * sizeof(QEntry);
-    const bool in_smem = smem + 1024 <= (size_t)e->stage_limit;
-    const long long groups = (n + 31) / 32;
-    const long long warps_per_cta = FN3_CMP_BLOCK / 32;
-    long long ctas = (groups + warps_per_cta - 1) / warps_per_cta;
-    long long per_sm = 4;                                         // 64 registers x 256 threads
-    if (in_smem) per_sm = std::max<long long>(1, std::min<long long>(per_sm, (long long)(228 * 1024) / (long long)(smem + 1024)));
+    const bool in_smem = smem + (size_t)e->q_static_smem + 256 <= (size_t)e->stage_limit;
+    if (!in_smem) {
+        const size_t bm_bytes = (size_t)e->qstate.nw * 2 * sizeof(uint32_t);
+        if (bm_bytes + 1024 <= (size_t)e->stage_limit)
+            k_build_query<true><<<ns, FN3_BUILD_THREADS, bm_bytes, st>>>(d_slots, e->qstate, e->pos_bits);
+        else
+            k_build_query<false><<<ns, FN3_BUILD_THREADS, 0, st>>>(d_slots, e->qstate, e->pos_bits);
+        e->launches += 1;
+        CU(e, cudaGetLastError());
+    }
+    if (split) CU(e, cudaEventRecord(split, st));
+    if (n <= 0) return FN3_OK;
+    CompareParams p;
+    p.hdr = ht; p.qs = e->qstate; p.rows = d_rows; p.row_begin = row_begin; p.n = n;
+    p.slots = d_slots;
+    p.out = e->d_out; p.out_count = e->d_count; p.touched = e->d_count + 1; p.out_cap = e->out_cap;
+    p.ceiling = ceiling; p.pos_bits = e->pos_bits; p.filter_len = filter_len_for(ceiling);
+    const bool filter = p.filter_len > 0;
+    const long long warps_per_cta = FN3_Q_THREADS / 32;
+    const long long units = filter ? (n + 31) / 32 : n;             // warp-sized work units
+    long long ctas = (units + warps_per_cta - 1) / warps_per_cta;
+    long long per_sm = 2;                                           // __launch_bounds__(512, 2)
+    if (in_smem && 2 * (smem + (size_t)e->q_static_smem + 1024) > (size_t)228 * 1024) per_sm = 1;
     const long long max_ctas = (long long)e->sm_count * per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
     dim3 g((unsigned)ctas, (unsigned)ns);
     if (in_smem) {
-        if (count_bytes) k_compare<true, true><<<g, FN3_CMP_BLOCK, smem, e->q_stream>>>(p);
-        else k_compare<false, true><<<g, FN3_CMP_BLOCK, smem, e->q_stream>>>(p);
+        if (count_bytes) launch_query<true, 1>(filter, g, smem, st, p);
+        else launch_query<false, 1>(filter, g, smem, st, p);
     } else {
-        if (count_bytes) k_compare<true, false><<<g, FN3_CMP_BLOCK, 0, e->q_stream>>>(p);
-        else k_compare<false, false><<<g, FN3_CMP_BLOCK, 0, e->q_stream>>>(p);
+        if (count_bytes) launch_query<true, 0>(filter, g, 0, st, p);
+        else launch_query<false, 0>(filter, g, 0, st, p);
     }
     e->launches += 1;
     CU(e, cudaGetLastError());
@@ -1165,10 +1349,10 @@ static int enqueue_compare(fn3_engine* e, const HdrTable& ht, const long long* d
 
 // upload a non-stored sample into scratch slot `which` (0/1); returns its header
 static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const int32_t off[7], int invalid, RowHdr* out,
-                          uint32_t* nblk = nullptr) {
+                          uint32_t* nblk = nullptr, RowHead* head_out = nullptr) {
     RowHdr h; memset(&h, 0, sizeof h);
     if (nblk) *nblk = 0;
-    if (invalid) { *out = h; return FN3_OK; }
+    if (invalid) { *out = h; if (head_out) fill_head(*head_out, h, nullptr); return FN3_OK; }
     long long o[7];
     for (int b = 0; b < 7; ++b) o[b] = off[b];
     long long w = row_words_needed(e, pos, o, 0, nblk);
@@ -1192,6 +1376,7 @@ static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const in
         for (size_t z = (size_t)w; z < need; ++z) e->stage[z] = 0;
         uint32_t* dst = e->d_scratch + (which ? e->scratch_words / 2 : 0);
         h.data = (unsigned long long)(uintptr_t)dst;
+        if (head_out) fill_head(*head_out, h, e->stage);
         CU(e, cudaMemcpyAsync(dst, e->stage, need * 4, cudaMemcpyHostToDevice, e->q_stream));
         e->h2d_bytes += (long long)need * 4;
         CU(e, cudaStreamSynchronize(e->q_stream));
@@ -1221,8 +1406,7 @@ static int run_one_vs_all(fn3_engine* e, int ceiling, const int64_t* rows, int64
     }
     if ((rc = ensure_out(e, n))) return rc;
     CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
-    if ((rc = enqueue_query_build(e, 1))) return rc;
-    if ((rc = enqueue_compare(e, ht, d_rows, 0, n, 1, ceiling, false))) return rc;
+    if ((rc = enqueue_query(e, ht, d_rows, 0, n, 1, ceiling, false))) return rc;
     // ONE device-to-host copy brings the counter and the first records; a second one only for long lists
     const long long first = std::min<long long>(n, FN3_FIRST_HITS);
     CU(e, cudaMemcpyAsync(e->h_outbuf, e->d_outbuf, FN3_OUT_HDR + (size_t)first * sizeof(EdgeRec), cudaMemcpyDeviceToHost,
@@ -1315,10 +1499,11 @@ extern "C" int fn3_pair_lists(fn3_engine* e, const int32_t* pos1, const int32_t 
     *has_dist = 0;
     RowHdr qh, ch; int rc;
     if ((rc = upload_scratch(e, 0, pos1, off1, invalid1, &qh, &e->slot_blocks[0]))) return rc;
-    if ((rc = upload_scratch(e, 1, pos2, off2, invalid2, &ch))) return rc;
+    RowHead chead;
+    if ((rc = upload_scratch(e, 1, pos2, off2, invalid2, &ch, nullptr, &chead))) return rc;
     if (qh.data == 0ull || ch.data == 0ull) return FN3_OK;   // either invalid: None (:438-442)
     // scratch header table: one chunk holding the candidate header at row 0
-    CU(e, cudaMemcpyAsync(e->d_scratch_hdr, &ch, sizeof ch, cudaMemcpyHostToDevice, e->q_stream));
+    CU(e, cudaMemcpyAsync(e->d_scratch_hdr, &chead, sizeof chead, cudaMemcpyHostToDevice, e->q_stream));
     HdrTable ht; memset(&ht, 0, sizeof ht);
     ht.chunk[0] = e->d_scratch_hdr; ht.shift = 1;
     QuerySlot& s = e->h_slots[0];
@@ -1365,8 +1550,7 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
         }
         const long long cbegin = upper_only ? min_row + 1 : 0;
         CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
-        if ((rc = enqueue_query_build(e, ns))) return rc;
-        if ((rc = enqueue_compare(e, ht, nullptr, cbegin, n_store - cbegin, ns, ceiling, false))) return rc;
+        if ((rc = enqueue_query(e, ht, nullptr, cbegin, n_store - cbegin, ns, ceiling, false))) return rc;
         CU(e, cudaMemcpyAsync(e->h_count, e->d_count, FN3_OUT_HDR, cudaMemcpyDeviceToHost, e->q_stream));
         CU(e, cudaStreamSynchronize(e->q_stream));
         e->d2h_bytes += FN3_OUT_HDR;
@@ -1514,9 +1698,7 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
         if (flush_l2) { k_fill<<<e->sm_count * 4, 512, 0, st>>>(e->d_flush, e->flush_n, (uint32_t)it); e->launches += 1; }
         e->d_count = d_pc + (size_t)it * (FN3_OUT_HDR / sizeof(unsigned long long));
         cudaEventRecord(evs[(size_t)it * 3 + 0], st);
-        if ((rc = enqueue_query_build(e, 1, d_ps + it))) break;
-        cudaEventRecord(evs[(size_t)it * 3 + 1], st);
-        if ((rc = enqueue_compare(e, ht, nullptr, 0, n_store, 1, ceiling, false, d_ps + it))) break;
+        if ((rc = enqueue_query(e, ht, nullptr, 0, n_store, 1, ceiling, false, d_ps + it, evs[(size_t)it * 3 + 1]))) break;
         cudaEventRecord(evs[(size_t)it * 3 + 2], st);
     }
     e->d_count = saved;
@@ -1538,8 +1720,7 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
         cudaMemsetAsync(d_pc, 0, (size_t)n * FN3_OUT_HDR, st);
         for (int it = 0; it < n && rc == FN3_OK; ++it) {
             e->d_count = d_pc + (size_t)it * (FN3_OUT_HDR / sizeof(unsigned long long));
-            if ((rc = enqueue_query_build(e, 1, d_ps + it))) break;
-            if ((rc = enqueue_compare(e, ht, nullptr, 0, n_store, 1, ceiling, true, d_ps + it))) break;
+            if ((rc = enqueue_query(e, ht, nullptr, 0, n_store, 1, ceiling, true, d_ps + it))) break;
         }
         e->d_count = saved;
         cudaStreamSynchronize(st);

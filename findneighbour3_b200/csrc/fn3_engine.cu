@@ -330,6 +330,7 @@ __device__ __forceinline__ void block_exscan3(uint32_t& a, uint32_t& b, uint32_t
     a = ws[warp] + ia - a; b = ws[33 + warp] + ib - b; c = ws[66 + warp] + ic - c;
 }
 
+#define FN3_BUILD_KEEP 2
 // Build the query's compact structure in shared memory from its row.  sm_bp: nw uint2, sm_en: (cap+1) QEntry.
 // Returns totals (|V_q|,|U_q|,|M_q|) in tot[3].  All threads of the CTA must call.
 __device__ __forceinline__ void build_query_smem(const QuerySlot& q, int nw, int pos_bits, uint2* sm_bp, QEntry* sm_en,
@@ -343,9 +344,13 @@ __device__ __forceinline__ void build_query_smem(const QuerySlot& q, int nw, int
         uint4* z = reinterpret_cast<uint4*>(sm_bp);
         for (int i = tid; i < nw / 2; i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    // the row is read once: up to FN3_BUILD_KEEP words per thread stay in registers for pass 4
+    uint32_t keep[FN3_BUILD_KEEP];
+#pragma unroll
+    for (int r = 0; r < FN3_BUILD_KEEP; ++r) { const uint32_t i = tid + r * nt; keep[r] = i < e5 ? __ldg(d + i) : 0u; }
     __syncthreads();
-    for (uint32_t i = tid; i < e5; i += nt) {                   // 1. touched blocks
-        const uint32_t w = __ldg(d + i);
+    for (uint32_t i = tid, r = 0; i < e5; i += nt, ++r) {       // 1. touched blocks
+        const uint32_t w = r < FN3_BUILD_KEEP ? keep[r < FN3_BUILD_KEEP ? r : 0] : __ldg(d + i);
         if (i < e3) {
             const uint32_t blk = w >> 5;
             atomicOr(&sm_bp[blk >> 5].x, 1u << (blk & 31u));
@@ -367,8 +372,8 @@ __device__ __forceinline__ void build_query_smem(const QuerySlot& q, int nw, int
         for (uint32_t i = tid; i < 2u * (nE + 1u); i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    for (uint32_t i = tid; i < e5; i += nt) {                   // 4. per-position masks
-        const uint32_t w = __ldg(d + i);
+    for (uint32_t i = tid, r = 0; i < e5; i += nt, ++r) {       // 4. per-position masks
+        const uint32_t w = r < FN3_BUILD_KEEP ? keep[r < FN3_BUILD_KEEP ? r : 0] : __ldg(d + i);
         if (i < e3) {
             const uint32_t blk = w >> 5;
             const uint2 bp = sm_bp[blk >> 5];
@@ -416,17 +421,20 @@ __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __r
                                             uint32_t e2, uint32_t e3, uint32_t e4, uint32_t e5, int k, int pos_bits,
                                             uint32_t pmask, int lane, unsigned long long& touched) {
     Tally t; t.S1 = 0; t.qdefV = 0; t.qdefU = 0; t.nNc = 0; t.nNU = 0; t.nNM = 0; t.dead = false;
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if ((uint32_t)lane * 4u < e5) { cur = ld_stream_v4(d + lane * 4); if (COUNT) touched += 16; }
-    for (uint32_t base = 0; base < e5; base += 128) {
+    // 256 words per warp step (two 128-bit loads per lane), the next 256 already in flight
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+    if ((uint32_t)lane * 4u < e5) { c0 = ld_stream_v4(d + lane * 4); if (COUNT) touched += 16; }
+    if ((uint32_t)lane * 4u + 128u < e5) { c1 = ld_stream_v4(d + lane * 4 + 128); if (COUNT) touched += 16; }
+    for (uint32_t base = 0; base < e5; base += 256) {
         const uint32_t idx = base + lane * 4;
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (idx + 128u < e5) { nxt = ld_stream_v4(d + idx + 128); if (COUNT) touched += 16; }   // next chunk in flight
-        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        if (idx + 256u < e5) { n0 = ld_stream_v4(d + idx + 256); if (COUNT) touched += 16; }
+        if (idx + 384u < e5) { n1 = ld_stream_v4(d + idx + 384); if (COUNT) touched += 16; }
+        const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
         int mism = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t ii = idx + j;
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t ii = idx + (j & 3) + ((j >> 2) << 7);
             if (ii < e3) {
                 const uint32_t r = look_v(qv, w[j], (ii >= e0) + (ii >= e1) + (ii >= e2));
                 mism += r & 1u;
@@ -446,7 +454,7 @@ __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __r
             t.S1 += __reduce_add_sync(0xffffffffu, mism);
             if (t.S1 > k) { t.dead = true; break; }
         }
-        cur = nxt;
+        c0 = n0; c1 = n1;
     }
     return t;
 }
@@ -520,17 +528,18 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, 2) k_query(const CompareParams 
                 row = p.rows ? p.rows[ci] : p.row_begin + ci;
                 if (row != qs.exclude && row > qs.skip_le) {
                     const uint4* hp = reinterpret_cast<const uint4*>(p.hdr.chunk[row >> p.hdr.shift] + (row & hmask));
+                    // header and head words are requested together: ONE memory round trip per candidate
                     h0 = __ldg(hp); h1 = __ldg(hp + 1);
+                    uint4 f[FN3_HEAD_WORDS / 4];
+#pragma unroll
+                    for (int j = 0; j < FN3_HEAD_WORDS / 4; ++j) {
+                        f[j] = make_uint4(0, 0, 0, 0);
+                        if (4 * j < p.filter_len) { f[j] = __ldg(hp + 2 + j); if (COUNT) touched += 16; }
+                    }
                     if (COUNT) touched += 32;
                     if ((h0.x | h0.y) != 0u) {             // data pointer 0: invalid or removed candidate
                         const uint32_t e0 = h0.z, e1 = h0.w, e2 = h1.x, e3 = h1.y;
                         const uint32_t lim = min(e3, (uint32_t)p.filter_len);
-                        uint4 f[FN3_HEAD_WORDS / 4];
-#pragma unroll
-                        for (int j = 0; j < FN3_HEAD_WORDS / 4; ++j) {
-                            f[j] = make_uint4(0, 0, 0, 0);
-                            if ((uint32_t)(4 * j) < lim) { f[j] = __ldg(hp + 2 + j); if (COUNT) touched += 16; }
-                        }
                         int S = 0;
 #pragma unroll
                         for (int j = 0; j < FN3_HEAD_WORDS / 4; ++j) {

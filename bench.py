@@ -312,7 +312,7 @@ def main():
     eng = Engine(coll.genome_length, local)
     eng.append_bulk(coll.pos, coll.off, coll.invalid)
     K, W = args.steps, args.warmup
-    queries = make_queries(common, 2 * (K + W))      # the same new samples on every rank
+    queries = make_queries(common, 3 * (K + W))      # the same new samples on every rank
     t_gen = time.time() - t_gen
 
     # ---- leg 1: device-resident value ------------------------------------------------------------
@@ -375,37 +375,48 @@ def main():
     fresh = queries[K + W:]
     ceiling = args.ceiling
 
-    def e2e_step(sample):
+    def step_fused(sample):
+        p, o, inv = sample                          # server insert(): persist + mcompare, one ABI call
+        return eng.insert_query(p, o, inv, ceiling)[1]
+
+    def step_two_calls(sample):
         p, o, inv = sample
         row = eng.append(p, o, inv)                 # persist: pack -> pinned staging -> H2D
         return eng.one_vs_all(row, ceiling)         # mcompare: build + compare -> D2H of the neighbour records
 
-    lat = []
-    for s in fresh[:W]:
-        e2e_step(s)
-    st0 = eng.stats()
-    barrier()
-    t0 = time.perf_counter()
-    n_neighbours = 0
-    for s in fresh[W:W + K]:
-        t1 = time.perf_counter()
-        hits = e2e_step(s)
-        lat.append(time.perf_counter() - t1)
-        n_neighbours += len(hits)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    barrier()
+    def run_e2e(step, samples):
+        lat = []
+        for s in samples[:W]:
+            step(s)
+        st0 = eng.stats()
+        barrier()
+        t0 = time.perf_counter()
+        n_neighbours = 0
+        for s in samples[W:W + K]:
+            t1 = time.perf_counter()
+            hits = step(s)
+            lat.append(time.perf_counter() - t1)
+            n_neighbours += len(hits)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        barrier()
+        st1 = eng.stats()
+        t = max_over_ranks(t)
+        comps = sum_over_ranks(float(sum(range(st0["n_rows"], st0["n_rows"] + K))))   # the store grows by one per step
+        return {"value": comps / t, "unit": UNIT,
+                "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) / K,
+                "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) / K,
+                "ms_per_step": 1e3 * t / K,
+                "p50_ms": 1e3 * statistics.median(lat), "p95_ms": 1e3 * sorted(lat)[int(0.95 * (len(lat) - 1))],
+                "neighbours_per_query": n_neighbours / K}
+
+    half = len(fresh) // 2
+    e2e_two = run_e2e(step_two_calls, fresh[:half])
+    e2e_two["call"] = "fn3_append + fn3_one_vs_all via ctypes (seqComparer.persist, then seqComparer.mcompare)"
+    e2e = run_e2e(step_fused, fresh[half:])
+    e2e["call"] = "fn3_insert_query via ctypes (server insert(): persist + mcompare, findNeighbour3-server.py:516+530)"
+    e2e["two_calls"] = e2e_two
     clocks = sampler.stop()
-    st1 = eng.stats()
-    t_e2e = max_over_ranks(t_e2e)
-    e2e_comps = sum_over_ranks(float(sum(range(st0["n_rows"], st0["n_rows"] + K))))   # store grows by one per step
-    e2e = {"value": e2e_comps / t_e2e, "unit": UNIT,
-           "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) / K,
-           "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) / K,
-           "ms_per_step": 1e3 * t_e2e / K,
-           "p50_ms": 1e3 * statistics.median(lat), "p95_ms": 1e3 * sorted(lat)[int(0.95 * (len(lat) - 1))],
-           "neighbours_per_query": n_neighbours / K,
-           "call": "fn3_append + fn3_one_vs_all via ctypes (seqComparer.persist + mcompare sit on these)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

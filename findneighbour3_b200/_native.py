@@ -51,6 +51,7 @@ SIGNATURES = {
     "fn3_stats_get": (C.c_int, [_vp, C.POINTER(Stats)]),
     "fn3_row_get": (C.c_int, [_vp, C.c_int64, _i32p, C.c_int64, _i32p, _i32p, _i64p]),
     "fn3_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, _i64p, C.c_int64, C.POINTER(Hit), C.c_int64, _i64p]),
+    "fn3_insert_query": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, C.POINTER(Hit), C.c_int64, _i64p]),
     "fn3_lists_vs_all": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, C.c_int64,
                                    C.POINTER(Hit), C.c_int64, _i64p]),
     "fn3_all_vs_all": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,

@@ -1468,6 +1468,66 @@ extern "C" int fn3_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling,
     return run_one_vs_all(e, ceiling, rows, n_rows, n_store, ht, out, cap, n_out);
 }
 
+// insert() of the reference's server (findNeighbour3-server.py:516 persist + :530 mcompare) as ONE call on ONE
+// stream with ONE host synchronisation: row data + row head + query slot go host->device, k_query runs against
+// every earlier row, the neighbour records come back.
+extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
+                                int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out) {
+    if (!e || !n_out || !out_row || (cap > 0 && !out) || (!invalid && !off))
+        return set_err(e, FN3_EARG, "fn3_insert_query: bad arguments");
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    HdrTable ht; long long row; RowHdr h; memset(&h, 0, sizeof h);
+    uint32_t nblk = 0;
+    {
+        std::lock_guard<std::mutex> g(e->store_mu);
+        long long o[7] = {0, 0, 0, 0, 0, 0, 0};
+        if (!invalid) for (int b = 0; b < 7; ++b) o[b] = off[b];
+        const long long w = row_words_needed(e, pos, o, invalid, &nblk);
+        if (w < 0) return FN3_EARG;
+        size_t need = ((size_t)w + 3) & ~(size_t)3; if (need == 0) need = 4;
+        int rc = ensure_stage(e, need, 1);
+        if (rc) return rc;
+        uint32_t* dbase = nullptr;
+        if ((rc = arena_alloc(e, need, &dbase))) return rc;
+        row = e->n_rows;
+        if ((rc = ensure_hdr_chunk(e, row))) return rc;
+        if (invalid) memset(e->stage, 0, need * 4);
+        else {
+            pack_row(e, pos, o, e->stage, h.end);
+            for (size_t z = (size_t)w; z < need; ++z) e->stage[z] = 0;
+            h.data = (unsigned long long)(uintptr_t)dbase;
+        }
+        fill_head(e->stage_hdr[0], h, e->stage);
+        // the header chunk may have just been created (zeroed on copy_stream): order q_stream behind it
+        CU(e, cudaStreamSynchronize(e->copy_stream));
+        CU(e, cudaMemcpyAsync(dbase, e->stage, need * 4, cudaMemcpyHostToDevice, e->q_stream));
+        CU(e, cudaMemcpyAsync(e->hdr_chunks[(size_t)(row >> e->hdr_shift)] + (row & ((1ll << e->hdr_shift) - 1)),
+                              e->stage_hdr, sizeof(RowHead), cudaMemcpyHostToDevice, e->q_stream));
+        e->h2d_bytes += (long long)need * 4 + (long long)sizeof(RowHead);
+        // the pinned staging buffers are reused by the next append: wait until the copies have left them.
+        // (q_stream is otherwise idle here; this is the copy latency only, the kernel is queued below.)
+        e->h_hdr.push_back(h);
+        e->h_flags.push_back(invalid ? 1 : 0);
+        const uint32_t np = invalid ? 0u : (uint32_t)(o[6] - o[0]);
+        e->h_npos.push_back(np);
+        e->h_nblk.push_back(nblk);
+        e->positions += np;
+        e->n_live++; if (invalid) e->n_invalid++;
+        e->n_rows = row + 1;
+        fill_hdr_table(e, ht);
+        QuerySlot& s = e->h_slots[0];
+        s.hdr = h; s.row = row; s.skip_le = -1; s.exclude = row; s.pad = 0;
+        e->slot_blocks[0] = nblk;
+        *out_row = row;
+        // run the query while still holding store_mu: the staging buffers must not be repacked by a concurrent
+        // append until the stream has consumed them (the synchronise inside run_one_vs_all covers that)
+        rc = run_one_vs_all(e, ceiling, nullptr, 0, row, ht, out, cap, n_out);
+        if (invalid || row == 0) CU(e, cudaStreamSynchronize(e->q_stream));   // paths that return without a sync
+        return rc;
+    }
+}
+
 extern "C" int fn3_lists_vs_all(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
                                 const int64_t* rows, int64_t n_rows, fn3_hit* out, int64_t cap, int64_t* n_out) {
     if (!e || !n_out || (cap > 0 && !out) || (!invalid && !off)) return set_err(e, FN3_EARG, "fn3_lists_vs_all: bad arguments");

@@ -45,6 +45,7 @@ class Engine:
         self.device = int(device)
         self._hits = np.empty(4096, dtype=HIT_DTYPE)
         self._edges = np.empty(1 << 16, dtype=EDGE_DTYPE)
+        self._n_rows = 0          # rows appended through this object (sizes the hit buffer without an ABI call)
 
     # -- plumbing -------------------------------------------------------------------------
     def close(self):
@@ -84,6 +85,7 @@ class Engine:
                 raise ValueError("off must have 7 entries")
             rc = self._lib.fn3_append(self._h, _ptr(pos, _i32p), _ptr(off, _i32p), 0, C.byref(row))
         self._check(rc)
+        self._n_rows = max(self._n_rows, row.value + 1)
         return row.value
 
     def append_bulk(self, pos, off, invalid=None):
@@ -99,6 +101,7 @@ class Engine:
         first = C.c_int64(-1)
         rc = self._lib.fn3_append_bulk(self._h, n, _ptr(pos, _i32p), _ptr(off, _i64p), _ptr(inv, _u8p), C.byref(first))
         self._check(rc)
+        self._n_rows = max(self._n_rows, first.value + n)
         return first.value
 
     def remove(self, row):
@@ -167,7 +170,7 @@ class Engine:
     def one_vs_all(self, query_row, ceiling, rows=None):
         """mcompare: stored row vs all (or `rows`); -> structured array of survivors (copy)."""
         rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
-        n_cand = self.stats()["n_rows"] if rows_a is None else rows_a.size
+        n_cand = self._n_rows if rows_a is None else rows_a.size
         buf = self._hit_buf(max(int(n_cand), 1))
         n_out = C.c_int64(0)
         rc = self._lib.fn3_one_vs_all(self._h, int(query_row), int(ceiling), _ptr(rows_a, _i64p),
@@ -176,9 +179,26 @@ class Engine:
         self._check(rc)
         return buf[: n_out.value].copy()
 
+    def insert_query(self, pos, off, invalid, ceiling):
+        """persist + mcompare in one ABI call -> (row, structured array of survivors among the earlier rows)."""
+        buf = self._hit_buf(max(self._n_rows + 1, 1))
+        row = C.c_int64(-1)
+        n_out = C.c_int64(0)
+        if invalid:
+            pos_a, off_a = None, None
+        else:
+            pos_a, off_a = _as_i32(pos), _as_i32(off)
+        rc = self._lib.fn3_insert_query(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
+                                        int(ceiling), C.byref(row), buf.ctypes.data_as(C.POINTER(N.Hit)), buf.size,
+                                        C.byref(n_out))
+        if row.value >= 0:
+            self._n_rows = max(self._n_rows, row.value + 1)
+        self._check(rc)
+        return row.value, buf[: n_out.value].copy()
+
     def lists_vs_all(self, pos, off, invalid, ceiling, rows=None):
         rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
-        n_cand = self.stats()["n_rows"] if rows_a is None else rows_a.size
+        n_cand = self._n_rows if rows_a is None else rows_a.size
         buf = self._hit_buf(max(int(n_cand), 1))
         n_out = C.c_int64(0)
         if invalid:

@@ -134,6 +134,13 @@ int fn3_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling,
                    const int64_t* rows, int64_t n_rows,
                    fn3_hit* out, int64_t cap, int64_t* n_out);
 
+/* insert() of the reference's server — persist(obj, guid) immediately followed by mcompare(guid)
+ * (findNeighbour3-server.py:516, :530) — as ONE call: the sample is appended (*out_row receives its row) and
+ * compared against every EARLIER row; one stream, one host synchronisation.  The row stays inserted even if
+ * the call then fails with FN3_ECAPACITY (repeat the query with fn3_one_vs_all and a larger buffer). */
+int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
+                     int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out);
+
 /* Same, for a query that is NOT in the store (lists as in fn3_append): the sharded
  * host layer uses it on the ranks that do not own the query row. */
 int fn3_lists_vs_all(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid,

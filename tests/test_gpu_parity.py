@@ -301,6 +301,26 @@ def test_incremental_insert_then_query_matches_bulk(monkeypatch):
     eng.close()
 
 
+def test_insert_query_fused_call_matches_two_calls():
+    """fn3_insert_query (persist + mcompare in one ABI call) == fn3_append followed by fn3_one_vs_all."""
+    from findneighbour3_b200.engine import Engine
+    from oracle import c_oracle
+    coll = _synthetic(5, 16, 250000, 44, k1=300, s=3.0, n_blocks=8, n_mean=2500, m_mean=4, rule="any", p_invalid=0.05)
+    a, b = Engine(coll.genome_length, 0), Engine(coll.genome_length, 0)
+    for i in range(coll.n):
+        p, o, inv = coll.lists(i)
+        row, hits = a.insert_query(p, o, inv, 20)
+        assert row == i == b.append(p, o, inv)
+        two = hits_to_dict(b.one_vs_all(i, 20))
+        assert hits_to_dict(hits) == two
+        if i % 9 == 0:
+            sub = coll.subset(np.arange(i + 1))
+            assert two == c_oracle.one_vs_all(sub.pos, sub.off, sub.invalid, i, 20)
+    assert a.stats()["n_rows"] == b.stats()["n_rows"] == coll.n
+    a.close()
+    b.close()
+
+
 def test_properties_at_scale():
     """size-independent properties on a TB-sized genome: symmetry of the distance, zero self distance,
     hits at a low ceiling are a subset of hits at a higher one with identical values, monotone counts."""

@@ -375,7 +375,14 @@ def main():
     fresh = queries[K + W:]
     ceiling = args.ceiling
 
+    sharded = None
+    if world > 1:
+        from findneighbour3_b200.sharded import ShardedStore
+        sharded = ShardedStore(eng, local_rows=eng.stats()["n_rows"])
+
     def step_fused(sample):
+        if sharded is not None:                     # N ranks: NCCL broadcast of the sample, local kernels, NCCL all-gather
+            return sharded.insert_query(sample if rank == 0 else None, ceiling)[1]
         p, o, inv = sample                          # server insert(): persist + mcompare, one ABI call
         return eng.insert_query(p, o, inv, ceiling)[1]
 
@@ -392,17 +399,21 @@ def main():
         barrier()
         t0 = time.perf_counter()
         n_neighbours = 0
+        comps = 0
+        rows_now = st0["n_rows"]
         for s in samples[W:W + K]:
             t1 = time.perf_counter()
             hits = step(s)
             lat.append(time.perf_counter() - t1)
             n_neighbours += len(hits)
+            comps += rows_now                        # candidates this rank compared in this step
+            rows_now = eng._n_rows
         torch.cuda.synchronize()
         t = time.perf_counter() - t0
         barrier()
         st1 = eng.stats()
         t = max_over_ranks(t)
-        comps = sum_over_ranks(float(sum(range(st0["n_rows"], st0["n_rows"] + K))))   # the store grows by one per step
+        comps = sum_over_ranks(float(comps))
         return {"value": comps / t, "unit": UNIT,
                 "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) / K,
                 "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) / K,
@@ -411,11 +422,17 @@ def main():
                 "neighbours_per_query": n_neighbours / K}
 
     half = len(fresh) // 2
-    e2e_two = run_e2e(step_two_calls, fresh[:half])
-    e2e_two["call"] = "fn3_append + fn3_one_vs_all via ctypes (seqComparer.persist, then seqComparer.mcompare)"
+    e2e_two = None
+    if world == 1:
+        e2e_two = run_e2e(step_two_calls, fresh[:half])
+        e2e_two["call"] = "fn3_append + fn3_one_vs_all via ctypes (seqComparer.persist, then seqComparer.mcompare)"
     e2e = run_e2e(step_fused, fresh[half:])
-    e2e["call"] = "fn3_insert_query via ctypes (server insert(): persist + mcompare, findNeighbour3-server.py:516+530)"
-    e2e["two_calls"] = e2e_two
+    e2e["call"] = ("fn3_insert_query via ctypes (server insert(): persist + mcompare, findNeighbour3-server.py:516+530)"
+                   if world == 1 else
+                   "ShardedStore.insert_query: NCCL broadcast of the sample, fn3_insert_query on the owner rank / "
+                   "fn3_lists_vs_all on the others, NCCL all-gather of the neighbour blocks")
+    if e2e_two is not None:
+        e2e["two_calls"] = e2e_two
     clocks = sampler.stop()
 
     line = {

@@ -1,0 +1,89 @@
+"""not-gpu: the N>1 host path (findneighbour3_b200/sharded.py) with world_size 2 over gloo on the CPU.
+The per-rank engine is the oracle-backed stand-in of tests/fake_engine.py; what is under test is the sharding:
+ownership i % G, broadcast of the new sample, all-gather of the neighbour blocks (incl. block overflow),
+global id mapping, shard bulk load and queries on stored samples owned by either rank."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_engine import OracleEngine
+        from findneighbour3_b200 import synth
+        from findneighbour3_b200.sharded import ShardedStore
+        from oracle import c_oracle
+
+        L = 60000
+        coll = synth.make_collection(4, 12, genome_length=L, seed=8, k1=80, s=2.0, n_blocks=4, n_mean=300, m_mean=3,
+                                     rule="any", p_invalid=0.05)
+        # (1) bulk load: rank r takes samples r, r+G, ... of the first 24
+        base = 24
+        mine = np.arange(rank, base, world)
+        shard = coll.subset(mine)
+        store = ShardedStore(OracleEngine(L), max_hits=2)          # tiny block: forces the overflow round
+        store.load_shard(shard.pos, shard.off, shard.invalid)
+        assert store.n_global == base
+        # (2) streaming inserts, sample known on rank 0 only
+        results = {}
+        for i in range(base, coll.n):
+            sample = coll.lists(i) if rank == 0 else None
+            gid, hits = store.insert_query(sample, 20)
+            assert gid == i
+            results[gid] = hits
+        # (3) queries on stored samples owned by rank 0 and by rank 1
+        stored = {g: store.one_vs_all(g, 20) for g in (0, 1, 6, 31)}
+        # reference: one flat store in global order
+        ok = True
+        for gid, hits in results.items():
+            sub = coll.subset(np.arange(gid + 1))
+            want = c_oracle.one_vs_all(sub.pos, sub.off, sub.invalid, gid, 20)
+            ok &= hits == want
+        for g, hits in stored.items():
+            want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, g, 20)
+            ok &= hits == want
+        q.put((rank, bool(ok), len(results), sum(len(h) for h in results.values())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_store_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in out), out
+    assert out[0][2] == out[1][2] == 24 and out[0][3] == out[1][3] > 0
+
+
+def test_sharded_store_single_rank():
+    sys.path.insert(0, HERE)
+    from fake_engine import OracleEngine
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.sharded import ShardedStore
+    from oracle import c_oracle
+    coll = synth.make_collection(3, 8, genome_length=30000, seed=2, k1=50, s=2.0, n_blocks=3, n_mean=200, rule="any")
+    store = ShardedStore(OracleEngine(30000))
+    for i in range(coll.n):
+        gid, hits = store.insert_query(coll.lists(i), 20)
+        sub = coll.subset(np.arange(i + 1))
+        assert gid == i and hits == c_oracle.one_vs_all(sub.pos, sub.off, sub.invalid, i, 20)
+    assert ShardedStore.block_rows(10, 1, 4) == dict(row_begin=0, row_end=10, stride=4, phase=1)

@@ -264,12 +264,25 @@ def run_reference(args, rank, world):
         line["cpu_baseline_native"] = cpu_c_oracle(coll, queries[:3], args.ceiling, 10.0, os.cpu_count() or 1)
     except Exception as ex:       # pragma: no cover
         line["cpu_baseline_native"] = {"error": str(ex)}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else that writes to fd 1 (NCCL's version banner,
+    library chatter) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -461,7 +474,7 @@ def main():
         except Exception as ex:   # pragma: no cover
             line["cpu_baseline"] = {"error": str(ex)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

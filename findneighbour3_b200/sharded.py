@@ -27,6 +27,12 @@ class ShardedStore:
         backend = dist.get_backend(group) if dist.is_initialized() else "gloo"
         self.dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         self.max_hits = int(max_hits)
+        self.bcast_cap = 1 << 15                 # positions carried by the single fixed-size broadcast
+        self._bbuf = torch.zeros(9 + self.bcast_cap, dtype=torch.int32)
+        self._dbuf = None
+        if self.dev.type == "cuda":
+            self._bbuf = self._bbuf.pin_memory()
+            self._dbuf = torch.zeros(9 + self.bcast_cap, dtype=torch.int32, device=self.dev)
         # `local_rows`: rows the engine already holds (every rank the same number, placed as by load_shard)
         self._local_rows = int(local_rows)
         self.n_global = self._local_rows * self.world       # samples inserted so far (same value on every rank)
@@ -55,27 +61,42 @@ class ShardedStore:
         return first
 
     # -- collectives ------------------------------------------------------------------------
-    def _bcast_sample(self, sample):
-        """rank 0's (pos, off, invalid) -> every rank.  Two broadcasts: an 9-int header, then the positions."""
+    def _bcast_sample(self, sample, src=0):
+        """`src`'s (pos, off, invalid) -> every rank, in ONE broadcast of a fixed-size buffer
+        [n, off[0..6], invalid | positions ...] (a second one only for samples beyond `self.bcast_cap`)."""
         if self.world == 1:
             return sample
-        head = torch.zeros(9, dtype=torch.int32)
-        if self.rank == 0:
+        cap = self.bcast_cap
+        buf = self._bbuf
+        n = 0
+        if self.rank == src:
             pos, off, invalid = sample
-            head[0] = 0 if invalid else len(pos)
-            head[1:8] = torch.from_numpy(np.asarray(off, dtype=np.int32)) if not invalid else 0
-            head[8] = 1 if invalid else 0
-        head = head.to(self.dev)
-        dist.broadcast(head, src=0, group=self.group)
-        head = head.cpu()
-        n = int(head[0])
-        payload = torch.zeros(max(n, 1), dtype=torch.int32)
-        if self.rank == 0 and n:
-            payload[:n] = torch.from_numpy(np.ascontiguousarray(sample[0], dtype=np.int32))
-        payload = payload.to(self.dev)
-        dist.broadcast(payload, src=0, group=self.group)
-        pos = payload.cpu().numpy()[:n].copy()
-        return pos, head[1:8].numpy().astype(np.int32), bool(head[8])
+            n = 0 if invalid else len(pos)
+            buf[0] = n
+            buf[1:8] = 0 if invalid else torch.from_numpy(np.asarray(off, dtype=np.int32))
+            buf[8] = 1 if invalid else 0
+            m = min(n, cap)
+            if m:
+                buf[9:9 + m] = torch.from_numpy(np.ascontiguousarray(pos[:m], dtype=np.int32))
+        if self.dev.type == "cuda":
+            dbuf = self._dbuf
+            dbuf.copy_(buf, non_blocking=True)
+            dist.broadcast(dbuf, src=src, group=self.group)
+            buf.copy_(dbuf)                       # synchronises
+        else:
+            dist.broadcast(buf, src=src, group=self.group)
+        n = int(buf[0])
+        off = buf[1:8].numpy().astype(np.int32)
+        invalid = bool(buf[8])
+        pos = buf[9:9 + min(n, cap)].numpy().copy()
+        if n > cap:                               # rare: a sample larger than the fixed buffer
+            rest = torch.zeros(n - cap, dtype=torch.int32)
+            if self.rank == src:
+                rest[:] = torch.from_numpy(np.ascontiguousarray(sample[0][cap:], dtype=np.int32))
+            rest = rest.to(self.dev)
+            dist.broadcast(rest, src=src, group=self.group)
+            pos = np.concatenate([pos, rest.cpu().numpy()])
+        return pos, off, invalid
 
     def _all_gather_i64(self, t):
         if self.world == 1:
@@ -132,31 +153,9 @@ class ShardedStore:
         own = self.owner(gid) == self.rank
         if self.world == 1:
             return self._gather_hits(self.engine.one_vs_all(self.local_row(gid), ceiling))
-        # route through rank 0's broadcast: the owner first hands the lists to rank 0 (or is rank 0)
-        sample = None
         src = self.owner(gid)
-        if src == 0:
-            if own:
-                sample = self.engine.row_get(self.local_row(gid))
-        else:
-            head = torch.zeros(9, dtype=torch.int32)
-            if own:
-                p, o, inv = self.engine.row_get(self.local_row(gid))
-                head[0] = len(p)
-                head[1:8] = torch.from_numpy(np.asarray(o, dtype=np.int32))
-                head[8] = 1 if inv else 0
-            head = head.to(self.dev)
-            dist.broadcast(head, src=src, group=self.group)
-            head = head.cpu()
-            n = int(head[0])
-            payload = torch.zeros(max(n, 1), dtype=torch.int32)
-            if own and n:
-                payload[:n] = torch.from_numpy(np.ascontiguousarray(p, dtype=np.int32))
-            payload = payload.to(self.dev)
-            dist.broadcast(payload, src=src, group=self.group)
-            if self.rank == 0:
-                sample = (payload.cpu().numpy()[:n].copy(), head[1:8].numpy().astype(np.int32), bool(head[8]))
-        pos, off, invalid = self._bcast_sample(sample)
+        sample = self.engine.row_get(self.local_row(gid)) if own else None
+        pos, off, invalid = self._bcast_sample(sample, src=src)
         if own:
             hits = self.engine.one_vs_all(self.local_row(gid), ceiling)
         else:

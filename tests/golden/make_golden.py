@@ -293,7 +293,55 @@ def make_consensus():
     dump("consensus.json", out)
 
 
+def make_msa():
+    """multi_sequence_alignment outputs (seqComparer.py:691-1128; tests 45a-47c) on cases whose result does not depend
+    on set iteration order (the reference samples `sample_size` guids from an unordered set)."""
+    def norm(v):
+        if isinstance(v, (np.floating, float)):
+            return float(v)
+        if isinstance(v, (np.integer,)):
+            return int(v)
+        return v
+
+    out = []
+    ref = "GGGGGG"
+    fam_n = ["AAACGN", "CCCCGN", "TTTCGN", "GGGGGN", "NNNCGN", "ACTCGN", "TCTNGN"]
+    fam_m = ["AAACGY", "CCCCGY", "TTTCGY", "GGGGGY", "NNNCGY", "ACTCGY", "TCTQGY"]
+    for label, originals, maxNs, reps, kwargs in (
+            ("45a", fam_n, 1e8, 1, dict()),
+            ("45b", fam_n[:6] + ["TCTGGN"], 3, 1, dict()),
+            ("47c", fam_n, 3, 6, dict(expected_p1=0.995, sample_size=42)),
+            ("47b2", fam_m, 3, 6, dict(uncertain_base_type="M", sample_size=42)),
+            ("47a_nm", fam_n, 1e8, 6, dict(uncertain_base_type="N_or_M", sample_size=42))):
+        sc = REF.seqComparer(maxNs=maxNs, reference=ref, snpCeiling=10)
+        names = []
+        n = 0
+        for _ in range(reps):
+            for o in originals:
+                n += 1
+                g = "{0}-{1}".format(o, n)
+                sc.persist(sc.compress(o), guid=g)
+                names.append(g)
+        sel = names[0:8] if reps > 1 else names
+        res = sc.multi_sequence_alignment(sel, output="dict", **kwargs)
+        clean = {}
+        for k, v in res.items():
+            if isinstance(v, dict):
+                clean[k] = {kk: ([norm(x) for x in vv] if isinstance(vv, list) else norm(vv)) for kk, vv in v.items()}
+            else:
+                clean[k] = [norm(x) for x in v]
+        out.append({"label": label, "ref": ref, "maxNs": maxNs, "originals": originals, "reps": reps,
+                    "select": sel, "kwargs": kwargs, "got": clean})
+    sc = REF.seqComparer(maxNs=3, reference=ref, snpCeiling=10)
+    sc.persist(sc.compress("NNNCGN"), guid="NNNCGN-1")
+    assert sc.multi_sequence_alignment(["NNNCGN-1"]) is None
+    out.append({"label": "45c", "ref": ref, "maxNs": 3, "originals": ["NNNCGN"], "reps": 1, "select": ["NNNCGN-1"],
+                "kwargs": {}, "got": None})
+    dump("msa.json", out)
+
+
 if __name__ == "__main__":
+    make_msa()
     make_kat()
     make_compress()
     make_random_pairs()

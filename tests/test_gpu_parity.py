@@ -381,3 +381,41 @@ def test_threads_append_while_querying():
     full = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, 0, 20)
     assert hits_to_dict(eng.one_vs_all(0, 20)) == full
     eng.close()
+
+
+def test_msa_golden():
+    """multi_sequence_alignment / mixPORE statistics (seqComparer.py:691-1128) against the reference's outputs."""
+    import math
+    for case in golden("msa.json"):
+        sc = _sc(case["ref"], case["maxNs"], 10)
+        n = 0
+        for _ in range(case["reps"]):
+            for o in case["originals"]:
+                n += 1
+                sc.persist(sc.compress(o), guid="{0}-{1}".format(o, n))
+        res = sc.multi_sequence_alignment(case["select"], output="dict", **case["kwargs"])
+        want = case["got"]
+        if want is None:
+            assert res is None
+            continue
+        assert set(res.keys()) == set(want.keys()), case["label"]
+        for k, v in want.items():
+            got = res[k]
+            if isinstance(v, dict):
+                assert set(got.keys()) == set(v.keys()), (case["label"], k)
+                for g, x in v.items():
+                    y = got[g]
+                    if isinstance(x, float) and y is not None:
+                        assert math.isclose(float(y), x, rel_tol=1e-12, abs_tol=1e-15) or (math.isnan(x) and math.isnan(float(y))), (case["label"], k, g, x, y)
+                    elif isinstance(x, list):
+                        assert list(y) == x, (case["label"], k, g)
+                    else:
+                        assert (y is None and x is None) or y == x, (case["label"], k, g, x, y)
+            else:
+                assert list(got) == v, (case["label"], k)
+        df = sc.multi_sequence_alignment(case["select"], output="df", **case["kwargs"])
+        expected_cols = set(['what_tested', 'aligned_seq', 'aligned_seq_len', 'allN', 'alignN', 'allM', 'alignM', 'allN_or_M',
+                             'alignN_or_M', 'p_value1', 'p_value2', 'p_value3', 'p_value4', 'observed_proportion',
+                             'expected_proportion1', 'expected_proportion2', 'expected_proportion3', 'expected_proportion4'])
+        assert set(df.columns.values) == expected_cols
+        assert len(df.index) == len(want["guid2msa_seq"])

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libfn3.so")
 SRC = [os.path.join(HERE, "csrc", "fn3_engine.cu")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("fn3_types.h", "fn3_kernels.cuh", "fn3_compress.cuh")]
 HDR = [os.path.join(ROOT, "include", "fn3.h")]
 
 NVCC_FLAGS = [
@@ -34,7 +35,7 @@ def _stale(target, deps):
 
 def build_native(force=False, verbose=True):
     """Compile libfn3.so for sm_100a.  Returns the path."""
-    if not force and not _stale(LIB, SRC + HDR):
+    if not force and not _stale(LIB, SRC + HDR + DEPS):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):

@@ -1,0 +1,499 @@
+// fn3_kernels.cuh — sm_100a kernels of the SNV-distance engine: query build, k_query (the compare kernel),
+// head scatter.  Included by fn3_engine.cu only.
+//
+// Reference being replaced (davidhwyllie/findNeighbour3, src/seqComparer.py):
+//   countDifferences :424-458, countDifferences_byKey + _setStats :382-421/:354-380, mcompare :149-172.
+#pragma once
+#include "fn3_types.h"
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 ld_stream_v4(const uint32_t* p) {
+    // candidate row data is read once per comparison: do not let it displace anything in L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t lowmask(uint32_t k) { return (1u << k) - 1u; }    // k in 0..31
+
+// block-wide exclusive scan of one value per thread (blockDim.x multiple of 32, <= 1024);
+// ws = 33 words of shared scratch; *total receives the block total.
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* ws, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();                       // ws may still be read from a previous call
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t a = lane < nwarp ? ws[lane] : 0u, i2 = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, i2, o); if (lane >= o) i2 += t; }
+        ws[lane] = i2 - a;
+        if (lane == 31) ws[32] = i2;
+    }
+    __syncthreads();
+    *total = ws[32];
+    return ws[warp] + inc - v;
+}
+
+// three exclusive block scans sharing their barriers; ws = 99 words
+__device__ __forceinline__ void block_exscan3(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t* ws,
+                                              uint32_t& ta, uint32_t& tb, uint32_t& tc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t ia = a, ib = b, ic = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t x = __shfl_up_sync(0xffffffffu, ia, o), y = __shfl_up_sync(0xffffffffu, ib, o), z = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) { ia += x; ib += y; ic += z; }
+    }
+    __syncthreads();
+    if (lane == 31) { ws[warp] = ia; ws[33 + warp] = ib; ws[66 + warp] = ic; }
+    __syncthreads();
+    if (warp < 3) {
+        uint32_t* w = ws + 33 * warp;
+        uint32_t v = lane < nwarp ? w[lane] : 0u, i2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, i2, o); if (lane >= o) i2 += t; }
+        w[lane] = i2 - v;
+        if (lane == 31) w[32] = i2;
+    }
+    __syncthreads();
+    ta = ws[32]; tb = ws[65]; tc = ws[98];
+    a = ws[warp] + ia - a; b = ws[33 + warp] + ib - b; c = ws[66 + warp] + ic - c;
+}
+
+// address of the tile holding `row`, and the row's lane in it
+__device__ __forceinline__ const unsigned char* tile_of(const HdrTable& ht, long long row, int& lane) {
+    const long long local = row & ((1ll << ht.shift) - 1);
+    long long tile;
+    fn3_slot_of(local, ht.sb_shift, tile, lane);
+    return ht.chunk[row >> ht.shift] + tile * FN3_TILE_BYTES;
+}
+
+__device__ __forceinline__ void put_head(const HdrTable& ht, long long row, const RowHead& h) {
+    int lane;
+    unsigned char* t = const_cast<unsigned char*>(tile_of(ht, row, lane));
+    const uint4* src = reinterpret_cast<const uint4*>(&h);
+    uint4* hdr = reinterpret_cast<uint4*>(t + lane * 32);
+    // fingerprints first, header last: a concurrent reader sees either a zero (skipped) or a complete head
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(t + FN3_TILE_FP_OFF + j * 512 + lane * 16) = src[2 + j];
+    __threadfence();
+    hdr[1] = src[1];
+    hdr[0] = src[0];
+}
+
+// bulk append: heads arrive in row order, go to their tiles
+__global__ void k_scatter_heads(const RowHead* __restrict__ src, long long first_row, long long n, const HdrTable ht) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) put_head(ht, first_row + i, src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// query build: one CTA turns the query's own row into {bmpref, coarse, entries} — in shared memory
+// (inside k_query) or in global memory (k_build_query, for queries that exceed shared memory)
+// ------------------------------------------------------------------------------------------------
+
+#define FN3_BUILD_KEEP 2
+
+template <bool GLOBAL> __device__ __forceinline__ uint32_t ldq(const uint32_t* p) { return GLOBAL ? __ldcg(p) : *p; }
+
+// All threads of the CTA must call.  bp: nw uint2; coarse: ncw words; en: (touched+1) entries; ws: 99 words.
+// tot[0..2] = |V_q|, |U_q|, |M_q|; returns the number of touched blocks.
+template <bool GLOBAL>
+__device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int ncw, int fshift, int pos_bits,
+                                                uint2* bp, uint32_t* coarse, QEntry* en, uint32_t* ws, uint32_t tot[3]) {
+    const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(q.hdr.data);
+    const uint32_t e0 = q.hdr.end[0], e1 = q.hdr.end[1], e2 = q.hdr.end[2], e3 = q.hdr.end[3],
+                   e4 = q.hdr.end[4], e5 = d ? q.hdr.end[5] : 0u;
+    const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // the row is read once: up to FN3_BUILD_KEEP words per thread stay in registers for the second pass
+    uint32_t keep[FN3_BUILD_KEEP];
+#pragma unroll
+    for (int r = 0; r < FN3_BUILD_KEEP; ++r) { const uint32_t i = tid + r * nt; keep[r] = i < e5 ? __ldg(d + i) : 0u; }
+    {
+        uint4* z = reinterpret_cast<uint4*>(bp);
+        for (int i = tid; i < nw / 2; i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* zc = reinterpret_cast<uint4*>(coarse);
+        for (int i = tid; i < ncw / 4; i += nt) zc[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (GLOBAL) __threadfence_block();
+    __syncthreads();
+    const int cs = fshift - 5;                                   // coarse block = 1 << cs fine blocks
+    for (uint32_t i = tid, r = 0; i < e5; i += nt, ++r) {       // 1. touched blocks (fine and coarse)
+        const uint32_t w = r < FN3_BUILD_KEEP ? keep[r < FN3_BUILD_KEEP ? r : 0] : __ldg(d + i);
+        uint32_t b0, b1;
+        if (i < e3) { b0 = b1 = w >> 5; }
+        else {
+            const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u);
+            b0 = s >> 5; b1 = (s + len - 1u) >> 5;
+        }
+        for (uint32_t blk = b0; blk <= b1; ++blk) atomicOr(&bp[blk >> 5].x, 1u << (blk & 31u));
+        for (uint32_t cb = b0 >> cs; cb <= (b1 >> cs); ++cb) atomicOr(&coarse[cb >> 5], 1u << (cb & 31u));
+    }
+    if (GLOBAL) __threadfence_block();
+    __syncthreads();
+    const int chunk = (nw + nt - 1) / nt;                        // 2. prefix of touched-block counts
+    const int lo = min(nw, tid * chunk), hi = min(nw, lo + chunk);
+    uint32_t local = 0;
+    for (int w = lo; w < hi; ++w) local += __popc(ldq<GLOBAL>(&bp[w].x));
+    uint32_t nE;
+    uint32_t run = block_exscan(local, ws, &nE);
+    for (int w = lo; w < hi; ++w) { const uint32_t b = ldq<GLOBAL>(&bp[w].x); bp[w].y = run; run += __popc(b); }
+    {
+        uint4* z = reinterpret_cast<uint4*>(en);                 // 3. clear entries incl. the sentinel
+        for (uint32_t i = tid; i < 2u * (nE + 1u); i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (GLOBAL) __threadfence_block();
+    __syncthreads();
+    for (uint32_t i = tid, r = 0; i < e5; i += nt, ++r) {       // 4. per-position masks
+        const uint32_t w = r < FN3_BUILD_KEEP ? keep[r < FN3_BUILD_KEEP ? r : 0] : __ldg(d + i);
+        if (i < e3) {
+            const uint32_t blk = w >> 5;
+            const uint32_t bx = ldq<GLOBAL>(&bp[blk >> 5].x), by = ldq<GLOBAL>(&bp[blk >> 5].y);
+            QEntry* t = en + (by + __popc(bx & lowmask(blk & 31u)));
+            const uint32_t pb = 1u << (w & 31u);
+            const uint32_t base = (i >= e0) + (i >= e1) + (i >= e2);
+            atomicOr(&t->mDef, pb);
+            if (base & 1u) atomicOr(&t->mB0, pb);
+            if (base & 2u) atomicOr(&t->mB1, pb);
+        } else {
+            const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u), e = s + len;
+            for (uint32_t blk = s >> 5; blk <= ((e - 1u) >> 5); ++blk) {
+                const uint32_t first = blk << 5;
+                const uint32_t from = s > first ? s - first : 0u, to = min(e - first, 32u);
+                const uint32_t m = (to >= 32u ? 0xffffffffu : lowmask(to)) & ~lowmask(from);
+                const uint32_t bx = ldq<GLOBAL>(&bp[blk >> 5].x), by = ldq<GLOBAL>(&bp[blk >> 5].y);
+                QEntry* t = en + (by + __popc(bx & lowmask(blk & 31u)));
+                atomicOr(&t->mU, m);
+                if (i >= e4) atomicOr(&t->mM, m);
+            }
+        }
+    }
+    if (GLOBAL) __threadfence_block();
+    __syncthreads();
+    const uint32_t echunk = (nE + nt - 1) / nt;                  // 5. running counts
+    const uint32_t elo = min(nE, tid * echunk), ehi = min(nE, elo + echunk);
+    uint32_t sD = 0, sU = 0, sM = 0;
+    for (uint32_t i = elo; i < ehi; ++i) {
+        sD += __popc(ldq<GLOBAL>(&en[i].mDef)); sU += __popc(ldq<GLOBAL>(&en[i].mU)); sM += __popc(ldq<GLOBAL>(&en[i].mM));
+    }
+    uint32_t tD, tU, tM;
+    block_exscan3(sD, sU, sM, ws, tD, tU, tM);
+    for (uint32_t i = elo; i < ehi; ++i) {
+        const uint32_t a = __popc(ldq<GLOBAL>(&en[i].mDef)), b = __popc(ldq<GLOBAL>(&en[i].mU)), c = __popc(ldq<GLOBAL>(&en[i].mM));
+        en[i].cDef = sD; en[i].cU = sU; en[i].cM = sM;
+        sD += a; sU += b; sM += c;
+    }
+    if (tid == 0) { en[nE].cDef = tD; en[nE].cU = tU; en[nE].cM = tM; }
+    __syncthreads();
+    tot[0] = tD; tot[1] = tU; tot[2] = tM;
+    return nE;
+}
+
+#define FN3_Q_THREADS 512
+
+__global__ void __launch_bounds__(FN3_Q_THREADS) k_build_query(const QuerySlot* __restrict__ slots, const QueryState qs,
+                                                               int nw, int ncw, int fshift, int pos_bits) {
+    __shared__ uint32_t ws[99];
+    const int slot = blockIdx.x;
+    const QuerySlot q = slots[slot];
+    uint32_t tot[3];
+    const uint32_t nE = build_query<true>(q, nw, ncw, fshift, pos_bits, qs.bmpref + (long long)slot * nw,
+                                          qs.coarse + (long long)slot * ncw, qs.ent + (long long)slot * qs.ent_stride, ws, tot);
+    if (threadIdx.x == 0) qs.info[slot] = make_uint4(nE, tot[0], tot[1], tot[2]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_query — the compare kernel
+// ------------------------------------------------------------------------------------------------
+//
+// Streaming identity (SURVEY.md §8 "Spec"), with V = definite non-reference positions,
+// U = N u M positions, q = query (seq1), c = candidate (seq2):
+//   S1    = #{p in V_c : code_q[p] is ref, or ACGT and != code_c[p]}         (monotone)
+//   dist  = S1 + |V_q| - |V_c n V_q| - |U_c n V_q|
+//   n1    = |U_q|,  n2 = |N_c| + |M_q| - |N_c n M_q|,  nboth = n1 + |N_c| - |N_c n U_q|
+// S1 alone is a lower bound of dist, so a pair leaves as soon as S1 > ceiling.
+//
+// ONE launch per one-vs-all query.  Every CTA first builds the query's compact structure in its own SHARED
+// memory straight from the query's ~2 KB row (QMODE 1) — every later lookup is an LDS, never an L2 gather.
+// Queries whose structure exceeds shared memory use the copy k_build_query left in global memory (QMODE 0).
+//   FILTER variant (ceiling <= 24): one THREAD per candidate reads the candidate's head from its tile — header
+//     and 32 fingerprints, coalesced across the warp, one memory round trip — and counts the fingerprints that
+//     fall in coarse blocks the query does not touch at all: each such position is a certain mismatch, so a
+//     count above the ceiling proves "not a neighbour" (this is ~every unrelated pair).  Survivors are then
+//     streamed one WARP per candidate.
+//   STREAM variant (larger ceilings): one WARP per candidate from the start, next header prefetched.
+// Row streaming: coalesced 128-bit loads, 256 words per warp step with the next 256 in flight,
+// __reduce_add_sync tallies, survivors compacted into the neighbour buffer with one atomic each.
+
+struct QView {                  // where the query structure lives (shared or global)
+    const uint2* bmpref;
+    const uint32_t* coarse;
+    const uint4* ent;           // two uint4 per entry
+};
+
+// V element at list index ii: returns mismatch flag (bit0) | query-is-Def flag (bit1)
+__device__ __forceinline__ uint32_t look_v(const QView& qv, uint32_t p, uint32_t ii, uint32_t e0, uint32_t e1, uint32_t e2) {
+    const uint32_t blk = p >> 5;
+    const uint2 bp = qv.bmpref[blk >> 5];
+    const uint32_t bit = blk & 31u;
+    if (!((bp.x >> bit) & 1u)) return 1u;                       // query is reference all over this block
+    const uint4 a = qv.ent[2u * (bp.y + __popc(bp.x & lowmask(bit)))];
+    const uint32_t k = p & 31u;
+    const uint32_t D = (a.x >> k) & 1u, U = (a.y >> k) & 1u;
+    const uint32_t qb = ((a.z >> k) & 1u) | (((a.w >> k) & 1u) << 1);
+    const uint32_t b = (ii >= e0) + (ii >= e1) + (ii >= e2);    // candidate's base code, needed only here
+    const uint32_t mism = (U ^ 1u) & ((D ^ 1u) | (uint32_t)(qb != b));
+    return mism | (D << 1);
+}
+
+// number of query positions of each kind strictly below x (Def, U, M)
+__device__ __forceinline__ void rank3(const QView& qv, uint32_t x, uint32_t& rD, uint32_t& rU, uint32_t& rM, bool want_um) {
+    const uint32_t blk = x >> 5;
+    const uint2 bp = qv.bmpref[blk >> 5];
+    const uint32_t bit = blk & 31u;
+    const uint32_t idx = bp.y + __popc(bp.x & lowmask(bit));
+    const bool touched = (bp.x >> bit) & 1u;
+    const uint4 b = qv.ent[2u * idx + 1u];                      // {mM, cDef, cU, cM}
+    rD = b.y; rU = b.z; rM = b.w;
+    if (touched) {
+        const uint4 a = qv.ent[2u * idx];                       // {mDef, mU, mB0, mB1}
+        const uint32_t lm = lowmask(x & 31u);
+        rD += __popc(a.x & lm);
+        if (want_um) { rU += __popc(a.y & lm); rM += __popc(b.x & lm); }
+    }
+}
+
+struct Tally { int S1, qdefV, qdefU, nNc, nNU, nNM; bool dead; };
+
+// One warp streams one candidate row against the query (all 32 lanes must call).
+template <bool COUNT>
+__device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __restrict__ d, uint32_t e0, uint32_t e1,
+                                            uint32_t e2, uint32_t e3, uint32_t e4, uint32_t e5, int k, int pos_bits,
+                                            uint32_t pmask, int lane, unsigned long long& touched) {
+    Tally t; t.S1 = 0; t.qdefV = 0; t.qdefU = 0; t.nNc = 0; t.nNU = 0; t.nNM = 0; t.dead = false;
+    // 256 words per warp step (two 128-bit loads per lane), the next 256 already in flight
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+    if ((uint32_t)lane * 4u < e5) { c0 = ld_stream_v4(d + lane * 4); if (COUNT) touched += 16; }
+    if ((uint32_t)lane * 4u + 128u < e5) { c1 = ld_stream_v4(d + lane * 4 + 128); if (COUNT) touched += 16; }
+    for (uint32_t base = 0; base < e5; base += 256) {
+        const uint32_t idx = base + lane * 4;
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        if (idx + 256u < e5) { n0 = ld_stream_v4(d + idx + 256); if (COUNT) touched += 16; }
+        if (idx + 384u < e5) { n1 = ld_stream_v4(d + idx + 384); if (COUNT) touched += 16; }
+        const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        int mism = 0;
+        if (base + 256u <= e3) {                                // warp-uniform: the whole step is V words
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t r = look_v(qv, w[j], idx + (j & 3) + ((j >> 2) << 7), e0, e1, e2);
+                mism += r & 1u;
+                t.qdefV += r >> 1;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t ii = idx + (j & 3) + ((j >> 2) << 7);
+                if (ii < e3) {
+                    const uint32_t r = look_v(qv, w[j], ii, e0, e1, e2);
+                    mism += r & 1u;
+                    t.qdefV += r >> 1;
+                } else if (ii < e5) {
+                    const uint32_t s = w[j] & pmask;
+                    const uint32_t len = (pos_bits >= 32) ? 1u : ((w[j] >> pos_bits) + 1u);
+                    const bool isN = ii < e4;
+                    uint32_t aD, aU, aM, bD, bU, bM;
+                    rank3(qv, s, aD, aU, aM, isN);
+                    rank3(qv, s + len, bD, bU, bM, isN);
+                    t.qdefU += (int)(bD - aD);
+                    if (isN) { t.nNc += (int)len; t.nNU += (int)(bU - aU); t.nNM += (int)(bM - aM); }
+                }
+            }
+        }
+        if (base < e3) {                                        // warp-uniform: this step touched V words
+            t.S1 += __reduce_add_sync(0xffffffffu, mism);
+            if (t.S1 > k) { t.dead = true; break; }
+        }
+        c0 = n0; c1 = n1;
+    }
+    return t;
+}
+
+__device__ __forceinline__ void emit_if_close(const CompareParams& p, const Tally& t0, int k, uint32_t nVq, uint32_t nUq,
+                                              uint32_t nMq, long long qrow, long long crow, int lane) {
+    if (t0.dead) return;
+    const int qdefV = __reduce_add_sync(0xffffffffu, t0.qdefV);
+    const int qdefU = __reduce_add_sync(0xffffffffu, t0.qdefU);
+    const int dist = t0.S1 + (int)nVq - qdefV - qdefU;
+    if (dist > k) return;
+    const int nNc = __reduce_add_sync(0xffffffffu, t0.nNc);
+    const int nNU = __reduce_add_sync(0xffffffffu, t0.nNU);
+    const int nNM = __reduce_add_sync(0xffffffffu, t0.nNM);
+    if (lane == 0) {
+        const unsigned long long at = atomicAdd(p.out_count, 1ull);
+        if ((long long)at < p.out_cap) {
+            EdgeRec r;
+            r.row1 = qrow; r.row2 = crow; r.dist = dist;
+            r.n1 = (int)nUq; r.n2 = nNc + (int)nMq - nNM; r.nboth = (int)nUq + nNc - nNU;
+            p.out[at] = r;
+        }
+    }
+}
+
+// QMODE 0: query structure in global memory (built by k_build_query); 1: built here in shared memory
+template <bool COUNT, int QMODE, bool FILTER>
+__global__ void __launch_bounds__(FN3_Q_THREADS, 2) k_query(const CompareParams p) {
+    extern __shared__ __align__(128) uint4 qsm[];
+    __shared__ uint32_t ws[99];
+    if (p.debug_stop == 3) return;
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.y;
+    const QuerySlot qs = p.slot_inline ? p.slot0 : p.slots[slot];
+    if (p.commit_row >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        put_head(p.hdr, p.commit_row, p.commit_head);      // fn3_insert_query: the new row's head (never a candidate here)
+    if (qs.hdr.data == 0ull) return;                       // invalid query: no distances at all
+    if (p.debug_stop == 4) return;
+    const int nw = p.nw, ncw = p.ncw;
+    uint32_t nVq, nUq, nMq;
+    QView qv;
+    if (QMODE == 1) {
+        uint2* sm_bp = reinterpret_cast<uint2*>(qsm);
+        uint32_t* sm_co = reinterpret_cast<uint32_t*>(qsm + nw / 2);
+        QEntry* sm_en = reinterpret_cast<QEntry*>(qsm + nw / 2 + ncw / 4);
+        uint32_t tot[3];
+        build_query<false>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bp, sm_co, sm_en, ws, tot);
+        nVq = tot[0]; nUq = tot[1]; nMq = tot[2];
+        qv.bmpref = sm_bp; qv.coarse = sm_co; qv.ent = reinterpret_cast<const uint4*>(sm_en);
+    } else {
+        const uint4 info = p.qs.info[slot];
+        nVq = info.y; nUq = info.z; nMq = info.w;
+        qv.bmpref = p.qs.bmpref + (long long)slot * nw;
+        qv.coarse = p.qs.coarse + (long long)slot * ncw;
+        qv.ent = reinterpret_cast<const uint4*>(p.qs.ent + (long long)slot * p.qs.ent_stride);
+    }
+    if (p.debug_stop == 1) return;
+    const int k = p.ceiling;
+    const int pos_bits = p.pos_bits;
+    const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int tshift = p.hdr.shift - 5;                    // tiles per chunk = 1 << tshift
+    unsigned long long touched = 0;
+
+    if (FILTER) {
+        // work unit = 32 candidates: a tile (full scan) or 32 strided entries of the explicit list
+        const long long units = p.rows ? (p.n_list + 31) >> 5
+                                       : ((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
+        for (long long u = warp0; u < units; u += nwarps) {
+            // ---- phase A: one thread per candidate, on the candidate's head ---------------------
+            long long row = -1;
+            const unsigned char* tile = nullptr;
+            int tl = lane;
+            if (p.rows) {
+                const long long ci = u + (long long)lane * units;
+                if (ci < p.n_list) { row = p.rows[ci]; tile = tile_of(p.hdr, row, tl); }
+            } else {
+                const long long chunk = u >> tshift, lt = u & ((1ll << tshift) - 1);
+                row = (chunk << p.hdr.shift) + fn3_row_of(lt, lane, p.hdr.sb_shift);
+                tile = p.hdr.chunk[chunk] + lt * FN3_TILE_BYTES;
+                if (row >= p.n_rows) row = -1;
+            }
+            uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+            bool pass = false;
+            if (row >= 0 && row != qs.exclude && row > qs.skip_le) {
+                // header and fingerprints are requested together: ONE memory round trip per candidate
+                const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
+                const uint4* fp = reinterpret_cast<const uint4*>(tile + FN3_TILE_FP_OFF + tl * 16);
+                h0 = __ldg(hp); h1 = __ldg(hp + 1);
+                uint4 f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = __ldg(fp + j * 32);
+                if (COUNT) touched += 96;
+                if ((h0.x | h0.y) != 0u) {                 // data pointer 0: invalid or removed candidate
+                    const uint32_t nv = min(h1.y, (uint32_t)FN3_HEAD_FP);
+                    int S = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t cb = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                            const uint32_t untouched = ((qv.coarse[cb >> 5] >> (cb & 31u)) & 1u) ^ 1u;
+                            S += ((uint32_t)(8 * j + i) < nv) ? (int)untouched : 0;
+                        }
+                    }
+                    pass = S <= k;
+                }
+            }
+            // ---- phase B: one warp per surviving candidate ----------------------------------------
+            uint32_t alive = __ballot_sync(0xffffffffu, pass);
+            if (p.debug_stop == 2) alive = 0u;
+            while (alive) {
+                const int src = __ffs(alive) - 1;
+                alive &= alive - 1u;
+                const uint32_t dlo = __shfl_sync(0xffffffffu, h0.x, src), dhi = __shfl_sync(0xffffffffu, h0.y, src);
+                const uint32_t e0 = __shfl_sync(0xffffffffu, h0.z, src), e1 = __shfl_sync(0xffffffffu, h0.w, src);
+                const uint32_t e2 = __shfl_sync(0xffffffffu, h1.x, src), e3 = __shfl_sync(0xffffffffu, h1.y, src);
+                const uint32_t e4 = __shfl_sync(0xffffffffu, h1.z, src), e5 = __shfl_sync(0xffffffffu, h1.w, src);
+                const long long crow = __shfl_sync(0xffffffffu, row, src);
+                const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)dhi << 32) | dlo);
+                const Tally t = stream_row<COUNT>(qv, d, e0, e1, e2, e3, e4, e5, k, pos_bits, pmask, lane, touched);
+                emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, crow, lane);
+            }
+        }
+    } else {
+        // one warp per candidate; the next candidate's header is requested before the current row is streamed
+        const long long n = p.rows ? p.n_list
+                                   : ((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << p.hdr.sb_shift;   // slots
+        auto fetch = [&](long long ci, long long& r, uint4& a, uint4& b) {
+            a = make_uint4(0, 0, 0, 0); b = a; r = -1;
+            if (ci < n) {
+                const unsigned char* tile; int tl;
+                if (p.rows) { r = p.rows[ci]; tile = tile_of(p.hdr, r, tl); }
+                else {
+                    const long long t = ci >> 5, chunk = t >> tshift, lt = t & ((1ll << tshift) - 1);
+                    tl = (int)(ci & 31);
+                    r = (chunk << p.hdr.shift) + fn3_row_of(lt, tl, p.hdr.sb_shift);
+                    tile = p.hdr.chunk[chunk] + lt * FN3_TILE_BYTES;
+                    if (r >= p.n_rows) r = -1;
+                }
+                if (r >= 0 && r != qs.exclude && r > qs.skip_le) {
+                    const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
+                    a = __ldg(hp); b = __ldg(hp + 1);
+                    if (COUNT && lane == 0) touched += 32;
+                }
+            }
+        };
+        long long i = warp0, row;
+        uint4 h0, h1;
+        fetch(i, row, h0, h1);
+        while (i < n) {
+            long long nrow; uint4 n0, n1;
+            fetch(i + nwarps, nrow, n0, n1);
+            if ((h0.x | h0.y) != 0u) {
+                const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
+                const Tally t = stream_row<COUNT>(qv, d, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, k, pos_bits, pmask, lane, touched);
+                emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, row, lane);
+            }
+            i += nwarps; row = nrow; h0 = n0; h1 = n1;
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, o);
+        if (lane == 0) atomicAdd(p.touched, touched);
+    }
+}
+
+// L2 flush helper for the measurement hook
+__global__ void k_fill(uint4* p, long long n, uint32_t v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = make_uint4(v, v, v, v);
+}

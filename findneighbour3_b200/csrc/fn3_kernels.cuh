@@ -424,9 +424,10 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, 2) k_query(const CompareParams 
                         const uint32_t w[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const uint32_t cb = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                            const bool in = (uint32_t)(8 * j + i) < nv;          // beyond nv the fingerprint is padding
+                            const uint32_t cb = in ? (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu : 0u;
                             const uint32_t untouched = ((qv.coarse[cb >> 5] >> (cb & 31u)) & 1u) ^ 1u;
-                            S += ((uint32_t)(8 * j + i) < nv) ? (int)untouched : 0;
+                            S += in ? (int)untouched : 0;
                         }
                     }
                     pass = S <= k;

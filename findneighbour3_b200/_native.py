@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfn3.so")
+LIB_PATH = os.environ.get("FN3_LIB_PATH") or os.path.join(HERE, "libfn3.so")   # override: kernel experiments only
 
 FN3_OK = 0
 FN3_EARG = -1

@@ -268,7 +268,7 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         QueryState& q = e->qstate;
         memset(&q, 0, sizeof q);
         q.ent_stride = (long long)e->n_blk + 1;
-        if ((s = cudaMalloc(&q.bmpref, (size_t)e->nw * sizeof(uint2) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(bmpref)", s);
+        if ((s = cudaMalloc(&q.bm, (size_t)e->nw * 2 * sizeof(uint32_t) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(bm)", s);
         if ((s = cudaMalloc(&q.coarse, (size_t)e->ncw * sizeof(uint32_t) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(coarse)", s);
         if ((s = cudaMalloc(&q.ent, (size_t)q.ent_stride * sizeof(QEntry) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(entries)", s);
         if ((s = cudaMalloc(&q.info, sizeof(uint4) * FN3_MAX_SLOTS)) != cudaSuccess) return fail("cudaMalloc(info)", s);
@@ -308,7 +308,7 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     for (auto p : e->data_chunks) cudaFree(p);
     for (auto p : e->hdr_chunks) cudaFree(p);
-    cudaFree(e->qstate.bmpref); cudaFree(e->qstate.coarse); cudaFree(e->qstate.ent); cudaFree(e->qstate.info);
+    cudaFree(e->qstate.bm); cudaFree(e->qstate.coarse); cudaFree(e->qstate.ent); cudaFree(e->qstate.info);
     cudaFree(e->d_heads);
     cudaFree(e->d_slots);
     cudaFree(e->d_outbuf); cudaFree(e->d_rows); cudaFree(e->d_scratch);
@@ -693,8 +693,8 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     const long long cand = job.d_rows ? job.n_list : slots_scanned;
     const long long units = filter ? (cand + 31) / 32 : cand;                   // warp-sized work units
     long long ctas = std::max<long long>(1, (units + warps_per_cta - 1) / warps_per_cta);
-    long long per_sm = 2;                                           // __launch_bounds__(512, 2)
-    if (in_smem && 2 * (smem + (size_t)e->q_static_smem + 1024) > (size_t)228 * 1024) per_sm = 1;
+    long long per_sm = FN3_Q_MINB;                                  // __launch_bounds__(512, FN3_Q_MINB)
+    if (in_smem && per_sm * (long long)(smem + (size_t)e->q_static_smem + 1024) > (long long)228 * 1024) per_sm = 1;
     ctas = std::min<long long>(ctas, (long long)e->sm_count * per_sm);
     dim3 g((unsigned)ctas, (unsigned)ns);
     if (in_smem) {

@@ -103,11 +103,13 @@ __global__ void k_scatter_heads(const RowHead* __restrict__ src, long long first
 
 template <bool GLOBAL> __device__ __forceinline__ uint32_t ldq(const uint32_t* p) { return GLOBAL ? __ldcg(p) : *p; }
 
-// All threads of the CTA must call.  bp: nw uint2; coarse: ncw words; en: (touched+1) entries; ws: 99 words.
+// All threads of the CTA must call.  bm: 2*nw words (bitmap, then prefix); coarse: ncw words; en: (touched+1)
+// entries; ws: 99 words.
 // tot[0..2] = |V_q|, |U_q|, |M_q|; returns the number of touched blocks.
 template <bool GLOBAL>
 __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int ncw, int fshift, int pos_bits,
-                                                uint2* bp, uint32_t* coarse, QEntry* en, uint32_t* ws, uint32_t tot[3]) {
+                                                uint32_t* bm, uint32_t* coarse, QEntry* en, uint32_t* ws, uint32_t tot[3]) {
+    uint32_t* pref = bm + nw;
     const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(q.hdr.data);
     const uint32_t e0 = q.hdr.end[0], e1 = q.hdr.end[1], e2 = q.hdr.end[2], e3 = q.hdr.end[3],
                    e4 = q.hdr.end[4], e5 = d ? q.hdr.end[5] : 0u;
@@ -118,8 +120,8 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
 #pragma unroll
     for (int r = 0; r < FN3_BUILD_KEEP; ++r) { const uint32_t i = tid + r * nt; keep[r] = i < e5 ? __ldg(d + i) : 0u; }
     {
-        uint4* z = reinterpret_cast<uint4*>(bp);
-        for (int i = tid; i < nw / 2; i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* z = reinterpret_cast<uint4*>(bm);
+        for (int i = tid; i < nw / 4; i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
         uint4* zc = reinterpret_cast<uint4*>(coarse);
         for (int i = tid; i < ncw / 4; i += nt) zc[i] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -134,7 +136,7 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
             const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u);
             b0 = s >> 5; b1 = (s + len - 1u) >> 5;
         }
-        for (uint32_t blk = b0; blk <= b1; ++blk) atomicOr(&bp[blk >> 5].x, 1u << (blk & 31u));
+        for (uint32_t blk = b0; blk <= b1; ++blk) atomicOr(&bm[blk >> 5], 1u << (blk & 31u));
         for (uint32_t cb = b0 >> cs; cb <= (b1 >> cs); ++cb) atomicOr(&coarse[cb >> 5], 1u << (cb & 31u));
     }
     if (GLOBAL) __threadfence_block();
@@ -142,10 +144,10 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
     const int chunk = (nw + nt - 1) / nt;                        // 2. prefix of touched-block counts
     const int lo = min(nw, tid * chunk), hi = min(nw, lo + chunk);
     uint32_t local = 0;
-    for (int w = lo; w < hi; ++w) local += __popc(ldq<GLOBAL>(&bp[w].x));
+    for (int w = lo; w < hi; ++w) local += __popc(ldq<GLOBAL>(&bm[w]));
     uint32_t nE;
     uint32_t run = block_exscan(local, ws, &nE);
-    for (int w = lo; w < hi; ++w) { const uint32_t b = ldq<GLOBAL>(&bp[w].x); bp[w].y = run; run += __popc(b); }
+    for (int w = lo; w < hi; ++w) { const uint32_t b = ldq<GLOBAL>(&bm[w]); pref[w] = run; run += __popc(b); }
     {
         uint4* z = reinterpret_cast<uint4*>(en);                 // 3. clear entries incl. the sentinel
         for (uint32_t i = tid; i < 2u * (nE + 1u); i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -156,7 +158,7 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
         const uint32_t w = r < FN3_BUILD_KEEP ? keep[r < FN3_BUILD_KEEP ? r : 0] : __ldg(d + i);
         if (i < e3) {
             const uint32_t blk = w >> 5;
-            const uint32_t bx = ldq<GLOBAL>(&bp[blk >> 5].x), by = ldq<GLOBAL>(&bp[blk >> 5].y);
+            const uint32_t bx = ldq<GLOBAL>(&bm[blk >> 5]), by = ldq<GLOBAL>(&pref[blk >> 5]);
             QEntry* t = en + (by + __popc(bx & lowmask(blk & 31u)));
             const uint32_t pb = 1u << (w & 31u);
             const uint32_t base = (i >= e0) + (i >= e1) + (i >= e2);
@@ -169,7 +171,7 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
                 const uint32_t first = blk << 5;
                 const uint32_t from = s > first ? s - first : 0u, to = min(e - first, 32u);
                 const uint32_t m = (to >= 32u ? 0xffffffffu : lowmask(to)) & ~lowmask(from);
-                const uint32_t bx = ldq<GLOBAL>(&bp[blk >> 5].x), by = ldq<GLOBAL>(&bp[blk >> 5].y);
+                const uint32_t bx = ldq<GLOBAL>(&bm[blk >> 5]), by = ldq<GLOBAL>(&pref[blk >> 5]);
                 QEntry* t = en + (by + __popc(bx & lowmask(blk & 31u)));
                 atomicOr(&t->mU, m);
                 if (i >= e4) atomicOr(&t->mM, m);
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS) k_build_query(const QuerySlot* 
     const int slot = blockIdx.x;
     const QuerySlot q = slots[slot];
     uint32_t tot[3];
-    const uint32_t nE = build_query<true>(q, nw, ncw, fshift, pos_bits, qs.bmpref + (long long)slot * nw,
+    const uint32_t nE = build_query<true>(q, nw, ncw, fshift, pos_bits, qs.bm + (long long)slot * 2 * nw,
                                           qs.coarse + (long long)slot * ncw, qs.ent + (long long)slot * qs.ent_stride, ws, tot);
     if (threadIdx.x == 0) qs.info[slot] = make_uint4(nE, tot[0], tot[1], tot[2]);
 }
@@ -234,18 +236,21 @@ __global__ void __launch_bounds__(FN3_Q_THREADS) k_build_query(const QuerySlot* 
 // __reduce_add_sync tallies, survivors compacted into the neighbour buffer with one atomic each.
 
 struct QView {                  // where the query structure lives (shared or global)
-    const uint2* bmpref;
+    const uint32_t* bm;         // bit per 32-position block: touched by the query
+    const uint32_t* pref;       // touched blocks below block 32w
     const uint32_t* coarse;
     const uint4* ent;           // two uint4 per entry
 };
 
-// V element at list index ii: returns mismatch flag (bit0) | query-is-Def flag (bit1)
-__device__ __forceinline__ uint32_t look_v(const QView& qv, uint32_t p, uint32_t ii, uint32_t e0, uint32_t e1, uint32_t e2) {
-    const uint32_t blk = p >> 5;
-    const uint2 bp = qv.bmpref[blk >> 5];
-    const uint32_t bit = blk & 31u;
-    if (!((bp.x >> bit) & 1u)) return 1u;                       // query is reference all over this block
-    const uint4 a = qv.ent[2u * (bp.y + __popc(bp.x & lowmask(bit)))];
+// is the 32-position block of p touched by the query?  (the common answer for an unrelated candidate is no)
+__device__ __forceinline__ uint32_t touched_bit(const QView& qv, uint32_t p) {
+    return (qv.bm[p >> 10] >> ((p >> 5) & 31u)) & 1u;
+}
+
+// V element at list index ii whose block IS touched: returns mismatch flag (bit0) | query-is-Def flag (bit1)
+__device__ __forceinline__ uint32_t look_touched(const QView& qv, uint32_t p, uint32_t ii, uint32_t e0, uint32_t e1, uint32_t e2) {
+    const uint32_t blk = p >> 5, wi = blk >> 5, bit = blk & 31u;
+    const uint4 a = qv.ent[2u * (qv.pref[wi] + __popc(qv.bm[wi] & lowmask(bit)))];
     const uint32_t k = p & 31u;
     const uint32_t D = (a.x >> k) & 1u, U = (a.y >> k) & 1u;
     const uint32_t qb = ((a.z >> k) & 1u) | (((a.w >> k) & 1u) << 1);
@@ -256,11 +261,10 @@ __device__ __forceinline__ uint32_t look_v(const QView& qv, uint32_t p, uint32_t
 
 // number of query positions of each kind strictly below x (Def, U, M)
 __device__ __forceinline__ void rank3(const QView& qv, uint32_t x, uint32_t& rD, uint32_t& rU, uint32_t& rM, bool want_um) {
-    const uint32_t blk = x >> 5;
-    const uint2 bp = qv.bmpref[blk >> 5];
-    const uint32_t bit = blk & 31u;
-    const uint32_t idx = bp.y + __popc(bp.x & lowmask(bit));
-    const bool touched = (bp.x >> bit) & 1u;
+    const uint32_t blk = x >> 5, wi = blk >> 5, bit = blk & 31u;
+    const uint32_t bits = qv.bm[wi];
+    const uint32_t idx = qv.pref[wi] + __popc(bits & lowmask(bit));
+    const bool touched = (bits >> bit) & 1u;
     const uint4 b = qv.ent[2u * idx + 1u];                      // {mM, cDef, cU, cM}
     rD = b.y; rU = b.z; rM = b.w;
     if (touched) {
@@ -291,20 +295,26 @@ __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __r
         const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
         int mism = 0;
         if (base + 256u <= e3) {                                // warp-uniform: the whole step is V words
+            // (a branch-free variant — all 8 bitmap tests first, touched words afterwards — measured slower on
+            //  B200: more registers, spills at 64 regs/thread, 57 vs 42 us at ceiling 250; profiles/README.md)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint32_t r = look_v(qv, w[j], idx + (j & 3) + ((j >> 2) << 7), e0, e1, e2);
-                mism += r & 1u;
-                t.qdefV += r >> 1;
+                if (touched_bit(qv, w[j])) {
+                    const uint32_t r = look_touched(qv, w[j], idx + (j & 3) + ((j >> 2) << 7), e0, e1, e2);
+                    mism += r & 1u;
+                    t.qdefV += r >> 1;
+                } else mism += 1;
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint32_t ii = idx + (j & 3) + ((j >> 2) << 7);
                 if (ii < e3) {
-                    const uint32_t r = look_v(qv, w[j], ii, e0, e1, e2);
-                    mism += r & 1u;
-                    t.qdefV += r >> 1;
+                    if (touched_bit(qv, w[j])) {
+                        const uint32_t r = look_touched(qv, w[j], ii, e0, e1, e2);
+                        mism += r & 1u;
+                        t.qdefV += r >> 1;
+                    } else mism += 1;
                 } else if (ii < e5) {
                     const uint32_t s = w[j] & pmask;
                     const uint32_t len = (pos_bits >= 32) ? 1u : ((w[j] >> pos_bits) + 1u);
@@ -348,8 +358,11 @@ __device__ __forceinline__ void emit_if_close(const CompareParams& p, const Tall
 }
 
 // QMODE 0: query structure in global memory (built by k_build_query); 1: built here in shared memory
+#ifndef FN3_Q_MINB
+#define FN3_Q_MINB 2
+#endif
 template <bool COUNT, int QMODE, bool FILTER>
-__global__ void __launch_bounds__(FN3_Q_THREADS, 2) k_query(const CompareParams p) {
+__global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const CompareParams p) {
     extern __shared__ __align__(128) uint4 qsm[];
     __shared__ uint32_t ws[99];
     if (p.debug_stop == 3) return;
@@ -364,17 +377,18 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, 2) k_query(const CompareParams 
     uint32_t nVq, nUq, nMq;
     QView qv;
     if (QMODE == 1) {
-        uint2* sm_bp = reinterpret_cast<uint2*>(qsm);
+        uint32_t* sm_bm = reinterpret_cast<uint32_t*>(qsm);                       // [bitmap nw | prefix nw]
         uint32_t* sm_co = reinterpret_cast<uint32_t*>(qsm + nw / 2);
         QEntry* sm_en = reinterpret_cast<QEntry*>(qsm + nw / 2 + ncw / 4);
         uint32_t tot[3];
-        build_query<false>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bp, sm_co, sm_en, ws, tot);
+        build_query<false>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
         nVq = tot[0]; nUq = tot[1]; nMq = tot[2];
-        qv.bmpref = sm_bp; qv.coarse = sm_co; qv.ent = reinterpret_cast<const uint4*>(sm_en);
+        qv.bm = sm_bm; qv.pref = sm_bm + nw; qv.coarse = sm_co; qv.ent = reinterpret_cast<const uint4*>(sm_en);
     } else {
         const uint4 info = p.qs.info[slot];
         nVq = info.y; nUq = info.z; nMq = info.w;
-        qv.bmpref = p.qs.bmpref + (long long)slot * nw;
+        qv.bm = p.qs.bm + (long long)slot * 2 * nw;
+        qv.pref = qv.bm + nw;
         qv.coarse = p.qs.coarse + (long long)slot * ncw;
         qv.ent = reinterpret_cast<const uint4*>(p.qs.ent + (long long)slot * p.qs.ent_stride);
     }

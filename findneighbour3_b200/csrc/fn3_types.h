@@ -55,8 +55,8 @@ FN3_HD long long fn3_row_of(long long tile, int lane, int sb_shift) {
 }
 
 // ---- the query, compact --------------------------------------------------------
-// bmpref[w] : .x bit per 32-position block 32w..32w+31 "the query is non-reference/N/M somewhere in it" (touched),
-//             .y number of touched blocks below block 32w
+// bm[w]     : bit per 32-position block 32w..32w+31 "the query is non-reference/N/M somewhere in it" (touched)
+// pref[w]   : number of touched blocks below block 32w
 // coarse    : bit per coarse block (position >> fshift) touched — what the fingerprints are tested against
 // entry[i]  : the i-th touched block; entry[nE] is a sentinel whose counts are the totals |V_q|,|U_q|,|M_q|
 struct __align__(32) QEntry {
@@ -65,7 +65,7 @@ struct __align__(32) QEntry {
 };
 
 struct QueryState {                // global-memory copies (only queries too large for shared memory use them)
-    uint2* bmpref;                 // slot s at bmpref + s*nw
+    uint32_t* bm;                  // slot s at bm + s*2*nw : [touched-block bitmap nw | prefix counts nw]
     uint32_t* coarse;              // slot s at coarse + s*ncw
     QEntry* ent;                   // slot s at ent + s*ent_stride
     uint4* info;                   // slot s: {nE, |V_q|, |U_q|, |M_q|}

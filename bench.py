@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--ceiling", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-allvsall", dest="allvsall", action="store_false", help="skip the extra all-vs-all leg")
     return ap.parse_args()
 
 
@@ -448,6 +449,20 @@ def main():
         e2e["two_calls"] = e2e_two
     clocks = sampler.stop()
 
+    # ---- leg 3 (extra, not the headline): all-vs-all sparse matrix of the shard at 12 SNV (configs[2] shape) ----
+    ava = None
+    if args.allvsall and world == 1:
+        torch.cuda.synchronize()
+        n_now = eng.stats()["n_rows"]
+        t0 = time.perf_counter()
+        edges = eng.all_vs_all(12, upper_only=True)
+        t_ava = time.perf_counter() - t0
+        live = n_now - int(coll.invalid.sum())
+        ava = {"samples": int(n_now), "ceiling": 12, "seconds": t_ava, "edges": int(len(edges)),
+               "pairs": n_now * (n_now - 1) // 2, "comparisons_per_s": n_now * (n_now - 1) / 2 / t_ava,
+               "canonical_GBps": (bytes_canon_all / max(live, 1)) * (n_now * (n_now - 1) / 2) / t_ava / 1e9,
+               "note": "fn3_all_vs_all, upper triangle, tiles of 8 queries, wall clock incl. the copy of the edges to the host"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -466,6 +481,8 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum_over_ranks(float(launches))),
         "roofline": roofline, "host_cpus": os.cpu_count(), "setup_s": t_gen,
     }
+    if ava is not None:
+        line["all_vs_all"] = ava
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_python_port(coll, fresh[W:], ceiling, args.cpu_seconds)

@@ -56,6 +56,7 @@ SIGNATURES = {
                                    C.POINTER(Hit), C.c_int64, _i64p]),
     "fn3_all_vs_all": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                  C.POINTER(Edge), C.c_int64, _i64p]),
+    "fn3_all_vs_all_fetch": (C.c_int, [_vp, C.POINTER(Edge), C.c_int64, _i64p]),
     "fn3_pair": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(Hit), _i32p]),
     "fn3_pair_lists": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, _i32p, _i32p, C.c_int32, C.c_int32,
                                  C.POINTER(Hit), _i32p]),

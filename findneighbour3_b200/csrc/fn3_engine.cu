@@ -86,7 +86,7 @@ struct fn3_engine {
     int q_static_smem = 0;                 // static shared memory of k_query
     int debug_stop = 0;                    // env FN3_DEBUG_STOP (profiling aid, wrong results when set)
     uint32_t slot_blocks[FN3_MAX_SLOTS];   // touched-block count of the query in each slot (sizes the staging)
-    QuerySlot* d_slots = nullptr; QuerySlot* h_slots = nullptr;   // h_slots pinned
+    QuerySlot* d_slots = nullptr; QuerySlot* h_slots = nullptr;   // [FN3_SLOT_RING tiles][FN3_MAX_SLOTS]; h_slots pinned
     // survivor buffer: one allocation = [32-byte counter block | records], mirrored in pinned host memory so
     // that the counter and the first records come back in ONE device-to-host copy
     unsigned char* d_outbuf = nullptr; unsigned char* h_outbuf = nullptr;
@@ -95,6 +95,7 @@ struct fn3_engine {
     unsigned long long* h_count = nullptr;
     EdgeRec* h_out = nullptr; long long h_out_cap = 0;
     std::atomic<long long> h2d_bytes{0}, d2h_bytes{0};
+    long long edges_ready = -1;              // edges of the last fn3_all_vs_all still in d_out (-1: none)
     long long* d_rows = nullptr; long long d_rows_cap = 0;
     long long* h_rows = nullptr; long long h_rows_cap = 0;       // pinned
     // scratch rows for samples that are not stored (pair_lists / lists_vs_all)
@@ -142,6 +143,7 @@ extern "C" const char* fn3_last_error(fn3_engine* e) {
 
 extern "C" int64_t fn3_launch_count(fn3_engine* e) { return e ? e->launches.load() : 0; }
 
+#define FN3_SLOT_RING 32        // all-vs-all: query tiles queued between two host synchronisations
 #define FN3_OUT_HDR 32
 #define FN3_FIRST_HITS 256      // records fetched together with the counter
 
@@ -287,8 +289,8 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
                 return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", s);
         }
     }
-    if ((s = cudaMalloc(&e->d_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS)) != cudaSuccess) return fail("cudaMalloc(slots)", s);
-    if ((s = cudaHostAlloc(&e->h_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(slots)", s);
+    if ((s = cudaMalloc(&e->d_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS * FN3_SLOT_RING)) != cudaSuccess) return fail("cudaMalloc(slots)", s);
+    if ((s = cudaHostAlloc(&e->h_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS * FN3_SLOT_RING, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(slots)", s);
     if (ensure_out(e, 4096) != FN3_OK || ensure_hout(e, 4096) != FN3_OK) {
         set_err(nullptr, FN3_ENOMEM, "fn3_create: survivor buffers: %s", e->err.c_str());
         fn3_destroy(e);
@@ -645,7 +647,9 @@ struct QueryJob {                    // what enqueue_query needs beyond the engi
     const long long* d_rows = nullptr;   // explicit candidate list (device) or nullptr = all rows < n_rows
     long long n_list = 0;
     long long n_rows = 0;
-    int ns = 1;                          // query slots: 1 = e->h_slots[0] passed by value; >1 = e->d_slots (uploaded here)
+    int ns = 1;                          // query slots: 1 = passed by value; >1 = uploaded to e->d_slots here
+    int slot_base = 0;                   // first slot of this tile inside the h_slots/d_slots ring
+    uint32_t blocks = 0;                 // max touched-block bound over the tile's queries (sizes shared memory)
     int ceiling = 0;
     bool count_bytes = false;
     const RowHead* commit_head = nullptr;   // fn3_insert_query: head of the new row, placed by the kernel
@@ -658,21 +662,23 @@ struct QueryJob {                    // what enqueue_query needs beyond the engi
 static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     cudaStream_t st = e->q_stream;
     const int ns = job.ns;
+    QuerySlot* h_sl = e->h_slots + job.slot_base;
+    QuerySlot* d_sl = e->d_slots + job.slot_base;
     if (ns > 1) {
-        CU(e, cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(QuerySlot) * ns, cudaMemcpyHostToDevice, st));
+        CU(e, cudaMemcpyAsync(d_sl, h_sl, sizeof(QuerySlot) * ns, cudaMemcpyHostToDevice, st));
         e->h2d_bytes += (long long)sizeof(QuerySlot) * ns;
     }
-    uint32_t blocks = 0;
-    for (int s = 0; s < ns; ++s) blocks = std::max(blocks, e->slot_blocks[s]);
+    uint32_t blocks = job.blocks;
+    if (ns == 1 && blocks == 0) blocks = e->slot_blocks[0];
     blocks = std::min<uint32_t>(blocks, (uint32_t)e->n_blk);
     const size_t smem = (size_t)e->nw * sizeof(uint2) + (size_t)e->ncw * 4 + ((size_t)blocks + 1) * sizeof(QEntry);
     const bool in_smem = smem + (size_t)e->q_static_smem + 256 <= (size_t)e->stage_limit;
     if (!in_smem) {
         if (ns == 1) {                    // the build kernel reads its slots from device memory
-            CU(e, cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(QuerySlot), cudaMemcpyHostToDevice, st));
+            CU(e, cudaMemcpyAsync(d_sl, h_sl, sizeof(QuerySlot), cudaMemcpyHostToDevice, st));
             e->h2d_bytes += (long long)sizeof(QuerySlot);
         }
-        k_build_query<<<ns, FN3_Q_THREADS, 0, st>>>(e->d_slots, e->qstate, e->nw, e->ncw, e->fshift, e->pos_bits);
+        k_build_query<<<ns, FN3_Q_THREADS, 0, st>>>(d_sl, e->qstate, e->nw, e->ncw, e->fshift, e->pos_bits);
         e->launches += 1;
         CU(e, cudaGetLastError());
     }
@@ -680,7 +686,7 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     CompareParams p;
     memset(&p, 0, sizeof p);
     p.hdr = job.ht; p.qs = e->qstate; p.rows = job.d_rows; p.n_list = job.n_list; p.n_rows = job.n_rows;
-    p.slots = e->d_slots; p.slot0 = e->h_slots[0]; p.slot_inline = ns == 1 ? 1 : 0;
+    p.slots = d_sl; p.slot0 = h_sl[0]; p.slot_inline = ns == 1 ? 1 : 0;
     p.commit_row = job.commit_row;
     if (job.commit_head) p.commit_head = *job.commit_head;
     p.out = e->d_out; p.out_count = e->d_count; p.touched = e->d_count + 1; p.out_cap = e->out_cap;
@@ -695,7 +701,9 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     long long ctas = std::max<long long>(1, (units + warps_per_cta - 1) / warps_per_cta);
     long long per_sm = FN3_Q_MINB;                                  // __launch_bounds__(512, FN3_Q_MINB)
     if (in_smem && per_sm * (long long)(smem + (size_t)e->q_static_smem + 1024) > (long long)228 * 1024) per_sm = 1;
-    ctas = std::min<long long>(ctas, (long long)e->sm_count * per_sm);
+    // every CTA builds its query first: with several slots per launch give each slot its share of the resident
+    // CTAs and let every CTA scan more candidates, rather than several waves that each rebuild the query
+    ctas = std::min<long long>(ctas, std::max<long long>(1, (long long)e->sm_count * per_sm / ns));
     dim3 g((unsigned)ctas, (unsigned)ns);
     if (in_smem) {
         if (job.count_bytes) launch_query<true, 1>(filter, g, smem, st, p);
@@ -752,6 +760,7 @@ static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int
                           int64_t* n_out) {
     const long long n = rows ? n_list : job.n_rows;
     *n_out = 0;
+    e->edges_ready = -1;
     const bool nothing = e->h_slots[0].hdr.data == 0ull || n <= 0;   // invalid query: nothing is a neighbour
     if (nothing && job.commit_row < 0) return FN3_OK;
     int rc;
@@ -948,6 +957,21 @@ extern "C" int fn3_pair_lists(fn3_engine* e, const int32_t* pos1, const int32_t 
     return rc;
 }
 
+// grow the survivor buffer keeping its first `keep` records and its counter block
+static int grow_out_keep(fn3_engine* e, long long cap, long long keep) {
+    if (cap <= e->out_cap) return FN3_OK;
+    unsigned char* nb = nullptr;
+    CU(e, cudaStreamSynchronize(e->q_stream));
+    CU(e, cudaMalloc(&nb, FN3_OUT_HDR + (size_t)cap * sizeof(EdgeRec)));
+    CU(e, cudaMemcpy(nb, e->d_outbuf, FN3_OUT_HDR + (size_t)keep * sizeof(EdgeRec), cudaMemcpyDeviceToDevice));
+    cudaFree(e->d_outbuf);
+    e->d_outbuf = nb;
+    e->d_count = reinterpret_cast<unsigned long long*>(nb);
+    e->d_out = reinterpret_cast<EdgeRec*>(nb + FN3_OUT_HDR);
+    e->out_cap = cap;
+    return FN3_OK;
+}
+
 extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only, int64_t row_begin, int64_t row_end,
                               int64_t stride, int64_t phase, fn3_edge* out, int64_t cap, int64_t* n_out) {
     if (!e || !n_out || (cap > 0 && !out) || stride < 1 || phase < 0 || phase >= stride)
@@ -960,44 +984,75 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
     if (row_begin < 0) row_begin = 0;
     if (row_end > n_store) row_end = n_store;
     *n_out = 0;
-    long long total = 0;
     int rc;
     const int T = e->n_slots;
-    if ((rc = ensure_out(e, std::max<long long>(1, (long long)T * n_store)))) return rc;
     std::vector<long long> qrows;
+    std::vector<RowHdr> qhdr;
+    std::vector<uint32_t> qblk;
     {
         std::lock_guard<std::mutex> g(e->store_mu);
         for (long long r = row_begin; r < row_end; ++r)
-            if ((r % stride) == phase && e->h_flags[(size_t)r] == 0) qrows.push_back(r);
+            if ((r % stride) == phase && e->h_flags[(size_t)r] == 0) {
+                qrows.push_back(r); qhdr.push_back(e->h_hdr[(size_t)r]); qblk.push_back(e->h_nblk[(size_t)r]);
+            }
     }
-    for (size_t t0 = 0; t0 < qrows.size(); t0 += (size_t)T) {
-        const int ns = (int)std::min<size_t>((size_t)T, qrows.size() - t0);
-        {
-            std::lock_guard<std::mutex> g(e->store_mu);
-            for (int s = 0; s < ns; ++s) {
-                const long long r = qrows[t0 + s];
-                QuerySlot& qs = e->h_slots[s];
-                qs.hdr = e->h_hdr[(size_t)r]; qs.row = r; qs.exclude = r; qs.skip_le = upper_only ? r : -1; qs.pad = 0;
-                e->slot_blocks[s] = e->h_nblk[(size_t)r];
+    // Tiles of T queries are queued FN3_SLOT_RING at a time with no host synchronisation in between; edges
+    // accumulate behind one device counter.  After each batch the counter is read back; if the batch overflowed
+    // the buffer (the kernels never write past it) the buffer grows and the batch is repeated.
+    if ((rc = ensure_out(e, std::max<long long>(1 << 20, 4 * (long long)qrows.size())))) return rc;
+    CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
+    long long total = 0;
+    const size_t n_tiles = (qrows.size() + (size_t)T - 1) / (size_t)T;
+    for (size_t b0 = 0; b0 < n_tiles; b0 += FN3_SLOT_RING) {
+        const size_t b1 = std::min(n_tiles, b0 + (size_t)FN3_SLOT_RING);
+        for (;;) {
+            for (size_t t = b0; t < b1; ++t) {
+                const size_t q0 = t * (size_t)T;
+                const int ns = (int)std::min<size_t>((size_t)T, qrows.size() - q0);
+                job.ns = ns;
+                job.slot_base = (int)(t - b0) * FN3_MAX_SLOTS;
+                job.blocks = 1;
+                for (int s = 0; s < ns; ++s) {
+                    const long long r = qrows[q0 + s];
+                    QuerySlot& qs = e->h_slots[job.slot_base + s];
+                    qs.hdr = qhdr[q0 + s]; qs.row = r; qs.exclude = r; qs.skip_le = upper_only ? r : -1; qs.pad = 0;
+                    job.blocks = std::max(job.blocks, qblk[q0 + s]);
+                }
+                if ((rc = enqueue_query(e, job))) return rc;
             }
-        }
-        job.ns = ns;
-        CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
-        if ((rc = enqueue_query(e, job))) return rc;
-        CU(e, cudaMemcpyAsync(e->h_count, e->d_count, FN3_OUT_HDR, cudaMemcpyDeviceToHost, e->q_stream));
-        CU(e, cudaStreamSynchronize(e->q_stream));
-        e->d2h_bytes += FN3_OUT_HDR;
-        const long long cnt = (long long)e->h_count[0];
-        if (cnt > 0) {
-            if (total + cnt <= cap) {
-                CU(e, cudaMemcpy(out + total, e->d_out, (size_t)cnt * sizeof(EdgeRec), cudaMemcpyDeviceToHost));
-                e->d2h_bytes += cnt * (long long)sizeof(EdgeRec);
-            }
-            total += cnt;
+            CU(e, cudaMemcpyAsync(e->h_count, e->d_count, FN3_OUT_HDR, cudaMemcpyDeviceToHost, e->q_stream));
+            CU(e, cudaStreamSynchronize(e->q_stream));
+            e->d2h_bytes += FN3_OUT_HDR;
+            const long long cnt = (long long)e->h_count[0];
+            if (cnt <= e->out_cap) { total = cnt; break; }
+            // overflow: records beyond the capacity were dropped; keep what earlier batches wrote, grow, redo the batch
+            if ((rc = grow_out_keep(e, std::max<long long>(cnt * 2, e->out_cap * 4), total))) return rc;
+            e->h_count[0] = (unsigned long long)total;
+            CU(e, cudaMemcpyAsync(e->d_count, e->h_count, sizeof(unsigned long long), cudaMemcpyHostToDevice, e->q_stream));
+            CU(e, cudaStreamSynchronize(e->q_stream));
         }
     }
     *n_out = total;
+    e->edges_ready = total;                           // fetchable until the next query on this engine
     if (total > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld edges, %lld needed", (long long)cap, total);
+    if (total > 0) {
+        CU(e, cudaMemcpy(out, e->d_out, (size_t)total * sizeof(EdgeRec), cudaMemcpyDeviceToHost));
+        e->d2h_bytes += total * (long long)sizeof(EdgeRec);
+    }
+    return FN3_OK;
+}
+
+extern "C" int fn3_all_vs_all_fetch(fn3_engine* e, fn3_edge* out, int64_t cap, int64_t* n_out) {
+    if (!e || !n_out || (cap > 0 && !out)) return set_err(e, FN3_EARG, "fn3_all_vs_all_fetch: bad arguments");
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    if (e->edges_ready < 0) return set_err(e, FN3_ENOTFOUND, "fn3_all_vs_all_fetch: no all-vs-all result is pending");
+    *n_out = e->edges_ready;
+    if (e->edges_ready > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld edges, %lld needed", (long long)cap, e->edges_ready);
+    if (e->edges_ready > 0) {
+        CU(e, cudaMemcpy(out, e->d_out, (size_t)e->edges_ready * sizeof(EdgeRec), cudaMemcpyDeviceToHost));
+        e->d2h_bytes += e->edges_ready * (long long)sizeof(EdgeRec);
+    }
     return FN3_OK;
 }
 
@@ -1095,6 +1150,7 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     CU(e, cudaSetDevice(e->device));
     QueryJob job; job.ceiling = ceiling;
     snapshot_store(e, job);
+    e->edges_ready = -1;
     int rc = FN3_OK;
     if ((rc = ensure_out(e, std::max<long long>(job.n_rows, 1)))) return rc;
     if (flush_l2 && !e->d_flush) {

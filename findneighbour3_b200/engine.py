@@ -216,16 +216,15 @@ class Engine:
         if row_end is None:
             row_end = self.stats()["n_rows"]
         n_out = C.c_int64(0)
-        while True:
-            buf = self._edges
-            rc = self._lib.fn3_all_vs_all(self._h, int(ceiling), 1 if upper_only else 0, int(row_begin), int(row_end),
-                                          int(stride), int(phase), buf.ctypes.data_as(C.POINTER(N.Edge)), buf.size,
-                                          C.byref(n_out))
-            if rc == N.FN3_ECAPACITY:
-                self._edges = np.empty(int(n_out.value) + 1024, dtype=EDGE_DTYPE)
-                continue
-            self._check(rc)
-            return buf[: n_out.value].copy()
+        buf = self._edges
+        rc = self._lib.fn3_all_vs_all(self._h, int(ceiling), 1 if upper_only else 0, int(row_begin), int(row_end),
+                                      int(stride), int(phase), buf.ctypes.data_as(C.POINTER(N.Edge)), buf.size,
+                                      C.byref(n_out))
+        if rc == N.FN3_ECAPACITY:                 # the edges are still on the device: fetch, do not recompute
+            buf = self._edges = np.empty(int(n_out.value), dtype=EDGE_DTYPE)
+            rc = self._lib.fn3_all_vs_all_fetch(self._h, buf.ctypes.data_as(C.POINTER(N.Edge)), buf.size, C.byref(n_out))
+        self._check(rc)
+        return buf[: n_out.value].copy()
 
     def pair(self, row1, row2, ceiling):
         """countDifferences_byKey on stored rows -> (dist,n1,n2,nboth) or None."""

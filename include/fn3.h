@@ -157,6 +157,10 @@ int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only,
                    int64_t row_begin, int64_t row_end, int64_t stride, int64_t phase,
                    fn3_edge* out, int64_t cap, int64_t* n_out);
 
+/* When fn3_all_vs_all returns FN3_ECAPACITY the edges stay on the device: fetch them into a buffer of at least
+ * *n_out entries without recomputing (valid until the next query call on this engine). */
+int fn3_all_vs_all_fetch(fn3_engine* e, fn3_edge* out, int64_t cap, int64_t* n_out);
+
 /* countDifferences_byKey((k1,k2), cutoff) (:382-421) on two stored rows.
  * *has_dist = 0 reproduces the reference's None distance (invalid sample or > ceiling). */
 int fn3_pair(fn3_engine* e, int64_t row1, int64_t row2, int32_t ceiling,

@@ -419,3 +419,24 @@ def test_msa_golden():
                              'expected_proportion1', 'expected_proportion2', 'expected_proportion3', 'expected_proportion4'])
         assert set(df.columns.values) == expected_cols
         assert len(df.index) == len(want["guid2msa_seq"])
+
+
+def test_all_vs_all_batched_tiles_vs_one_vs_all():
+    """all-vs-all queues many query tiles between host synchronisations and grows its edge buffer on overflow:
+    on a collection with more than FN3_SLOT_RING tiles its edges must equal the union of one-vs-all results."""
+    from findneighbour3_b200.engine import Engine
+    coll = _synthetic(12, 40, 300000, 71, k1=200, s=2.0, n_blocks=6, n_mean=1500, m_mean=2, rule="any", p_invalid=0.02)
+    eng = Engine(coll.genome_length, 0)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    assert coll.n > 32 * 8                                   # several batches of tiles
+    for ceiling in (12, 400):
+        edges = eng.all_vs_all(ceiling, upper_only=True)
+        got = {(int(e["row1"]), int(e["row2"])): (int(e["dist"]), int(e["n1"]), int(e["n2"]), int(e["nboth"])) for e in edges}
+        assert len(got) == len(edges)                        # no duplicates
+        want = {}
+        for q in range(coll.n):
+            for r, v in hits_to_dict(eng.one_vs_all(q, ceiling)).items():
+                if q < r:
+                    want[(q, r)] = v
+        assert got == want
+    eng.close()

@@ -95,6 +95,12 @@ struct fn3_engine {
     unsigned long long* h_count = nullptr;
     EdgeRec* h_out = nullptr; long long h_out_cap = 0;
     std::atomic<long long> h2d_bytes{0}, d2h_bytes{0};
+    // zero-copy completion of one-vs-all queries (mapped pinned memory)
+    unsigned char* zc_buf = nullptr;         // [64-byte flag block | FN3_ZC_CAP records]
+    unsigned int* d_done = nullptr;
+    unsigned long long zc_seq = 0;
+    bool count_dirty = false;                // the device counter was left non-zero by a path that does not re-arm it
+    bool zero_copy = true;
     long long edges_ready = -1;              // edges of the last fn3_all_vs_all still in d_out (-1: none)
     long long* d_rows = nullptr; long long d_rows_cap = 0;
     long long* h_rows = nullptr; long long h_rows_cap = 0;       // pinned
@@ -144,6 +150,7 @@ extern "C" const char* fn3_last_error(fn3_engine* e) {
 extern "C" int64_t fn3_launch_count(fn3_engine* e) { return e ? e->launches.load() : 0; }
 
 #define FN3_SLOT_RING 32        // all-vs-all: query tiles queued between two host synchronisations
+#define FN3_ZC_CAP 4096         // survivor records the mapped host buffer holds (longer lists: one extra copy)
 #define FN3_OUT_HDR 32
 #define FN3_FIRST_HITS 256      // records fetched together with the counter
 
@@ -154,6 +161,7 @@ static int ensure_out(fn3_engine* e, long long cap) {
     if (e->d_outbuf) { cudaStreamSynchronize(e->q_stream); cudaFree(e->d_outbuf); }
     e->d_outbuf = nullptr; e->out_cap = 0;
     CU(e, cudaMalloc(&e->d_outbuf, FN3_OUT_HDR + (size_t)want * sizeof(EdgeRec)));
+    CU(e, cudaMemsetAsync(e->d_outbuf, 0, FN3_OUT_HDR, e->q_stream));
     e->d_count = reinterpret_cast<unsigned long long*>(e->d_outbuf);
     e->d_out = reinterpret_cast<EdgeRec*>(e->d_outbuf + FN3_OUT_HDR);
     e->out_cap = want;
@@ -296,6 +304,11 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         fn3_destroy(e);
         return nullptr;
     }
+    e->zero_copy = env_ll("FN3_ZERO_COPY", 1) != 0 && e->debug_stop == 0;
+    if ((s = cudaHostAlloc(&e->zc_buf, 64 + (size_t)FN3_ZC_CAP * sizeof(EdgeRec), cudaHostAllocMapped)) != cudaSuccess) return fail("cudaHostAlloc(mapped)", s);
+    memset(e->zc_buf, 0, 64);
+    if ((s = cudaMalloc(&e->d_done, sizeof(unsigned int))) != cudaSuccess) return fail("cudaMalloc(done)", s);
+    if ((s = cudaMemset(e->d_done, 0, sizeof(unsigned int))) != cudaSuccess) return fail("cudaMemset(done)", s);
     if ((s = cudaMalloc(&e->d_scratch_tile, FN3_TILE_BYTES)) != cudaSuccess) return fail("cudaMalloc(scratch tile)", s);
     if ((s = cudaMemset(e->d_scratch_tile, 0, FN3_TILE_BYTES)) != cudaSuccess) return fail("cudaMemset(scratch tile)", s);
     if ((s = cudaDeviceSynchronize()) != cudaSuccess) return fail("cudaDeviceSynchronize", s);
@@ -314,7 +327,8 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     cudaFree(e->d_heads);
     cudaFree(e->d_slots);
     cudaFree(e->d_outbuf); cudaFree(e->d_rows); cudaFree(e->d_scratch);
-    cudaFree(e->d_scratch_tile); cudaFree(e->d_flush);
+    cudaFree(e->d_scratch_tile); cudaFree(e->d_flush); cudaFree(e->d_done);
+    if (e->zc_buf) cudaFreeHost(e->zc_buf);
     cudaFree(e->d_refmask); cudaFree(e->d_seq); cudaFree(e->d_mchars); cudaFree(e->d_cpos);
     cudaFree(e->d_ccounts); cudaFree(e->d_ctotals);
     if (e->h_seq) cudaFreeHost(e->h_seq);
@@ -655,6 +669,7 @@ struct QueryJob {                    // what enqueue_query needs beyond the engi
     const RowHead* commit_head = nullptr;   // fn3_insert_query: head of the new row, placed by the kernel
     long long commit_row = -1;
     cudaEvent_t split = nullptr;         // measurement hook: recorded between the optional build kernel and k_query
+    bool zero_copy = false;              // results + completion through mapped host memory (one-vs-all paths)
 };
 
 // enqueue one query tile on q_stream.  Normally ONE kernel (k_query builds the query structure in shared memory
@@ -692,6 +707,11 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     p.out = e->d_out; p.out_count = e->d_count; p.touched = e->d_count + 1; p.out_cap = e->out_cap;
     p.ceiling = job.ceiling; p.pos_bits = e->pos_bits; p.use_filter = use_filter_for(job.ceiling) ? 1 : 0;
     p.fshift = e->fshift; p.nw = e->nw; p.ncw = e->ncw; p.debug_stop = e->debug_stop;
+    if (job.zero_copy) {
+        p.host_out = reinterpret_cast<EdgeRec*>(e->zc_buf + 64);
+        p.host_flag = reinterpret_cast<volatile unsigned long long*>(e->zc_buf);
+        p.done_ctas = e->d_done; p.host_cap = FN3_ZC_CAP; p.seq = e->zc_seq;
+    }
     const bool filter = p.use_filter != 0;
     const long long warps_per_cta = FN3_Q_THREADS / 32;
     const long long sb = 1ll << e->sb_shift;
@@ -776,25 +796,61 @@ static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int
         job.d_rows = e->d_rows; job.n_list = n;
     }
     if ((rc = ensure_out(e, std::max<long long>(n, 1)))) return rc;
-    CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
-    if ((rc = enqueue_query(e, job))) return rc;
-    // ONE device-to-host copy brings the counter and the first records; a second one only for long lists
-    const long long first = std::min<long long>(std::max<long long>(n, 0), FN3_FIRST_HITS);
-    CU(e, cudaMemcpyAsync(e->h_outbuf, e->d_outbuf, FN3_OUT_HDR + (size_t)first * sizeof(EdgeRec), cudaMemcpyDeviceToHost,
-                          e->q_stream));
-    CU(e, cudaStreamSynchronize(e->q_stream));
-    e->d2h_bytes += FN3_OUT_HDR + first * (long long)sizeof(EdgeRec);
-    const long long cnt = (long long)e->h_count[0];
-    *n_out = cnt;
-    if (cnt > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld hits, %lld needed", (long long)cap, cnt);
-    if (cnt > first) {
-        if ((rc = ensure_hout(e, cnt))) return rc;
-        CU(e, cudaMemcpyAsync(e->h_out, e->d_out, (size_t)cnt * sizeof(EdgeRec), cudaMemcpyDeviceToHost, e->q_stream));
+    const EdgeRec* recs;
+    long long cnt;
+    if (e->zero_copy) {
+        // Results and completion travel through mapped pinned memory: no memset, no device-to-host copy, no
+        // stream synchronisation — the host spins on the sequence number the last CTA writes.
+        if (e->count_dirty) { CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream)); e->count_dirty = false; }
+        job.zero_copy = true;
+        ++e->zc_seq;
+        if ((rc = enqueue_query(e, job))) return rc;
+        volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(e->zc_buf);
+        for (unsigned long long spins = 1; flag[0] != e->zc_seq; ++spins) {
+            if ((spins & 0x3fff) == 0) {
+                const cudaError_t st = cudaStreamQuery(e->q_stream);
+                if (st != cudaSuccess && st != cudaErrorNotReady)
+                    return set_err(e, FN3_ECUDA, "k_query failed: %s", cudaGetErrorString(st));
+                if (st == cudaSuccess && flag[0] != e->zc_seq)
+                    return set_err(e, FN3_ECUDA, "k_query finished without publishing its result");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);      // records are read only after the flag
+        cnt = (long long)flag[1];
+        e->d2h_bytes += 16 + std::min<long long>(cnt, FN3_ZC_CAP) * (long long)sizeof(EdgeRec);
+        recs = reinterpret_cast<const EdgeRec*>(e->zc_buf + 64);
+        *n_out = cnt;
+        if (cnt > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld hits, %lld needed", (long long)cap, cnt);
+        if (cnt > FN3_ZC_CAP) {                       // a very long neighbour list: fetch it from the device buffer
+            if ((rc = ensure_hout(e, cnt))) return rc;
+            CU(e, cudaMemcpyAsync(e->h_out, e->d_out, (size_t)cnt * sizeof(EdgeRec), cudaMemcpyDeviceToHost, e->q_stream));
+            CU(e, cudaStreamSynchronize(e->q_stream));
+            e->d2h_bytes += cnt * (long long)sizeof(EdgeRec);
+            recs = e->h_out;
+        }
+    } else {
+        CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
+        if ((rc = enqueue_query(e, job))) return rc;
+        // ONE device-to-host copy brings the counter and the first records; a second one only for long lists
+        const long long first = std::min<long long>(std::max<long long>(n, 0), FN3_FIRST_HITS);
+        CU(e, cudaMemcpyAsync(e->h_outbuf, e->d_outbuf, FN3_OUT_HDR + (size_t)first * sizeof(EdgeRec), cudaMemcpyDeviceToHost,
+                              e->q_stream));
         CU(e, cudaStreamSynchronize(e->q_stream));
-        e->d2h_bytes += cnt * (long long)sizeof(EdgeRec);
+        e->d2h_bytes += FN3_OUT_HDR + first * (long long)sizeof(EdgeRec);
+        cnt = (long long)e->h_count[0];
+        e->count_dirty = true;
+        *n_out = cnt;
+        if (cnt > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld hits, %lld needed", (long long)cap, cnt);
+        if (cnt > first) {
+            if ((rc = ensure_hout(e, cnt))) return rc;
+            CU(e, cudaMemcpyAsync(e->h_out, e->d_out, (size_t)cnt * sizeof(EdgeRec), cudaMemcpyDeviceToHost, e->q_stream));
+            CU(e, cudaStreamSynchronize(e->q_stream));
+            e->d2h_bytes += cnt * (long long)sizeof(EdgeRec);
+        }
+        recs = e->h_out;
     }
     for (long long i = 0; i < cnt; ++i) {
-        const EdgeRec& r = e->h_out[i];
+        const EdgeRec& r = recs[i];
         out[i].row = r.row2; out[i].dist = r.dist; out[i].n1 = r.n1; out[i].n2 = r.n2; out[i].nboth = r.nboth;
     }
     return FN3_OK;
@@ -881,7 +937,7 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     QueryJob job; job.ceiling = ceiling;
     fill_hdr_table(e, job.ht);
     job.n_rows = row;                                // candidates: every earlier row
-    job.commit_head = &head; job.commit_row = row;
+    if (!invalid) { job.commit_head = &head; job.commit_row = row; }   // an invalid row's head stays zero
     set_slot0(e, h, row, row);
     e->slot_blocks[0] = nblk;
     return run_one_vs_all(e, job, nullptr, 0, out, cap, n_out);
@@ -1001,6 +1057,7 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
     // the buffer (the kernels never write past it) the buffer grows and the batch is repeated.
     if ((rc = ensure_out(e, std::max<long long>(1 << 20, 4 * (long long)qrows.size())))) return rc;
     CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
+    e->count_dirty = true;
     long long total = 0;
     const size_t n_tiles = (qrows.size() + (size_t)T - 1) / (size_t)T;
     for (size_t b0 = 0; b0 < n_tiles; b0 += FN3_SLOT_RING) {
@@ -1151,6 +1208,7 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     QueryJob job; job.ceiling = ceiling;
     snapshot_store(e, job);
     e->edges_ready = -1;
+    e->count_dirty = true;
     int rc = FN3_OK;
     if ((rc = ensure_out(e, std::max<long long>(job.n_rows, 1)))) return rc;
     if (flush_l2 && !e->d_flush) {

@@ -353,11 +353,31 @@ __device__ __forceinline__ void emit_if_close(const CompareParams& p, const Tall
             r.row1 = qrow; r.row2 = crow; r.dist = dist;
             r.n1 = (int)nUq; r.n2 = nNc + (int)nMq - nNM; r.nboth = (int)nUq + nNc - nNU;
             p.out[at] = r;
+            if (p.host_out && (long long)at < p.host_cap) p.host_out[at] = r;      // posted write over PCIe
         }
     }
 }
 
 // QMODE 0: query structure in global memory (built by k_build_query); 1: built here in shared memory
+// zero-copy completion: every CTA makes its host-memory records visible, the last one publishes count + sequence
+// number to the mapped host flag and re-arms the device counters (so the next query needs no memset).
+__device__ __forceinline__ void signal_done(const CompareParams& p) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y;
+        const unsigned int t = atomicAdd(p.done_ctas, 1u);
+        if (t == total - 1u) {
+            __threadfence();
+            const unsigned long long cnt = atomicExch(p.out_count, 0ull);
+            *p.done_ctas = 0u;
+            p.host_flag[1] = cnt;
+            __threadfence_system();
+            p.host_flag[0] = p.seq;
+        }
+    }
+}
+
 #ifndef FN3_Q_MINB
 #define FN3_Q_MINB 2
 #endif
@@ -371,7 +391,10 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     const QuerySlot qs = p.slot_inline ? p.slot0 : p.slots[slot];
     if (p.commit_row >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
         put_head(p.hdr, p.commit_row, p.commit_head);      // fn3_insert_query: the new row's head (never a candidate here)
-    if (qs.hdr.data == 0ull) return;                       // invalid query: no distances at all
+    if (qs.hdr.data == 0ull) {                             // invalid query: no distances at all
+        if (p.host_flag) signal_done(p);
+        return;
+    }
     if (p.debug_stop == 4) return;
     const int nw = p.nw, ncw = p.ncw;
     uint32_t nVq, nUq, nMq;
@@ -505,6 +528,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
         for (int o = 16; o > 0; o >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, o);
         if (lane == 0) atomicAdd(p.touched, touched);
     }
+    if (p.host_flag) signal_done(p);
 }
 
 // L2 flush helper for the measurement hook

@@ -101,6 +101,13 @@ struct CompareParams {
     unsigned long long* out_count;
     unsigned long long* touched;   // instrumented variant only
     long long out_cap;
+    // zero-copy completion (one-vs-all): survivors are ALSO written to mapped pinned host memory; the last CTA to
+    // finish publishes the count and the sequence number there and re-arms the device counters for the next query
+    EdgeRec* host_out;             // mapped host buffer (nullptr = off)
+    volatile unsigned long long* host_flag;   // mapped: [0] sequence number, [1] survivor count
+    unsigned int* done_ctas;       // device counter of finished CTAs
+    long long host_cap;
+    unsigned long long seq;
     int slot_inline;
     int ceiling;
     int pos_bits;

@@ -30,7 +30,8 @@ class Edge(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_live", C.c_int64), ("n_invalid", C.c_int64),
                 ("store_words", C.c_int64), ("store_bytes", C.c_int64), ("positions", C.c_int64),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("t_pack_ns", C.c_int64),
+                ("t_enqueue_ns", C.c_int64), ("t_wait_ns", C.c_int64), ("n_timed", C.c_int64)]
 
 
 _i32p = C.POINTER(C.c_int32)

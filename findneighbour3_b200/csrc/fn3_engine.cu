@@ -26,6 +26,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <chrono>
 
 static_assert(sizeof(RowHdr) == 32, "RowHdr must be one 32-byte sector");
 static_assert(sizeof(RowHead) == 96, "RowHead must be 96 bytes");
@@ -101,6 +102,7 @@ struct fn3_engine {
     unsigned long long zc_seq = 0;
     bool count_dirty = false;                // the device counter was left non-zero by a path that does not re-arm it
     bool zero_copy = true;
+    long long t_pack_ns = 0, t_enqueue_ns = 0, t_wait_ns = 0, n_timed = 0;   // fn3_insert_query host-time split
     long long edges_ready = -1;              // edges of the last fn3_all_vs_all still in d_out (-1: none)
     long long* d_rows = nullptr; long long d_rows_cap = 0;
     long long* h_rows = nullptr; long long h_rows_cap = 0;       // pinned
@@ -601,6 +603,7 @@ extern "C" int fn3_stats_get(fn3_engine* e, fn3_stats* out) {
     out->n_rows = e->n_rows; out->n_live = e->n_live; out->n_invalid = e->n_invalid;
     out->store_words = e->store_words; out->store_bytes = e->store_bytes; out->positions = e->positions;
     out->h2d_bytes = e->h2d_bytes.load(); out->d2h_bytes = e->d2h_bytes.load();
+    out->t_pack_ns = e->t_pack_ns; out->t_enqueue_ns = e->t_enqueue_ns; out->t_wait_ns = e->t_wait_ns; out->n_timed = e->n_timed;
     return FN3_OK;
 }
 
@@ -804,7 +807,10 @@ static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int
         if (e->count_dirty) { CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream)); e->count_dirty = false; }
         job.zero_copy = true;
         ++e->zc_seq;
+        const auto t_enq = std::chrono::steady_clock::now();
         if ((rc = enqueue_query(e, job))) return rc;
+        const auto t_wait = std::chrono::steady_clock::now();
+        e->t_enqueue_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(t_wait - t_enq).count();
         volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(e->zc_buf);
         for (unsigned long long spins = 1; flag[0] != e->zc_seq; ++spins) {
             if ((spins & 0x3fff) == 0) {
@@ -816,6 +822,7 @@ static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int
             }
         }
         std::atomic_thread_fence(std::memory_order_acquire);      // records are read only after the flag
+        e->t_wait_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_wait).count();
         cnt = (long long)flag[1];
         e->d2h_bytes += 16 + std::min<long long>(cnt, FN3_ZC_CAP) * (long long)sizeof(EdgeRec);
         recs = reinterpret_cast<const EdgeRec*>(e->zc_buf + 64);
@@ -900,6 +907,7 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     CU(e, cudaSetDevice(e->device));
     std::lock_guard<std::mutex> g(e->store_mu);      // held to the end: the pinned staging row must not be repacked
     RowHdr h; memset(&h, 0, sizeof h);               // by a concurrent append before the stream has consumed it
+    const auto t_begin = std::chrono::steady_clock::now();
     uint32_t nblk = 0;
     long long o[7] = {0, 0, 0, 0, 0, 0, 0};
     if (!invalid) for (int b = 0; b < 7; ++b) o[b] = off[b];
@@ -923,6 +931,8 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     }
     RowHead head;
     fill_head(e, head, h, e->stage);
+    e->t_pack_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
+    e->n_timed++;
     CU(e, cudaMemcpyAsync(dbase, e->stage, need * 4, cudaMemcpyHostToDevice, e->q_stream));
     e->h2d_bytes += (long long)need * 4;
     e->h_hdr.push_back(h);

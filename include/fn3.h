@@ -83,6 +83,10 @@ typedef struct fn3_stats {
     int64_t positions;       /* sum over live rows of |A|+|C|+|G|+|T|+|N|+|M| (canonical B_pair positions) */
     int64_t h2d_bytes;       /* bytes copied host->device by this engine since creation */
     int64_t d2h_bytes;       /* bytes copied device->host by this engine since creation */
+    int64_t t_pack_ns;       /* fn3_insert_query host-time split (cumulative): validate + pack the sample */
+    int64_t t_enqueue_ns;    /*   ... enqueue the copies and the kernel */
+    int64_t t_wait_ns;       /*   ... wait for the result */
+    int64_t n_timed;         /*   ... number of fn3_insert_query calls timed */
 } fn3_stats;
 
 /* ---- life cycle ------------------------------------------------------------------ */

@@ -15,7 +15,7 @@ every query is compared against all shards.
   e2e       the same metric through the C-ABI a user of the reference class would sit on
             (persist -> fn3_append, mcompare -> fn3_one_vs_all) with HOST buffers: every step copies the new
             sample's packed lists host->device and the neighbour records device->host; wall clock, max over ranks.
-  roofline  dominant kernel = k_compare.  achieved = algorithmic bytes / mean CUDA-event duration of the
+  roofline  dominant kernel = k_query.  achieved = algorithmic bytes / mean CUDA-event duration of the
             compare launch, algorithmic bytes = sum over compared candidates of B_pair = 4*(|A|+|C|+|G|+|T|+|N|+|M|)+32
             (SURVEY.md §8(d)).  Early exit and N-run coding make the kernel touch far fewer bytes than that,
             so `frac` can exceed 1; `touched_*` and `fullscan` (ceiling = 2^31-1: no pair may exit early,
@@ -63,7 +63,7 @@ def peaks():
 
 
 def ncu_traffic():
-    """per-launch DRAM bytes of k_compare from the committed ncu capture, if any (profiles/traffic.json)."""
+    """per-launch DRAM bytes of k_query from the committed ncu capture, if any (profiles/traffic.json)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         try:
@@ -362,9 +362,9 @@ def main():
     achieved = bytes_canon_all / (cmp_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     roofline = {
-        "bound": "hbm", "kernel": "k_compare", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+        "bound": "hbm", "kernel": "k_query", "achieved": achieved, "peak": peak, "peak_source": peak_src,
         "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None if not traffic else traffic.get("k_compare_bytes_per_launch"),
+        "traffic": None if not traffic else traffic.get("k_query_bytes_per_launch"),
         "launch_ms": cmp_ms,
         "algorithmic_bytes_per_launch": bytes_canon_all,
         "store_bytes_per_launch": store_bytes_rows,

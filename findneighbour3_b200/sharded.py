@@ -19,7 +19,7 @@ HIT_FIELDS = 5          # row, dist, n1, n2, nboth
 
 
 class ShardedStore:
-    def __init__(self, engine, group=None, max_hits=1024, local_rows=0):
+    def __init__(self, engine, group=None, max_hits=512, local_rows=0):
         self.engine = engine
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -27,12 +27,18 @@ class ShardedStore:
         backend = dist.get_backend(group) if dist.is_initialized() else "gloo"
         self.dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         self.max_hits = int(max_hits)
-        self.bcast_cap = 1 << 15                 # positions carried by the single fixed-size broadcast
+        self.bcast_cap = 1 << 13                 # positions carried by the single fixed-size broadcast (32 KB)
         self._bbuf = torch.zeros(9 + self.bcast_cap, dtype=torch.int32)
-        self._dbuf = None
+        self._hblk = torch.zeros(1 + HIT_FIELDS * self.max_hits, dtype=torch.int32)
+        self._dbuf = self._dhblk = self._dhall = self._hhall = None
         if self.dev.type == "cuda":
             self._bbuf = self._bbuf.pin_memory()
+            self._hblk = self._hblk.pin_memory()
             self._dbuf = torch.zeros(9 + self.bcast_cap, dtype=torch.int32, device=self.dev)
+            self._dhblk = torch.zeros(1 + HIT_FIELDS * self.max_hits, dtype=torch.int32, device=self.dev)
+            self._dhall = torch.zeros(self.world * (1 + HIT_FIELDS * self.max_hits), dtype=torch.int32, device=self.dev)
+            self._hhall = torch.zeros(self.world * (1 + HIT_FIELDS * self.max_hits), dtype=torch.int32).pin_memory()
+        self._bbuf_np = self._bbuf.numpy()
         # `local_rows`: rows the engine already holds (every rank the same number, placed as by load_shard)
         self._local_rows = int(local_rows)
         self.n_global = self._local_rows * self.world       # samples inserted so far (same value on every rank)
@@ -67,28 +73,27 @@ class ShardedStore:
         if self.world == 1:
             return sample
         cap = self.bcast_cap
-        buf = self._bbuf
-        n = 0
+        buf = self._bbuf_np                       # numpy view of the (pinned) staging tensor
         if self.rank == src:
             pos, off, invalid = sample
             n = 0 if invalid else len(pos)
             buf[0] = n
-            buf[1:8] = 0 if invalid else torch.from_numpy(np.asarray(off, dtype=np.int32))
+            buf[1:8] = 0 if invalid else off
             buf[8] = 1 if invalid else 0
             m = min(n, cap)
             if m:
-                buf[9:9 + m] = torch.from_numpy(np.ascontiguousarray(pos[:m], dtype=np.int32))
+                buf[9:9 + m] = pos[:m]
         if self.dev.type == "cuda":
-            dbuf = self._dbuf
-            dbuf.copy_(buf, non_blocking=True)
-            dist.broadcast(dbuf, src=src, group=self.group)
-            buf.copy_(dbuf)                       # synchronises
+            self._dbuf.copy_(self._bbuf, non_blocking=True)
+            dist.broadcast(self._dbuf, src=src, group=self.group)
+            self._bbuf.copy_(self._dbuf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         else:
-            dist.broadcast(buf, src=src, group=self.group)
+            dist.broadcast(self._bbuf, src=src, group=self.group)
         n = int(buf[0])
-        off = buf[1:8].numpy().astype(np.int32)
+        off = buf[1:8].astype(np.int32)
         invalid = bool(buf[8])
-        pos = buf[9:9 + min(n, cap)].numpy().copy()
+        pos = buf[9:9 + min(n, cap)].copy()
         if n > cap:                               # rare: a sample larger than the fixed buffer
             rest = torch.zeros(n - cap, dtype=torch.int32)
             if self.rank == src:
@@ -107,19 +112,43 @@ class ShardedStore:
         return out.cpu().reshape(self.world, -1)
 
     def _gather_hits(self, hits):
-        """each rank's structured hits (local rows) -> dict {global id: (dist, n1, n2, nboth)} on every rank."""
+        """each rank's structured hits (local rows) -> dict {global id: (dist, n1, n2, nboth)} on every rank.
+        One all-gather of fixed-size int32 blocks [count | row, dist, n1, n2, nboth ...] through pre-allocated
+        (pinned / device) buffers; a second, larger one only if some rank overflowed its block."""
         cap = self.max_hits
+        n = len(hits)
         while True:
-            block = torch.zeros(1 + HIT_FIELDS * cap, dtype=torch.int64)
-            n = len(hits)
-            block[0] = n
+            if cap == self.max_hits:
+                blk, dblk, dall, hall = self._hblk, self._dhblk, self._dhall, self._hhall
+            else:                                   # overflow round: temporary buffers
+                blk = torch.zeros(1 + HIT_FIELDS * cap, dtype=torch.int32)
+                dblk = dall = hall = None
+            b = blk.numpy()
+            b[0] = n
             m = min(n, cap)
             if m:
-                rec = np.stack([hits["row"][:m].astype(np.int64), hits["dist"][:m].astype(np.int64),
-                                hits["n1"][:m].astype(np.int64), hits["n2"][:m].astype(np.int64),
-                                hits["nboth"][:m].astype(np.int64)], axis=1)
-                block[1:1 + HIT_FIELDS * m] = torch.from_numpy(rec.reshape(-1))
-            allb = self._all_gather_i64(block)
+                rec = b[1:1 + HIT_FIELDS * m].reshape(m, HIT_FIELDS)
+                rec[:, 0] = hits["row"][:m]
+                rec[:, 1] = hits["dist"][:m]
+                rec[:, 2] = hits["n1"][:m]
+                rec[:, 3] = hits["n2"][:m]
+                rec[:, 4] = hits["nboth"][:m]
+            if self.world == 1:
+                allb = b.reshape(1, -1)
+            elif self.dev.type == "cuda":
+                if dblk is None:
+                    dblk = torch.empty_like(blk, device=self.dev)
+                    dall = torch.empty(self.world * blk.numel(), dtype=torch.int32, device=self.dev)
+                    hall = torch.empty(self.world * blk.numel(), dtype=torch.int32).pin_memory()
+                dblk.copy_(blk, non_blocking=True)
+                dist.all_gather_into_tensor(dall, dblk, group=self.group)
+                hall.copy_(dall, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                allb = hall.numpy().reshape(self.world, -1)
+            else:
+                hall = torch.empty(self.world * blk.numel(), dtype=torch.int32)
+                dist.all_gather_into_tensor(hall, blk, group=self.group)
+                allb = hall.numpy().reshape(self.world, -1)
             counts = allb[:, 0]
             if int(counts.max()) <= cap:
                 break
@@ -127,9 +156,11 @@ class ShardedStore:
         out = {}
         for r in range(self.world):
             c = int(counts[r])
-            rec = allb[r, 1:1 + HIT_FIELDS * c].reshape(c, HIT_FIELDS).numpy()
-            for row, d, n1, n2, nb in rec:
-                out[self.global_id(r, int(row))] = (int(d), int(n1), int(n2), int(nb))
+            if c == 0:
+                continue
+            rec = allb[r, 1:1 + HIT_FIELDS * c].reshape(c, HIT_FIELDS)
+            gids = (rec[:, 0].astype(np.int64) * self.world + r).tolist()
+            out.update(zip(gids, map(tuple, rec[:, 1:].tolist())))
         return out
 
     # -- the hot path -----------------------------------------------------------------------

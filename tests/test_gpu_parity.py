@@ -440,3 +440,39 @@ def test_all_vs_all_batched_tiles_vs_one_vs_all():
                     want[(q, r)] = v
         assert got == want
     eng.close()
+
+
+def test_config1_incremental_through_the_class_full_genome():
+    """BASELINE.json configs[0] flow through the drop-in class on a full-length (4.4 Mb) genome: sequence STRINGS ->
+    device compress -> persist -> mcompare after every insert, every neighbour list checked against the C oracle
+    (reduced to 120 samples so the test stays within seconds; bench.py / test_properties_at_scale cover the sizes)."""
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.seqComparer import seqComparer
+    from oracle import c_oracle
+    L = synth.TB_LENGTH
+    mask = synth.synthetic_mask(L, synth.TB_EXCLUDED, synth.TB_EXCLUDED_RUNS)
+    coll = synth.make_collection(4, 30, seed=1, excluded=mask, m_mean=3, rule="any")
+    ref_codes = synth.random_reference(L)
+    ref = synth.reference_string(ref_codes)
+    excluded = set(np.flatnonzero(mask).tolist())
+    sc = seqComparer(reference=ref, maxNs=130000, snpCeiling=20, excludePositions=excluded)
+    for i in range(coll.n):
+        p, o, inv = coll.lists(i)
+        if inv:
+            seq = "N" * L                                  # an all-N sample: invalid under maxNs
+        else:
+            seq = synth.to_string(ref_codes, p, o)
+        obj = sc.compress(seq)
+        assert obj["invalid"] == (1 if inv else 0)
+        if not inv:                                        # compress must give back exactly the generated lists
+            got = np.concatenate([np.sort(np.fromiter(obj[k], np.int64, len(obj[k]))) for k in "ACGTN"] +
+                                 [np.sort(np.fromiter(obj["M"].keys(), np.int64, len(obj["M"])))])
+            assert np.array_equal(got, p.astype(np.int64))
+        sc.persist(obj, "s%d" % i)
+        if i % 4 == 3 or i == coll.n - 1:
+            res = sc.mcompare("s%d" % i)
+            assert len(res) == i
+            got = {int(r[1][1:]): tuple(r[2:6]) for r in res if r[2] is not None}
+            sub = coll.subset(np.arange(i + 1))
+            assert got == c_oracle.one_vs_all(sub.pos, sub.off, sub.invalid, i, 20)
+    assert sc.summarise_stored_items()["server|scstat|nSeqs"] == coll.n

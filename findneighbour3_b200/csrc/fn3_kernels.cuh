@@ -378,11 +378,43 @@ __device__ __forceinline__ void signal_done(const CompareParams& p) {
     }
 }
 
+// phase A loads of one work unit (32 candidates: a tile of the full scan, or 32 strided entries of an explicit list):
+// header and fingerprints of this lane's candidate, requested together — ONE memory round trip.
+struct HeadRegs { uint4 h0, h1, f[4]; long long row; bool have; };
+
+__device__ __forceinline__ HeadRegs load_head(const CompareParams& p, const QuerySlot& qs, long long u, long long units,
+                                              int lane, int tshift) {
+    HeadRegs r;
+    r.h0 = make_uint4(0, 0, 0, 0); r.h1 = r.h0; r.row = -1; r.have = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.f[j] = r.h0;
+    const unsigned char* tile = nullptr;
+    int tl = lane;
+    if (p.rows) {
+        const long long ci = u + (long long)lane * units;
+        if (ci < p.n_list) { r.row = p.rows[ci]; tile = tile_of(p.hdr, r.row, tl); }
+    } else {
+        const long long chunk = u >> tshift, lt = u & ((1ll << tshift) - 1);
+        r.row = (chunk << p.hdr.shift) + fn3_row_of(lt, lane, p.hdr.sb_shift);
+        tile = p.hdr.chunk[chunk] + lt * FN3_TILE_BYTES;
+        if (r.row >= p.n_rows) r.row = -1;
+    }
+    if (r.row >= 0 && r.row != qs.exclude && r.row > qs.skip_le) {
+        const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
+        const uint4* fp = reinterpret_cast<const uint4*>(tile + FN3_TILE_FP_OFF + tl * 16);
+        r.h0 = __ldg(hp); r.h1 = __ldg(hp + 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.f[j] = __ldg(fp + j * 32);
+        r.have = true;
+    }
+    return r;
+}
+
 #ifndef FN3_Q_MINB
 #define FN3_Q_MINB 2
 #endif
 template <bool COUNT, int QMODE, bool FILTER>
-__global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const CompareParams p) {
+__global__ void __launch_bounds__(FN3_Q_THREADS, FILTER ? 1 : FN3_Q_MINB) k_query(const CompareParams p) {
     extern __shared__ __align__(128) uint4 qsm[];
     __shared__ uint32_t ws[99];
     if (p.debug_stop == 3) return;
@@ -397,6 +429,16 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     }
     if (p.debug_stop == 4) return;
     const int nw = p.nw, ncw = p.ncw;
+    const int tshift = p.hdr.shift - 5;                    // tiles per chunk = 1 << tshift
+    // FILTER: work unit = 32 candidates.  Consecutive units (tiles hold consecutively inserted rows, i.e. relatives)
+    // go to different CTAs, so that the few surviving candidates of a family are streamed on different SMs.  The
+    // first unit's heads are requested NOW: their memory round trip overlaps the query build below.
+    const long long units = !FILTER ? 0 : p.rows ? (p.n_list + 31) >> 5
+                            : ((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
+    const long long u0 = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    HeadRegs pre;
+    pre.have = false; pre.row = -1;
+    if (FILTER && u0 < units) pre = load_head(p, qs, u0, units, lane, tshift);
     uint32_t nVq, nUq, nMq;
     QView qv;
     if (QMODE == 1) {
@@ -421,44 +463,23 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const int tshift = p.hdr.shift - 5;                    // tiles per chunk = 1 << tshift
     unsigned long long touched = 0;
 
     if (FILTER) {
-        // work unit = 32 candidates: a tile (full scan) or 32 strided entries of the explicit list
-        const long long units = p.rows ? (p.n_list + 31) >> 5
-                                       : ((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
-        for (long long u = warp0; u < units; u += nwarps) {
+        for (long long u = u0; u < units; u += nwarps) {
             // ---- phase A: one thread per candidate, on the candidate's head ---------------------
-            long long row = -1;
-            const unsigned char* tile = nullptr;
-            int tl = lane;
-            if (p.rows) {
-                const long long ci = u + (long long)lane * units;
-                if (ci < p.n_list) { row = p.rows[ci]; tile = tile_of(p.hdr, row, tl); }
-            } else {
-                const long long chunk = u >> tshift, lt = u & ((1ll << tshift) - 1);
-                row = (chunk << p.hdr.shift) + fn3_row_of(lt, lane, p.hdr.sb_shift);
-                tile = p.hdr.chunk[chunk] + lt * FN3_TILE_BYTES;
-                if (row >= p.n_rows) row = -1;
-            }
-            uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+            const HeadRegs hr = (u == u0) ? pre : load_head(p, qs, u, units, lane, tshift);
+            const uint4 h0 = hr.h0, h1 = hr.h1;
+            const long long row = hr.row;
             bool pass = false;
-            if (row >= 0 && row != qs.exclude && row > qs.skip_le) {
-                // header and fingerprints are requested together: ONE memory round trip per candidate
-                const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
-                const uint4* fp = reinterpret_cast<const uint4*>(tile + FN3_TILE_FP_OFF + tl * 16);
-                h0 = __ldg(hp); h1 = __ldg(hp + 1);
-                uint4 f[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) f[j] = __ldg(fp + j * 32);
+            if (hr.have) {
                 if (COUNT) touched += 96;
                 if ((h0.x | h0.y) != 0u) {                 // data pointer 0: invalid or removed candidate
                     const uint32_t nv = min(h1.y, (uint32_t)FN3_HEAD_FP);
                     int S = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t w[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
+                        const uint32_t w[4] = {hr.f[j].x, hr.f[j].y, hr.f[j].z, hr.f[j].w};
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const bool in = (uint32_t)(8 * j + i) < nv;          // beyond nv the fingerprint is padding

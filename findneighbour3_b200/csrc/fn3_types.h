@@ -35,7 +35,7 @@ struct __align__(32) RowHead {     // row-order staging format (96 B); k_scatter
     uint16_t fp[FN3_HEAD_FP];      // FN3_FP_PAD beyond min(end[3], 32)
 };
 
-#define FN3_MAX_HDR_CHUNKS 128
+#define FN3_MAX_HDR_CHUNKS 32    /* x 2^20 rows each by default: 33 M rows per GPU; keeps the kernel parameters small */
 struct HdrTable {
     const unsigned char* chunk[FN3_MAX_HDR_CHUNKS];   // chunk c holds the tiles of rows [c << shift, (c+1) << shift)
     int shift;                     // rows per chunk = 1 << shift  (>= sb_shift)

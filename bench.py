@@ -463,6 +463,27 @@ def main():
                "canonical_GBps": (bytes_canon_all / max(live, 1)) * (n_now * (n_now - 1) / 2) / t_ava / 1e9,
                "note": "fn3_all_vs_all, upper triangle, tiles of 8 queries, wall clock incl. the copy of the edges to the host"}
 
+    # ---- leg 4 (extra): device compress() of full-length sequence strings --------------------
+    ingest = None
+    if args.allvsall and world == 1:
+        from findneighbour3_b200 import synth
+        ref_codes = synth.random_reference(coll.genome_length)
+        eng.set_reference(synth.reference_string(ref_codes), np.flatnonzero(_mask()).tolist())
+        seqs = []
+        for i in np.flatnonzero(coll.invalid == 0)[:8]:
+            p_, o_, _ = coll.lists(int(i))
+            seqs.append(synth.to_string(ref_codes, p_, o_).encode("ascii"))
+        for sq in seqs[:2]:
+            eng.compress(sq)
+        t0 = time.perf_counter()
+        for rep in range(5):
+            for sq in seqs:
+                eng.compress(sq)
+        t_c = (time.perf_counter() - t0) / (5 * len(seqs))
+        ingest = {"compress_ms_per_sequence": 1e3 * t_c, "sequence_bytes": int(coll.genome_length),
+                  "GBps_host_to_lists": coll.genome_length / t_c / 1e9,
+                  "note": "fn3_compress through ctypes: 4.4 MB sequence host->device, 3 kernels, lists device->host"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -483,6 +504,8 @@ def main():
     }
     if ava is not None:
         line["all_vs_all"] = ava
+    if ingest is not None:
+        line["ingest"] = ingest
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_python_port(coll, fresh[W:], ceiling, args.cpu_seconds)

@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-allvsall", dest="allvsall", action="store_false", help="skip the extra all-vs-all leg")
+    ap.add_argument("--workload", default="onevsall", choices=["onevsall", "allvsall"],
+                    help="allvsall = BASELINE configs[2]: replicated store, block rows per rank (not the headline line)")
+    ap.add_argument("--ava-ceiling", type=int, default=12)
     return ap.parse_args()
 
 
@@ -319,6 +322,12 @@ def main():
         return float(t.item())
 
     from findneighbour3_b200.engine import Engine
+
+    if args.workload == "allvsall":
+        run_allvsall(args, rank, world, local, barrier, max_over_ranks, sum_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     t_gen = time.time()
     common = make_common()

@@ -271,6 +271,84 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def run_allvsall(args, rank, world, local, barrier, max_over_ranks, sum_over_ranks):
+    """BASELINE configs[2]: all-vs-all sparse matrix at 12 SNV.  Every rank holds the WHOLE collection (replicated
+    store) and owns the query rows r with r % world == rank; no exchange until the edge counts are
+    summed.  Each rank generates 1/world of the families; the shards are all-gathered over NCCL."""
+    import torch
+    import torch.distributed as dist
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.engine import Engine
+    max_c = 100
+    n_anc = max(world, args.samples // max_c)
+    mine = list(range(rank, n_anc, world))
+    t0 = time.time()
+    parts = [synth.make_collection(1, max_c, seed=300000 + a, excluded=_mask()) for a in mine]
+    pos = np.concatenate([c.pos for c in parts])
+    offs, total = [np.zeros(1, np.int64)], 0
+    for c in parts:
+        offs.append(total + c.off[1:])
+        total += int(c.off[-1])
+    off = np.concatenate(offs)
+    inv = np.concatenate([c.invalid for c in parts])
+    eng = Engine(synth.TB_LENGTH, local)
+    if world == 1:
+        eng.append_bulk(pos, off, inv)
+    else:
+        sizes = torch.tensor([pos.size, inv.size], dtype=torch.int64, device="cuda")
+        allsz = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(allsz, sizes)
+        maxp, maxn = int(max(int(x[0]) for x in allsz)), int(max(int(x[1]) for x in allsz))
+        tp = torch.zeros(maxp, dtype=torch.int32, device="cuda"); tp[:pos.size] = torch.from_numpy(pos).cuda()
+        to = torch.zeros(6 * maxn + 1, dtype=torch.int64, device="cuda"); to[:off.size] = torch.from_numpy(off).cuda()
+        ti = torch.zeros(maxn, dtype=torch.uint8, device="cuda"); ti[:inv.size] = torch.from_numpy(inv).cuda()
+        gp = [torch.zeros_like(tp) for _ in range(world)]
+        go = [torch.zeros_like(to) for _ in range(world)]
+        gi = [torch.zeros_like(ti) for _ in range(world)]
+        dist.all_gather(gp, tp); dist.all_gather(go, to); dist.all_gather(gi, ti)
+        for r in range(world):
+            npos, nn = int(allsz[r][0]), int(allsz[r][1])
+            eng.append_bulk(gp[r][:npos].cpu().numpy(), go[r][:6 * nn + 1].cpu().numpy(), gi[r][:nn].cpu().numpy())
+        del gp, go, gi, tp, to, ti
+        torch.cuda.empty_cache()
+    st = eng.stats()
+    n = st["n_rows"]
+    t_setup = time.time() - t0
+    # warm-up on a slice of the rows, then the timed full pass over this rank's block rows
+    eng.all_vs_all(args.ava_ceiling, upper_only=True, row_begin=0, row_end=min(n, 2048), stride=world, phase=rank)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = eng.launch_count()
+    t1 = time.perf_counter()
+    edges = eng.all_vs_all(args.ava_ceiling, upper_only=True, stride=world, phase=rank)
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t1
+    barrier()
+    clocks = sampler.stop()
+    t = max_over_ranks(t)
+    n_edges = sum_over_ranks(float(len(edges)))
+    launches = sum_over_ranks(float(eng.launch_count() - launches0))
+    pairs = n * (n - 1) / 2
+    b_pair = (4.0 * st["positions"] + 32.0 * st["n_live"]) / max(st["n_live"], 1)      # mean canonical bytes per comparison
+    peak, peak_src = peaks()
+    line = {"metric": "pairwise SNV comparisons/sec (all-vs-all sparse matrix at %d SNV, block rows over %d GPU)" % (args.ava_ceiling, world),
+            "value": pairs / t, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": 1e3 * t,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "configs[2]: %d synthetic TB sequences all-vs-all at %d SNV, store replicated, query rows r %% %d == rank"
+                                   % (n, args.ava_ceiling, world), "samples": int(n), "genome_length": int(synth.TB_LENGTH),
+                       "l2": "head tiles %.0f MB + rows %.0f MB per GPU" % (n * 96 / 1e6, 4 * st["store_words"] / 1e6)},
+            "edges": int(n_edges), "pairs": int(pairs), "seconds": t, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_query", "achieved": pairs * b_pair / t / 1e9, "peak": peak * world,
+                         "peak_source": peak_src + " x n_gpus", "unit": "GB/s", "frac": pairs * b_pair / t / 1e9 / (peak * world),
+                         "traffic": None,
+                         "note": "canonical B_pair bytes (SURVEY 8(d)); the FILTER variant decides almost every pair from its 96-byte head"},
+            "setup_s": t_setup, "host_cpus": os.cpu_count()}
+    if rank == 0:
+        emit(line)
+    eng.close()
+
+
 # ----------------------------------------------------------------------------------------------------
 def emit(line):
     """the ONE JSON line goes to the real stdout; everything else that writes to fd 1 (NCCL's version banner,

@@ -260,7 +260,7 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
     e->sb_shift = std::min(13, e->hdr_shift);                   // 8192-row superblocks: neighbours in insertion
                                                                 // order sit 256 tiles apart
     e->debug_stop = (int)env_ll("FN3_DEBUG_STOP", 0);
-    e->n_slots = (int)env_ll("FN3_SLOTS", 8);
+    e->n_slots = (int)env_ll("FN3_SLOTS", 64);               // queries per all-vs-all tile (one k_query launch)
     if (e->n_slots < 1) e->n_slots = 1;
     if (e->n_slots > FN3_MAX_SLOTS) e->n_slots = FN3_MAX_SLOTS;
 
@@ -722,7 +722,7 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     const long long cand = job.d_rows ? job.n_list : slots_scanned;
     const long long units = filter ? (cand + 31) / 32 : cand;                   // warp-sized work units
     long long ctas = std::max<long long>(1, (units + warps_per_cta - 1) / warps_per_cta);
-    long long per_sm = filter ? 1 : FN3_Q_MINB;                     // __launch_bounds__(512, FILTER ? 1 : FN3_Q_MINB)
+    long long per_sm = FN3_Q_MINB;                                  // __launch_bounds__(512, FN3_Q_MINB)
     if (in_smem && per_sm * (long long)(smem + (size_t)e->q_static_smem + 1024) > (long long)228 * 1024) per_sm = 1;
     // every CTA builds its query first: with several slots per launch give each slot its share of the resident
     // CTAs and let every CTA scan more candidates, rather than several waves that each rebuild the query

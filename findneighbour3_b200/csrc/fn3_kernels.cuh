@@ -414,7 +414,7 @@ __device__ __forceinline__ HeadRegs load_head(const CompareParams& p, const Quer
 #define FN3_Q_MINB 2
 #endif
 template <bool COUNT, int QMODE, bool FILTER>
-__global__ void __launch_bounds__(FN3_Q_THREADS, FILTER ? 1 : FN3_Q_MINB) k_query(const CompareParams p) {
+__global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const CompareParams p) {
     extern __shared__ __align__(128) uint4 qsm[];
     __shared__ uint32_t ws[99];
     if (p.debug_stop == 3) return;
@@ -431,14 +431,11 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FILTER ? 1 : FN3_Q_MINB) k_quer
     const int nw = p.nw, ncw = p.ncw;
     const int tshift = p.hdr.shift - 5;                    // tiles per chunk = 1 << tshift
     // FILTER: work unit = 32 candidates.  Consecutive units (tiles hold consecutively inserted rows, i.e. relatives)
-    // go to different CTAs, so that the few surviving candidates of a family are streamed on different SMs.  The
-    // first unit's heads are requested NOW: their memory round trip overlaps the query build below.
+    // go to different CTAs, so that the few surviving candidates of a family are streamed on different SMs.
+    // (Requesting the first unit's heads before the query build was measured: no gain, +58 registers.)
     const long long units = !FILTER ? 0 : p.rows ? (p.n_list + 31) >> 5
                             : ((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
     const long long u0 = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-    HeadRegs pre;
-    pre.have = false; pre.row = -1;
-    if (FILTER && u0 < units) pre = load_head(p, qs, u0, units, lane, tshift);
     uint32_t nVq, nUq, nMq;
     QView qv;
     if (QMODE == 1) {
@@ -466,9 +463,12 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FILTER ? 1 : FN3_Q_MINB) k_quer
     unsigned long long touched = 0;
 
     if (FILTER) {
-        for (long long u = u0; u < units; u += nwarps) {
+        // upper triangle: superblocks that hold only rows <= skip_le cannot contain a candidate
+        const long long ufirst = (p.rows || qs.skip_le < 0) ? 0
+                                 : ((qs.skip_le + 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
+        for (long long u = ufirst + u0; u < units; u += nwarps) {
             // ---- phase A: one thread per candidate, on the candidate's head ---------------------
-            const HeadRegs hr = (u == u0) ? pre : load_head(p, qs, u, units, lane, tshift);
+            const HeadRegs hr = load_head(p, qs, u, units, lane, tshift);
             const uint4 h0 = hr.h0, h1 = hr.h1;
             const long long row = hr.row;
             bool pass = false;
@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FILTER ? 1 : FN3_Q_MINB) k_quer
                     int S = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        if (S > k) break;                                          // already proven: not a neighbour
                         const uint32_t w[4] = {hr.f[j].x, hr.f[j].y, hr.f[j].z, hr.f[j].w};
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {

@@ -411,7 +411,9 @@ def main():
     common = make_common()
     coll = make_shard(args.samples, rank, common)
     eng = Engine(coll.genome_length, local)
-    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    t_bulk = time.perf_counter()
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)       # server start-up reload path: validate, pack, copy, place heads
+    t_bulk = time.perf_counter() - t_bulk
     K, W = args.steps, args.warmup
     queries = make_queries(common, 3 * (K + W))      # the same new samples on every rank
     t_gen = time.time() - t_gen
@@ -588,6 +590,8 @@ def main():
         "neighbours_per_query": float(prof["n_hits"].mean()),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum_over_ranks(float(launches))),
         "roofline": roofline, "host_cpus": os.cpu_count(), "setup_s": t_gen,
+        "bulk_append": {"rows": int(coll.n), "seconds": t_bulk, "rows_per_s": coll.n / t_bulk,
+                        "positions_per_s": float(coll.pos.size) / t_bulk},
     }
     if ava is not None:
         line["all_vs_all"] = ava

@@ -50,12 +50,11 @@ struct fn3_engine {
     uint32_t max_run = 1;
 
     std::mutex store_mu;        // guards store metadata + append path
-    std::mutex query_mu;        // guards query state (maps, slots, out buffers, q_stream)
+    std::mutex query_mu;        // guards query state (slots, survivor buffers, q_stream); taken before store_mu
     std::string err;
     std::mutex err_mu;
 
-    cudaStream_t copy_stream = nullptr, q_stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr, q_stream = nullptr;   // appends / queries
 
     // store
     size_t chunk_words = 0;                 // words per data chunk
@@ -79,17 +78,17 @@ struct fn3_engine {
     RowHead* d_heads = nullptr; size_t d_heads_n = 0;      // device staging for k_scatter_heads
 
     // query state
-    int n_slots = 8;
+    int n_slots = 64;                      // queries per all-vs-all tile
     QueryState qstate;                     // global-memory query structures (n_slots), fallback path only
-    int nw = 0, ncw = 0, n_blk = 0, fshift = 5;   // bmpref words, coarse words, 32-position blocks, fingerprint shift
+    int nw = 0, ncw = 0, n_blk = 0, fshift = 5;   // bitmap words, coarse words, 32-position blocks, fingerprint shift
     int max_smem = 0;                      // opt-in dynamic shared memory per CTA
     int stage_limit = 0;                   // = max_smem, or 0 to force the global-memory query variants
     int q_static_smem = 0;                 // static shared memory of k_query
     int debug_stop = 0;                    // env FN3_DEBUG_STOP (profiling aid, wrong results when set)
-    uint32_t slot_blocks[FN3_MAX_SLOTS];   // touched-block count of the query in each slot (sizes the staging)
+    uint32_t slot_blocks[1];               // touched-block bound of the single query of a one-vs-all call (sizes smem)
     QuerySlot* d_slots = nullptr; QuerySlot* h_slots = nullptr;   // [FN3_SLOT_RING tiles][FN3_MAX_SLOTS]; h_slots pinned
-    // survivor buffer: one allocation = [32-byte counter block | records], mirrored in pinned host memory so
-    // that the counter and the first records come back in ONE device-to-host copy
+    // survivor buffer: one allocation = [32-byte counter block | records]; the pinned mirror is used by the
+    // copy-based paths (all-vs-all, FN3_ZERO_COPY=0)
     unsigned char* d_outbuf = nullptr; unsigned char* h_outbuf = nullptr;
     EdgeRec* d_out = nullptr; long long out_cap = 0;
     unsigned long long* d_count = nullptr;   // [0] hit counter, [1] touched bytes
@@ -266,8 +265,6 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
 
     if ((s = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", s);
     if ((s = cudaStreamCreateWithFlags(&e->q_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", s);
-    for (int i = 0; i < 4; ++i)
-        if ((s = cudaEventCreate(&e->ev[i])) != cudaSuccess) return fail("cudaEventCreate", s);
 
     // query structure sizes; the last 32-position block is the end sentinel for rank(L)
     {
@@ -343,7 +340,6 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->h_rows) cudaFreeHost(e->h_rows);
     if (e->stage) cudaFreeHost(e->stage);
     if (e->stage_hdr) cudaFreeHost(e->stage_hdr);
-    for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->q_stream) cudaStreamDestroy(e->q_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;

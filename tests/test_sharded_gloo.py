@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, exchange):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -33,7 +33,8 @@ def _worker(rank, world, port, q):
         base = 24
         mine = np.arange(rank, base, world)
         shard = coll.subset(mine)
-        store = ShardedStore(OracleEngine(L), max_hits=2)          # tiny block: forces the overflow round
+        # nccl-style transport: a tiny block forces the overflow round; shm: slots must hold the longest list
+        store = ShardedStore(OracleEngine(L), max_hits=2 if exchange == "nccl" else 256, exchange=exchange)
         store.load_shard(shard.pos, shard.off, shard.invalid)
         assert store.n_global == base
         # (2) streaming inserts, sample known on rank 0 only
@@ -55,18 +56,21 @@ def _worker(rank, world, port, q):
             want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, g, 20)
             ok &= hits == want
         q.put((rank, bool(ok), len(results), sum(len(h) for h in results.values())))
+        store.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_store_world2_gloo():
+@pytest.mark.parametrize("exchange", ["nccl", "shm"])
+def test_sharded_store_world2_gloo(exchange):
+    """exchange="nccl" = torch.distributed collectives (gloo here); "shm" = the one-box shared-memory transport."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if exchange == "shm" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, exchange)) for r in range(2)]
     for p in procs:
         p.start()
-    out = [q.get(timeout=240) for _ in procs]
+    out = [q.get(timeout=90) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -415,7 +415,7 @@ def main():
     eng.append_bulk(coll.pos, coll.off, coll.invalid)       # server start-up reload path: validate, pack, copy, place heads
     t_bulk = time.perf_counter() - t_bulk
     K, W = args.steps, args.warmup
-    queries = make_queries(common, 3 * (K + W))      # the same new samples on every rank
+    queries = make_queries(common, 4 * (K + W))      # the same new samples on every rank
     t_gen = time.time() - t_gen
 
     # ---- leg 1: device-resident value ------------------------------------------------------------

@@ -70,6 +70,11 @@ class ShardedStore:
         dist.broadcast_object_list(name, src=0, group=self.group)
         if self.rank != 0:
             self._shm = shared_memory.SharedMemory(name=name[0])
+            try:                                  # the creator (rank 0) owns the segment: keep Python's resource
+                from multiprocessing import resource_tracker      # tracker of the other ranks from unlinking it
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
         w = np.frombuffer(self._shm.buf, dtype=np.int64)
         self._s64 = w[: self._s_words]
         self._s32 = self._s64[16:].view(np.int32)

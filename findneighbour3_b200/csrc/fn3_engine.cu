@@ -406,6 +406,58 @@ static void pack_row(const fn3_engine* e, const int32_t* pos, const long long of
     }
 }
 
+// single pass for the insert hot path: validates the six lists AND writes the row words (dst must hold one word per
+// position, the worst case).  Returns the number of words, or -1 with the error set; *nblk = touched-block bound.
+static long long pack_checked(fn3_engine* e, const int32_t* pos, const long long off[7], uint32_t* dst, uint32_t ends[6],
+                              uint32_t* nblk) {
+    for (int b = 0; b < 6; ++b)
+        if (off[b + 1] < off[b]) { set_err(e, FN3_EARG, "list offsets must be non-decreasing"); return -1; }
+    const long long L = e->L;
+    long long blocks = 0;
+    uint32_t w = 0;
+    for (int b = 0; b < 4; ++b) {
+        const int32_t* p = pos + off[b];
+        const long long n = off[b + 1] - off[b];
+        int32_t prev = -1;
+        for (long long i = 0; i < n; ++i) {
+            const int32_t v = p[i];
+            if (v <= prev || (long long)v >= L) {
+                set_err(e, FN3_EARG, v < 0 || (long long)v >= L ? "position out of range" : "positions must be strictly increasing within a list");
+                return -1;
+            }
+            blocks += (i == 0) | ((v >> 5) != (prev >> 5));
+            dst[w++] = (uint32_t)v;
+            prev = v;
+        }
+        ends[b] = w;
+    }
+    for (int b = 4; b < 6; ++b) {
+        const int32_t* p = pos + off[b];
+        const long long n = off[b + 1] - off[b];
+        long long i = 0;
+        int32_t prev_last = -1;
+        while (i < n) {
+            const int32_t s0 = p[i];
+            if (s0 <= prev_last || (long long)s0 >= L) {
+                set_err(e, FN3_EARG, s0 < 0 || (long long)s0 >= L ? "position out of range" : "positions must be strictly increasing within a list");
+                return -1;
+            }
+            long long j = i + 1;
+            while (j < n && p[j] == p[j - 1] + 1 && (j - i) < (long long)e->max_run) ++j;
+            const int32_t last = p[j - 1];
+            if ((long long)last >= L) { set_err(e, FN3_EARG, "position out of range"); return -1; }
+            blocks += (last >> 5) - (s0 >> 5) + 1 - ((prev_last >= 0 && (prev_last >> 5) == (s0 >> 5)) ? 1 : 0);
+            const uint32_t len = (uint32_t)(j - i);
+            dst[w++] = (e->pos_bits >= 32) ? (uint32_t)s0 : (((len - 1u) << e->pos_bits) | (uint32_t)s0);
+            prev_last = last;
+            i = j;
+        }
+        ends[b] = w;
+    }
+    *nblk = (uint32_t)std::min<long long>(blocks, 0x7fffffff);
+    return (long long)w;
+}
+
 // header + 16-bit fingerprints (position >> fshift) of the row's first V words (fn3_types.h)
 static void fill_head(const fn3_engine* e, RowHead& hd, const RowHdr& h, const uint32_t* words) {
     hd.hdr = h;
@@ -907,11 +959,17 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     uint32_t nblk = 0;
     long long o[7] = {0, 0, 0, 0, 0, 0, 0};
     if (!invalid) for (int b = 0; b < 7; ++b) o[b] = off[b];
-    const long long w = row_words_needed(e, pos, o, invalid, &nblk);
-    if (w < 0) return FN3_EARG;
-    size_t need = ((size_t)w + 3) & ~(size_t)3; if (need == 0) need = 4;
-    int rc = ensure_stage(e, need, 1);
+    // one pass: validate + pack into pinned staging (one word per position is the worst case)
+    const size_t npos_in = invalid ? 0 : (size_t)(o[6] - o[0]);
+    int rc = ensure_stage(e, ((npos_in + 3) & ~(size_t)3) + 4, 1);
     if (rc) return rc;
+    long long w = 0;
+    if (!invalid) {
+        w = pack_checked(e, pos, o, e->stage, h.end, &nblk);
+        if (w < 0) return FN3_EARG;
+    }
+    size_t need = ((size_t)w + 3) & ~(size_t)3; if (need == 0) need = 4;
+    for (size_t z = (size_t)w; z < need; ++z) e->stage[z] = 0;
     uint32_t* dbase = nullptr;
     if ((rc = arena_alloc(e, need, &dbase))) return rc;
     const long long row = e->n_rows;
@@ -919,12 +977,7 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     if ((rc = ensure_hdr_chunk(e, row))) return rc;
     if (e->hdr_chunks.size() != chunks_before)       // a new chunk is zeroed on copy_stream: order q_stream behind it
         CU(e, cudaStreamSynchronize(e->copy_stream));
-    if (invalid) memset(e->stage, 0, need * 4);
-    else {
-        pack_row(e, pos, o, e->stage, h.end);
-        for (size_t z = (size_t)w; z < need; ++z) e->stage[z] = 0;
-        h.data = (unsigned long long)(uintptr_t)dbase;
-    }
+    if (!invalid) h.data = (unsigned long long)(uintptr_t)dbase;
     RowHead head;
     fill_head(e, head, h, e->stage);
     e->t_pack_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();

@@ -80,7 +80,8 @@ struct fn3_engine {
     // query state
     int n_slots = 64;                      // queries per all-vs-all tile
     QueryState qstate;                     // global-memory query structures (n_slots), fallback path only
-    int nw = 0, ncw = 0, n_blk = 0, fshift = 5;   // bitmap words, coarse words, 32-position blocks, fingerprint shift
+    int nw = 0, ncw = 0, n_blk = 0, fshift = 5;   // bitmap words, coarse map words, 32-position blocks, fingerprint shift
+    uint16_t fp_pad = 0;                   // coarse id carried by padded fingerprints (its map byte is always 1)
     int max_smem = 0;                      // opt-in dynamic shared memory per CTA
     int stage_limit = 0;                   // = max_smem, or 0 to force the global-memory query variants
     int q_static_smem = 0;                 // static shared memory of k_query
@@ -271,9 +272,10 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         e->n_blk = (int)((genome_length + 31) / 32 + 1);
         e->nw = ((e->n_blk + 31) / 32 + 3) & ~3;                 // entries start 32-byte aligned behind bmpref
         e->fshift = 5;
-        while (((genome_length - 1) >> e->fshift) > 65534) ++e->fshift;      // coarse block ids fit 16 bits
+        while (((genome_length - 1) >> e->fshift) + 2 > 16383) ++e->fshift;  // <= 16 K coarse blocks: a 16 KB byte map
         const long long n_coarse = ((genome_length - 1) >> e->fshift) + 2;   // + the block rank(L) may fall in
-        e->ncw = (int)(((n_coarse + 31) / 32 + 7) & ~7ll);
+        e->ncw = (int)((((n_coarse + 1) + 3) / 4 + 7) & ~7ll);               // bytes / 4, + 1 for the pad id
+        e->fp_pad = (uint16_t)(e->ncw * 4 - 1);
         QueryState& q = e->qstate;
         memset(&q, 0, sizeof q);
         q.ent_stride = (long long)e->n_blk + 1;
@@ -463,7 +465,7 @@ static void fill_head(const fn3_engine* e, RowHead& hd, const RowHdr& h, const u
     hd.hdr = h;
     const uint32_t nv = h.data ? std::min<uint32_t>(h.end[3], FN3_HEAD_FP) : 0u;
     for (uint32_t i = 0; i < nv; ++i) hd.fp[i] = (uint16_t)(words[i] >> e->fshift);
-    for (uint32_t i = nv; i < FN3_HEAD_FP; ++i) hd.fp[i] = (uint16_t)FN3_FP_PAD;
+    for (uint32_t i = nv; i < FN3_HEAD_FP; ++i) hd.fp[i] = e->fp_pad;
 }
 
 // device address of a row's header inside its tile

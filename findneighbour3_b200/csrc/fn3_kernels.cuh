@@ -128,6 +128,8 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
     if (GLOBAL) __threadfence_block();
     __syncthreads();
     const int cs = fshift - 5;                                   // coarse block = 1 << cs fine blocks
+    uint8_t* cmap = reinterpret_cast<uint8_t*>(coarse);          // one BYTE per coarse block: 1 = touched
+    if (tid == 0) cmap[ncw * 4 - 1] = 1;                         // the id padded fingerprints carry: never counts
     for (uint32_t i = tid, r = 0; i < e5; i += nt, ++r) {       // 1. touched blocks (fine and coarse)
         const uint32_t w = r < FN3_BUILD_KEEP ? keep[r < FN3_BUILD_KEEP ? r : 0] : __ldg(d + i);
         uint32_t b0, b1;
@@ -137,7 +139,7 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
             b0 = s >> 5; b1 = (s + len - 1u) >> 5;
         }
         for (uint32_t blk = b0; blk <= b1; ++blk) atomicOr(&bm[blk >> 5], 1u << (blk & 31u));
-        for (uint32_t cb = b0 >> cs; cb <= (b1 >> cs); ++cb) atomicOr(&coarse[cb >> 5], 1u << (cb & 31u));
+        for (uint32_t cb = b0 >> cs; cb <= (b1 >> cs); ++cb) cmap[cb] = 1;      // plain byte stores: every writer writes 1
     }
     if (GLOBAL) __threadfence_block();
     __syncthreads();
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS) k_build_query(const QuerySlot* 
 struct QView {                  // where the query structure lives (shared or global)
     const uint32_t* bm;         // bit per 32-position block: touched by the query
     const uint32_t* pref;       // touched blocks below block 32w
-    const uint32_t* coarse;
+    const uint8_t* cmap;        // one byte per coarse (fingerprint) block: 1 = touched by the query
     const uint4* ent;           // two uint4 per entry
 };
 
@@ -445,13 +447,13 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
         uint32_t tot[3];
         build_query<false>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
         nVq = tot[0]; nUq = tot[1]; nMq = tot[2];
-        qv.bm = sm_bm; qv.pref = sm_bm + nw; qv.coarse = sm_co; qv.ent = reinterpret_cast<const uint4*>(sm_en);
+        qv.bm = sm_bm; qv.pref = sm_bm + nw; qv.cmap = reinterpret_cast<const uint8_t*>(sm_co); qv.ent = reinterpret_cast<const uint4*>(sm_en);
     } else {
         const uint4 info = p.qs.info[slot];
         nVq = info.y; nUq = info.z; nMq = info.w;
         qv.bm = p.qs.bm + (long long)slot * 2 * nw;
         qv.pref = qv.bm + nw;
-        qv.coarse = p.qs.coarse + (long long)slot * ncw;
+        qv.cmap = reinterpret_cast<const uint8_t*>(p.qs.coarse + (long long)slot * ncw);
         qv.ent = reinterpret_cast<const uint4*>(p.qs.ent + (long long)slot * p.qs.ent_stride);
     }
     if (p.debug_stop == 1) return;
@@ -475,19 +477,16 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
             if (hr.have) {
                 if (COUNT) touched += 96;
                 if ((h0.x | h0.y) != 0u) {                 // data pointer 0: invalid or removed candidate
-                    const uint32_t nv = min(h1.y, (uint32_t)FN3_HEAD_FP);
+                    // a fingerprint whose coarse block the query does not touch is a certain mismatch; padded
+                    // fingerprints (rows with fewer than 32 V words) carry an id whose byte is always 1
                     int S = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (S > k) break;                                          // already proven: not a neighbour
                         const uint32_t w[4] = {hr.f[j].x, hr.f[j].y, hr.f[j].z, hr.f[j].w};
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const bool in = (uint32_t)(8 * j + i) < nv;          // beyond nv the fingerprint is padding
-                            const uint32_t cb = in ? (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu : 0u;
-                            const uint32_t untouched = ((qv.coarse[cb >> 5] >> (cb & 31u)) & 1u) ^ 1u;
-                            S += in ? (int)untouched : 0;
-                        }
+                        for (int i = 0; i < 4; ++i)
+                            S += 2 - (int)qv.cmap[w[i] & 0xffffu] - (int)qv.cmap[w[i] >> 16];
                     }
                     pass = S <= k;
                 }

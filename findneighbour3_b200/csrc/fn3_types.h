@@ -20,19 +20,18 @@ struct __align__(32) RowHdr {      // 32 B = one sector
 
 // ---- row heads: what the early-exit filter reads -----------------------------------------------
 // Per row: the header and a 16-bit FINGERPRINT of each of its first 32 V positions, fp = position >> fshift
-// (fshift chosen so that every coarse block id fits 16 bits; 128-position blocks for a 4.4 Mb genome).
+// (fshift chosen so that the genome has at most ~16 K coarse blocks: 512-position blocks for a 4.4 Mb genome).
 // Heads live in TILES of 32 rows laid out for coalesced warp access (lane l reads hdr[l] and fp[j][l]):
 //     tile = [ RowHdr hdr[32] | uint4 fp[4][32] ]        (1024 + 2048 = 3072 bytes)
 // and consecutive rows are spread over different tiles: inside a superblock of 32*G0 rows, row r sits in
 // tile r % G0, lane r / G0 — so a family of consecutively inserted relatives lands in different warps.
 #define FN3_HEAD_FP 32
-#define FN3_FP_PAD 0xFFFFu
 #define FN3_TILE_BYTES 3072
 #define FN3_TILE_FP_OFF 1024
 
 struct __align__(32) RowHead {     // row-order staging format (96 B); k_scatter_heads / k_query place it in its tile
     RowHdr hdr;
-    uint16_t fp[FN3_HEAD_FP];      // FN3_FP_PAD beyond min(end[3], 32)
+    uint16_t fp[FN3_HEAD_FP];      // beyond min(end[3], 32): the engine's pad id (a coarse id no position maps to)
 };
 
 #define FN3_MAX_HDR_CHUNKS 32    /* x 2^20 rows each by default: 33 M rows per GPU; keeps the kernel parameters small */
@@ -57,7 +56,8 @@ FN3_HD long long fn3_row_of(long long tile, int lane, int sb_shift) {
 // ---- the query, compact --------------------------------------------------------
 // bm[w]     : bit per 32-position block 32w..32w+31 "the query is non-reference/N/M somewhere in it" (touched)
 // pref[w]   : number of touched blocks below block 32w
-// coarse    : bit per coarse block (position >> fshift) touched — what the fingerprints are tested against
+// coarse    : one BYTE per coarse block (position >> fshift): 1 = touched — what the fingerprints are tested against
+//             (one LDS.U8 per fingerprint; the last byte is always 1 and is the id padded fingerprints carry)
 // entry[i]  : the i-th touched block; entry[nE] is a sentinel whose counts are the totals |V_q|,|U_q|,|M_q|
 struct __align__(32) QEntry {
     uint32_t mDef, mU, mB0, mB1;   // per position: ACGT-nonref / N-or-M / base code bit 0 / bit 1 (A0 C1 G2 T3)
@@ -66,7 +66,7 @@ struct __align__(32) QEntry {
 
 struct QueryState {                // global-memory copies (only queries too large for shared memory use them)
     uint32_t* bm;                  // slot s at bm + s*2*nw : [touched-block bitmap nw | prefix counts nw]
-    uint32_t* coarse;              // slot s at coarse + s*ncw
+    uint32_t* coarse;              // slot s at coarse + s*ncw (a byte map of 4*ncw entries)
     QEntry* ent;                   // slot s at ent + s*ent_stride
     uint4* info;                   // slot s: {nE, |V_q|, |U_q|, |M_q|}
     long long ent_stride;
@@ -114,6 +114,6 @@ struct CompareParams {
     int use_filter;
     int fshift;
     int nw;                        // bmpref words (multiple of 4)
-    int ncw;                       // coarse bitmap words (multiple of 8)
+    int ncw;                       // coarse byte map size in 32-bit words (multiple of 8)
     int debug_stop;                // profiling aid: 1 stop after build, 2 after phase A, 3 at entry, 4 after slot load
 };

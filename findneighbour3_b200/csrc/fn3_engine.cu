@@ -78,8 +78,9 @@ struct fn3_engine {
     RowHead* d_heads = nullptr; size_t d_heads_n = 0;      // device staging for k_scatter_heads
 
     // query state
-    int n_slots = 64;                      // queries per all-vs-all tile
-    QueryState qstate;                     // global-memory query structures (n_slots), fallback path only
+    int n_slots = 128;                     // queries per all-vs-all tile (one k_query launch)
+    QueryState qstate;                     // global-memory query structures, fallback path only (ensure_qstate)
+    int qstate_slots = 0;
     int nw = 0, ncw = 0, n_blk = 0, fshift = 5;   // bitmap words, coarse map words, 32-position blocks, fingerprint shift
     uint16_t fp_pad = 0;                   // coarse id carried by padded fingerprints (its map byte is always 1)
     int max_smem = 0;                      // opt-in dynamic shared memory per CTA
@@ -260,7 +261,7 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
     e->sb_shift = std::min(13, e->hdr_shift);                   // 8192-row superblocks: neighbours in insertion
                                                                 // order sit 256 tiles apart
     e->debug_stop = (int)env_ll("FN3_DEBUG_STOP", 0);
-    e->n_slots = (int)env_ll("FN3_SLOTS", 64);               // queries per all-vs-all tile (one k_query launch)
+    e->n_slots = (int)env_ll("FN3_SLOTS", 128);               // queries per all-vs-all tile (one k_query launch)
     if (e->n_slots < 1) e->n_slots = 1;
     if (e->n_slots > FN3_MAX_SLOTS) e->n_slots = FN3_MAX_SLOTS;
 
@@ -279,10 +280,8 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         QueryState& q = e->qstate;
         memset(&q, 0, sizeof q);
         q.ent_stride = (long long)e->n_blk + 1;
-        if ((s = cudaMalloc(&q.bm, (size_t)e->nw * 2 * sizeof(uint32_t) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(bm)", s);
-        if ((s = cudaMalloc(&q.coarse, (size_t)e->ncw * sizeof(uint32_t) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(coarse)", s);
-        if ((s = cudaMalloc(&q.ent, (size_t)q.ent_stride * sizeof(QEntry) * e->n_slots)) != cudaSuccess) return fail("cudaMalloc(entries)", s);
-        if ((s = cudaMalloc(&q.info, sizeof(uint4) * FN3_MAX_SLOTS)) != cudaSuccess) return fail("cudaMalloc(info)", s);
+        // (the global-memory copies behind `q` are only needed by queries too large for shared memory:
+        //  ensure_qstate allocates them on first use)
         e->max_smem = (int)prop.sharedMemPerBlockOptin;
         e->stage_limit = env_ll("FN3_FORCE_GLOBAL_QUERY", 0) ? 0 : e->max_smem;   // tests: exercise the global-memory variants
         // opt in to the full shared memory for the variants that build the query in shared memory
@@ -700,6 +699,21 @@ static void fill_hdr_table(fn3_engine* e, HdrTable& t) {   // store_mu held
     t.sb_shift = e->sb_shift;
 }
 
+// global-memory query structures for `ns` slots (fallback path), allocated on first use
+static int ensure_qstate(fn3_engine* e, int ns) {
+    if (ns <= e->qstate_slots) return FN3_OK;
+    QueryState& q = e->qstate;
+    CU(e, cudaStreamSynchronize(e->q_stream));
+    cudaFree(q.bm); cudaFree(q.coarse); cudaFree(q.ent); cudaFree(q.info);
+    q.bm = nullptr; q.coarse = nullptr; q.ent = nullptr; q.info = nullptr; e->qstate_slots = 0;
+    CU(e, cudaMalloc(&q.bm, (size_t)e->nw * 2 * sizeof(uint32_t) * ns));
+    CU(e, cudaMalloc(&q.coarse, (size_t)e->ncw * sizeof(uint32_t) * ns));
+    CU(e, cudaMalloc(&q.ent, (size_t)q.ent_stride * sizeof(QEntry) * ns));
+    CU(e, cudaMalloc(&q.info, sizeof(uint4) * ns));
+    e->qstate_slots = ns;
+    return FN3_OK;
+}
+
 // the FILTER variant needs the 32 fingerprints of a head to be able to exceed the ceiling with some slack
 static bool use_filter_for(int ceiling) { return ceiling <= FN3_HEAD_FP - 8; }
 
@@ -742,6 +756,8 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     const size_t smem = (size_t)e->nw * sizeof(uint2) + (size_t)e->ncw * 4 + ((size_t)blocks + 1) * sizeof(QEntry);
     const bool in_smem = smem + (size_t)e->q_static_smem + 256 <= (size_t)e->stage_limit;
     if (!in_smem) {
+        int rcq = ensure_qstate(e, ns);
+        if (rcq) return rcq;
         if (ns == 1) {                    // the build kernel reads its slots from device memory
             CU(e, cudaMemcpyAsync(d_sl, h_sl, sizeof(QuerySlot), cudaMemcpyHostToDevice, st));
             e->h2d_bytes += (long long)sizeof(QuerySlot);

@@ -15,5 +15,5 @@ t0 = time.perf_counter(); e = eng.all_vs_all(12); t = time.perf_counter() - t0
 n = coll.n
 print("FN3_SLOTS", os.environ.get("FN3_SLOTS"), "all-vs-all %.3f s  %.2e pairs/s  edges %d" % (t, n*(n-1)/2/t, len(e)))
 '''
-for slots in ("32", "64"):
+for slots in ("64", "128"):
     subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FN3_SLOTS=slots))

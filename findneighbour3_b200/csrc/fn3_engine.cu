@@ -459,6 +459,23 @@ static long long pack_checked(fn3_engine* e, const int32_t* pos, const long long
     return (long long)w;
 }
 
+// words a row occupies in the arena: its list words padded to 4, then ONE 16-bit fingerprint per V word (the STREAM
+// variant's certain-mismatch pre-pass reads these 2 bytes per word instead of the 4-byte positions), padded to 16 bytes
+static size_t row_alloc_words(size_t words, size_t nv) {
+    const size_t a = ((words + 3) & ~(size_t)3) + ((((nv + 1) / 2) + 3) & ~(size_t)3);
+    return a ? a : 4;
+}
+
+// dst[0..words) holds the packed lists: write the zero padding and the fingerprint array behind them
+static void finish_row(const fn3_engine* e, uint32_t* dst, size_t words, size_t nv) {
+    const size_t w4 = (words + 3) & ~(size_t)3, total = row_alloc_words(words, nv);
+    for (size_t z = words; z < w4; ++z) dst[z] = 0;
+    uint16_t* fp = reinterpret_cast<uint16_t*>(dst + w4);
+    const size_t nfp = (total - w4) * 2;
+    for (size_t i = 0; i < nv; ++i) fp[i] = (uint16_t)(dst[i] >> e->fshift);
+    for (size_t i = nv; i < nfp; ++i) fp[i] = e->fp_pad;
+}
+
 // header + 16-bit fingerprints (position >> fshift) of the row's first V words (fn3_types.h)
 static void fill_head(const fn3_engine* e, RowHead& hd, const RowHdr& h, const uint32_t* words) {
     hd.hdr = h;
@@ -534,8 +551,8 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
     while (i < n) {
         size_t batch_words = 0; long long j = i;
         while (j < n) {
-            size_t need = ((size_t)words[(size_t)j] + 3) & ~(size_t)3;
-            if (need == 0) need = 4;
+            const bool invj = invalid && invalid[j];
+            const size_t need = row_alloc_words((size_t)words[(size_t)j], invj ? 0 : (size_t)(off6[6 * j + 4] - off6[6 * j]));
             if (j > i && batch_words + need > batch_limit) break;
             batch_words += need; ++j;
         }
@@ -550,14 +567,14 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
             for (int b = 0; b < 7; ++b) o[b] = off6[6 * r + b];
             RowHdr h;
             const bool inv = invalid && invalid[r];
-            size_t need = ((size_t)words[(size_t)r] + 3) & ~(size_t)3;
-            if (need == 0) need = 4;
+            const size_t nv = inv ? 0 : (size_t)(o[4] - o[0]);
+            const size_t need = row_alloc_words((size_t)words[(size_t)r], nv);
             if (inv) {
                 h.data = 0; for (int b = 0; b < 6; ++b) h.end[b] = 0;
                 memset(e->stage + w, 0, need * 4);
             } else {
                 pack_row(e, pos, o, e->stage + w, h.end);
-                for (size_t z = (size_t)words[(size_t)r]; z < need; ++z) e->stage[w + z] = 0;
+                finish_row(e, e->stage + w, (size_t)words[(size_t)r], nv);
                 h.data = (unsigned long long)(uintptr_t)(dbase + w);
             }
             fill_head(e, e->stage_hdr[r - i], h, e->stage + w);
@@ -816,7 +833,8 @@ static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const in
     for (int b = 0; b < 7; ++b) o[b] = off[b];
     long long w = row_words_needed(e, pos, o, 0, nblk);
     if (w < 0) return FN3_EARG;
-    size_t need = ((size_t)w + 3) & ~(size_t)3; if (need == 0) need = 4;
+    const size_t nv = (size_t)(o[4] - o[0]);
+    const size_t need = row_alloc_words((size_t)w, nv);
     // scratch holds two samples: [0, half) and [half, 2*half)
     if (need * 2 > e->scratch_words) {
         size_t want = std::max(need * 2, e->scratch_words * 2);
@@ -832,7 +850,7 @@ static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const in
         int rc = ensure_stage(e, need, 1);
         if (rc) return rc;
         pack_row(e, pos, o, e->stage, h.end);
-        for (size_t z = (size_t)w; z < need; ++z) e->stage[z] = 0;
+        finish_row(e, e->stage, (size_t)w, nv);
         uint32_t* dst = e->d_scratch + (which ? e->scratch_words / 2 : 0);
         h.data = (unsigned long long)(uintptr_t)dst;
         if (head_out) fill_head(e, *head_out, h, e->stage);
@@ -979,15 +997,17 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     if (!invalid) for (int b = 0; b < 7; ++b) o[b] = off[b];
     // one pass: validate + pack into pinned staging (one word per position is the worst case)
     const size_t npos_in = invalid ? 0 : (size_t)(o[6] - o[0]);
-    int rc = ensure_stage(e, ((npos_in + 3) & ~(size_t)3) + 4, 1);
+    const size_t nv_in = invalid ? 0 : (size_t)(o[4] - o[0]);
+    int rc = ensure_stage(e, row_alloc_words(npos_in, nv_in) + 8, 1);
     if (rc) return rc;
     long long w = 0;
     if (!invalid) {
         w = pack_checked(e, pos, o, e->stage, h.end, &nblk);
         if (w < 0) return FN3_EARG;
     }
-    size_t need = ((size_t)w + 3) & ~(size_t)3; if (need == 0) need = 4;
-    for (size_t z = (size_t)w; z < need; ++z) e->stage[z] = 0;
+    const size_t need = row_alloc_words((size_t)w, nv_in);
+    if (invalid) memset(e->stage, 0, need * 4);
+    else finish_row(e, e->stage, (size_t)w, nv_in);
     uint32_t* dbase = nullptr;
     if ((rc = arena_alloc(e, need, &dbase))) return rc;
     const long long row = e->n_rows;

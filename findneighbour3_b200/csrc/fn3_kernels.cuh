@@ -338,6 +338,37 @@ __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __r
     return t;
 }
 
+// STREAM variant pre-pass on the row's 16-bit fingerprints (stored behind its list words): a V position whose coarse
+// block the query does not touch at all is a certain mismatch, so once their count exceeds the ceiling the pair is
+// proven "not a neighbour" from 2 bytes and ~4 instructions per word instead of 4 bytes and ~30.
+template <bool COUNT>
+__device__ __forceinline__ bool prepass_dead(const QView& qv, const uint32_t* __restrict__ d, uint32_t e3, uint32_t e5,
+                                             int k, int lane, unsigned long long& touched) {
+    const uint32_t* fp = d + ((e5 + 3u) & ~3u);
+    const uint32_t n8 = (e3 + 7u) >> 3;                        // 8 fingerprints per 128-bit load
+    int S = 0;
+    for (uint32_t b = 0; b < n8; b += 64) {                    // two loads per lane in flight: 512 fingerprints per step
+        uint4 f0 = make_uint4(0, 0, 0, 0), f1 = f0;
+        const bool h0 = b + lane < n8, h1 = b + 32u + lane < n8;
+        if (h0) { f0 = ld_stream_v4(fp + 4u * (b + lane)); if (COUNT) touched += 16; }
+        if (h1) { f1 = ld_stream_v4(fp + 4u * (b + 32u + lane)); if (COUNT) touched += 16; }
+        int s = 0;
+        if (h0) {
+            const uint32_t w[4] = {f0.x, f0.y, f0.z, f0.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s += 2 - (int)qv.cmap[w[i] & 0xffffu] - (int)qv.cmap[w[i] >> 16];
+        }
+        if (h1) {
+            const uint32_t w[4] = {f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s += 2 - (int)qv.cmap[w[i] & 0xffffu] - (int)qv.cmap[w[i] >> 16];
+        }
+        S += __reduce_add_sync(0xffffffffu, s);
+        if (S > k) return true;
+    }
+    return false;
+}
+
 __device__ __forceinline__ void emit_if_close(const CompareParams& p, const Tally& t0, int k, uint32_t nVq, uint32_t nUq,
                                               uint32_t nMq, long long qrow, long long crow, int lane) {
     if (t0.dead) return;
@@ -538,8 +569,12 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
             fetch(i + nwarps, nrow, n0, n1);
             if ((h0.x | h0.y) != 0u) {
                 const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
-                const Tally t = stream_row<COUNT>(qv, d, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, k, pos_bits, pmask, lane, touched);
-                emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, row, lane);
+                // rows with more V words than the ceiling can be rejected by the fingerprint pre-pass
+                const bool dead = (long long)h1.y > (long long)k && prepass_dead<COUNT>(qv, d, h1.y, h1.w, k, lane, touched);
+                if (!dead) {
+                    const Tally t = stream_row<COUNT>(qv, d, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, k, pos_bits, pmask, lane, touched);
+                    emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, row, lane);
+                }
             }
             i += nwarps; row = nrow; h0 = n0; h1 = n1;
         }

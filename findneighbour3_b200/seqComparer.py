@@ -18,6 +18,7 @@ persist() time instead of at the first comparison.
 """
 import hashlib
 import json
+import threading
 import uuid
 from collections import Counter
 from collections.abc import MutableMapping
@@ -95,6 +96,9 @@ class seqComparer():
         # anywhere; anything that needs a distance needs the CUDA engine and fails loudly without it.
         self._device = device
         self._engine = None
+        # persist() may run on another request thread while a query is in flight (server.py:513-516 is outside the
+        # write semaphore): the guid<->row maps and the device store change together under this lock
+        self._lock = threading.RLock()
         self._row_of = {}            # guid -> live row
         self._guid_of = {}           # row -> guid
         self._key_of = {}            # guid -> content key of what is in the device store
@@ -134,16 +138,17 @@ class seqComparer():
     def _store_put(self, guid, obj):
         pos, off, invalid = self._lists_of(obj)
         key = packing.content_key(pos, off, invalid)
-        if guid in self._row_of and self._key_of.get(guid) == key:
-            self.seqProfile._d[guid] = obj       # same expanded content (e.g. re-encoded as a patch): host-only change
-            return
-        if guid in self._row_of:
-            self._drop_row(guid)
-        row = self.engine.append(pos, off, invalid)
-        self._row_of[guid] = row
-        self._guid_of[row] = guid
-        self._key_of[guid] = key
-        self.seqProfile._d[guid] = obj
+        with self._lock:
+            if guid in self._row_of and self._key_of.get(guid) == key:
+                self.seqProfile._d[guid] = obj   # same expanded content (e.g. re-encoded as a patch): host-only change
+                return
+            if guid in self._row_of:
+                self._drop_row(guid)
+            row = self.engine.append(pos, off, invalid)
+            self._row_of[guid] = row
+            self._guid_of[row] = guid
+            self._key_of[guid] = key
+            self.seqProfile._d[guid] = obj
 
     def _drop_row(self, guid):
         row = self._row_of.pop(guid)
@@ -152,8 +157,9 @@ class seqComparer():
         self.engine.remove(row)
 
     def _store_del(self, guid):
-        self._drop_row(guid)
-        del self.seqProfile._d[guid]
+        with self._lock:
+            self._drop_row(guid)
+            del self.seqProfile._d[guid]
 
     def persist_many(self, objects, guids):
         """Bulk persist (server start-up reload, findNeighbour3-server.py:358-362): one device copy for all."""
@@ -390,9 +396,10 @@ class seqComparer():
                     raise KeyError("Key1={0} does not exist in the in-memory store.".format(guid))
                 rows.append(self._row_of[g])
             rows = np.asarray(rows, dtype=np.int64)
-        hits = self.engine.one_vs_all(self._row_of[guid], self._ceil(cutoff), rows)
-        gof = self._guid_of
-        return {gof[int(h['row'])]: (int(h['dist']), int(h['n1']), int(h['n2']), int(h['nboth'])) for h in hits}
+        with self._lock:
+            hits = self.engine.one_vs_all(self._row_of[guid], self._ceil(cutoff), rows)
+            gof = self._guid_of
+            return {gof[int(h['row'])]: (int(h['dist']), int(h['n1']), int(h['n2']), int(h['nboth'])) for h in hits}
 
     def mcompare(self, guid, guids=None):
         """one guid against all (or `guids`), one 9-element list per other guid (:149-172)."""

@@ -566,7 +566,7 @@ def main():
         ava = {"samples": int(n_now), "ceiling": 12, "seconds": t_ava, "edges": int(len(edges)),
                "pairs": n_now * (n_now - 1) // 2, "comparisons_per_s": n_now * (n_now - 1) / 2 / t_ava,
                "canonical_GBps": (bytes_canon_all / max(live, 1)) * (n_now * (n_now - 1) / 2) / t_ava / 1e9,
-               "note": "fn3_all_vs_all, upper triangle, tiles of 8 queries, wall clock incl. the copy of the edges to the host"}
+               "note": "fn3_all_vs_all, upper triangle, tiles of 128 queries queued 32 at a time, wall clock incl. the copy of the edges to the host"}
 
     # ---- leg 4 (extra): device compress() of full-length sequence strings --------------------
     ingest = None

@@ -109,6 +109,8 @@ struct fn3_engine {
     long long* h_rows = nullptr; long long h_rows_cap = 0;       // pinned
     // scratch rows for samples that are not stored (pair_lists / lists_vs_all)
     uint32_t* d_scratch = nullptr; size_t scratch_words = 0;
+    uint32_t* qstage = nullptr; size_t qstage_words = 0;      // pinned staging of the scratch samples (two halves)
+    bool qstage_busy = false;                                // a copy from qstage may still be in flight
     unsigned char* d_scratch_tile = nullptr; // one head tile for fn3_pair_lists' candidate
     uint4* d_flush = nullptr; long long flush_n = 0;
     // ingest (fn3_compress)
@@ -207,6 +209,7 @@ static int ensure_stage(fn3_engine* e, size_t words, size_t hdrs) {
         size_t want = std::max(words, e->stage_words * 2);
         want = std::max<size_t>(want, 1u << 16);
         if (e->stage) cudaFreeHost(e->stage);
+    if (e->qstage) cudaFreeHost(e->qstage);
         e->stage = nullptr; e->stage_words = 0;
         CU(e, cudaHostAlloc(&e->stage, want * 4, cudaHostAllocDefault));
         e->stage_words = want;
@@ -340,6 +343,7 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->h_outbuf) cudaFreeHost(e->h_outbuf);
     if (e->h_rows) cudaFreeHost(e->h_rows);
     if (e->stage) cudaFreeHost(e->stage);
+    if (e->qstage) cudaFreeHost(e->qstage);
     if (e->stage_hdr) cudaFreeHost(e->stage_hdr);
     if (e->q_stream) cudaStreamDestroy(e->q_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -831,33 +835,39 @@ static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const in
     if (invalid) { *out = h; if (head_out) fill_head(e, *head_out, h, nullptr); return FN3_OK; }
     long long o[7];
     for (int b = 0; b < 7; ++b) o[b] = off[b];
-    long long w = row_words_needed(e, pos, o, 0, nblk);
-    if (w < 0) return FN3_EARG;
-    const size_t nv = (size_t)(o[4] - o[0]);
-    const size_t need = row_alloc_words((size_t)w, nv);
-    // scratch holds two samples: [0, half) and [half, 2*half)
-    if (need * 2 > e->scratch_words) {
-        size_t want = std::max(need * 2, e->scratch_words * 2);
-        want = std::max<size_t>(want, 1u << 16);
+    const size_t npos_in = (size_t)(o[6] - o[0]), nv = (size_t)(o[4] - o[0]);
+    const size_t worst = row_alloc_words(npos_in, nv) + 8;          // one word per position is the worst case
+    // the query paths own a pinned staging buffer of two halves (guarded by query_mu, which every caller holds);
+    // a copy still in flight from a call that returned without waiting is drained first
+    if (e->qstage_busy) { CU(e, cudaStreamSynchronize(e->q_stream)); e->qstage_busy = false; }
+    if (worst * 2 > e->qstage_words) {
+        size_t want = std::max(worst * 2, std::max<size_t>(e->qstage_words * 2, 1u << 16));
+        if (e->qstage) cudaFreeHost(e->qstage);
+        e->qstage = nullptr; e->qstage_words = 0;
+        CU(e, cudaHostAlloc(&e->qstage, want * 4, cudaHostAllocDefault));
+        e->qstage_words = want;
+    }
+    if (worst * 2 > e->scratch_words) {
+        size_t want = std::max(worst * 2, std::max<size_t>(e->scratch_words * 2, 1u << 16));
         CU(e, cudaStreamSynchronize(e->q_stream));
         if (e->d_scratch) cudaFree(e->d_scratch);
         e->d_scratch = nullptr; e->scratch_words = 0;
         CU(e, cudaMalloc(&e->d_scratch, want * 4));
         e->scratch_words = want;
     }
-    {
-        std::lock_guard<std::mutex> g(e->store_mu);        // staging buffer is shared with append
-        int rc = ensure_stage(e, need, 1);
-        if (rc) return rc;
-        pack_row(e, pos, o, e->stage, h.end);
-        finish_row(e, e->stage, (size_t)w, nv);
-        uint32_t* dst = e->d_scratch + (which ? e->scratch_words / 2 : 0);
-        h.data = (unsigned long long)(uintptr_t)dst;
-        if (head_out) fill_head(e, *head_out, h, e->stage);
-        CU(e, cudaMemcpyAsync(dst, e->stage, need * 4, cudaMemcpyHostToDevice, e->q_stream));
-        e->h2d_bytes += (long long)need * 4;
-        CU(e, cudaStreamSynchronize(e->q_stream));
-    }
+    uint32_t* src = e->qstage + (which ? e->qstage_words / 2 : 0);
+    uint32_t nb = 0;
+    const long long w = pack_checked(e, pos, o, src, h.end, &nb);   // single pass: validate + pack
+    if (w < 0) return FN3_EARG;
+    if (nblk) *nblk = nb;
+    const size_t need = row_alloc_words((size_t)w, nv);
+    finish_row(e, src, (size_t)w, nv);
+    uint32_t* dst = e->d_scratch + (which ? e->scratch_words / 2 : 0);
+    h.data = (unsigned long long)(uintptr_t)dst;
+    if (head_out) fill_head(e, *head_out, h, src);
+    CU(e, cudaMemcpyAsync(dst, src, need * 4, cudaMemcpyHostToDevice, e->q_stream));   // consumed by the query that follows
+    e->qstage_busy = true;
+    e->h2d_bytes += (long long)need * 4;
     *out = h;
     return FN3_OK;
 }
@@ -906,6 +916,7 @@ static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int
             }
         }
         std::atomic_thread_fence(std::memory_order_acquire);      // records are read only after the flag
+        e->qstage_busy = false;                                   // the stream has consumed everything queued before
         e->t_wait_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_wait).count();
         cnt = (long long)flag[1];
         e->d2h_bytes += 16 + std::min<long long>(cnt, FN3_ZC_CAP) * (long long)sizeof(EdgeRec);
@@ -930,6 +941,7 @@ static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int
         e->d2h_bytes += FN3_OUT_HDR + first * (long long)sizeof(EdgeRec);
         cnt = (long long)e->h_count[0];
         e->count_dirty = true;
+        e->qstage_busy = false;
         *n_out = cnt;
         if (cnt > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld hits, %lld needed", (long long)cap, cnt);
         if (cnt > first) {
@@ -1099,7 +1111,7 @@ extern "C" int fn3_pair_lists(fn3_engine* e, const int32_t* pos1, const int32_t 
         e->stage_hdr[0] = chead;
         CU(e, cudaMemcpyAsync(e->d_heads, e->stage_hdr, sizeof(RowHead), cudaMemcpyHostToDevice, e->q_stream));
         k_scatter_heads<<<1, 32, 0, e->q_stream>>>(e->d_heads, 0, 1, job.ht);
-        e->launches += 2;
+        e->launches += 1;
         CU(e, cudaGetLastError());
         CU(e, cudaStreamSynchronize(e->q_stream));
     }

@@ -209,7 +209,6 @@ static int ensure_stage(fn3_engine* e, size_t words, size_t hdrs) {
         size_t want = std::max(words, e->stage_words * 2);
         want = std::max<size_t>(want, 1u << 16);
         if (e->stage) cudaFreeHost(e->stage);
-    if (e->qstage) cudaFreeHost(e->qstage);
         e->stage = nullptr; e->stage_words = 0;
         CU(e, cudaHostAlloc(&e->stage, want * 4, cudaHostAllocDefault));
         e->stage_words = want;
@@ -347,6 +346,7 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->stage_hdr) cudaFreeHost(e->stage_hdr);
     if (e->q_stream) cudaStreamDestroy(e->q_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    (void)cudaGetLastError();          // a failed release must not surface as the next engine's error
     delete e;
     return FN3_OK;
 }

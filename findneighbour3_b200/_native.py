@@ -63,6 +63,10 @@ SIGNATURES = {
                                  C.POINTER(Hit), _i32p]),
     "fn3_set_reference": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64]),
     "fn3_compress": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64, _i32p, C.c_char_p, C.c_int64, _i64p]),
+    "fn3_consensus": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),
+    "fn3_consensus_lists": (C.c_int, [_vp, C.c_int64, _i32p, _i64p, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),
+    "fn3_msa_sites": (C.c_int, [_vp, _i64p, C.c_int64, _i32p, C.c_int64, _i64p]),
+    "fn3_msa_align": (C.c_int, [_vp, _i64p, C.c_int64, _i32p, C.c_int64, _u8p, _i32p]),
     "fn3_profile_queries": (C.c_int, [_vp, _i64p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i64p, _i64p]),
     "fn3_launch_count": (C.c_int64, [_vp]),
 }

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libfn3.so")
 SRC = [os.path.join(HERE, "csrc", "fn3_engine.cu")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("fn3_types.h", "fn3_kernels.cuh", "fn3_compress.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("fn3_types.h", "fn3_kernels.cuh", "fn3_compress.cuh", "fn3_cluster.cuh")]
 HDR = [os.path.join(ROOT, "include", "fn3.h")]
 
 NVCC_FLAGS = [

@@ -35,6 +35,7 @@ static_assert(sizeof(EdgeRec) == sizeof(fn3_edge), "EdgeRec/fn3_edge mismatch");
 
 #include "fn3_kernels.cuh"
 #include "fn3_compress.cuh"
+#include "fn3_cluster.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -121,6 +122,16 @@ struct fn3_engine {
     int32_t* d_cpos = nullptr; uint32_t* d_ccounts = nullptr; uint32_t* d_ctotals = nullptr;
     uint8_t* h_seq = nullptr; uint32_t* h_ctotals = nullptr;   // pinned
     int32_t* h_cpos = nullptr; size_t h_cpos_cap = 0; uint8_t* h_mchars = nullptr; size_t h_mchars_cap = 0;   // pinned
+
+    // cluster statistics (fn3_consensus*, fn3_msa_*): vote planes + selection scratch, allocated on first use
+    uint32_t* d_votes = nullptr; long long vLpad = 0; int sel_ctas = 0;
+    uint32_t* d_sel_counts = nullptr; uint32_t* d_sel_totals = nullptr; uint32_t* h_sel_totals = nullptr;   // pinned
+    int32_t* d_sel_out = nullptr; size_t sel_out_cap = 0;
+    int32_t* d_sites = nullptr; size_t sites_cap = 0;
+    uint8_t* d_codes = nullptr; size_t codes_cap = 0;
+    int32_t* d_acounts = nullptr; size_t acounts_cap = 0;
+    int32_t* d_lpos = nullptr; size_t lpos_cap = 0;
+    long long* d_loff = nullptr; size_t loff_cap = 0;
 
     std::atomic<long long> launches{0};
 };
@@ -337,6 +348,9 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->h_ctotals) cudaFreeHost(e->h_ctotals);
     if (e->h_cpos) cudaFreeHost(e->h_cpos);
     if (e->h_mchars) cudaFreeHost(e->h_mchars);
+    cudaFree(e->d_votes); cudaFree(e->d_sel_counts); cudaFree(e->d_sel_totals); cudaFree(e->d_sel_out);
+    cudaFree(e->d_sites); cudaFree(e->d_codes); cudaFree(e->d_acounts); cudaFree(e->d_lpos); cudaFree(e->d_loff);
+    if (e->h_sel_totals) cudaFreeHost(e->h_sel_totals);
     if (e->in_stream) cudaStreamDestroy(e->in_stream);
     if (e->h_slots) cudaFreeHost(e->h_slots);
     if (e->h_outbuf) cudaFreeHost(e->h_outbuf);
@@ -1304,6 +1318,223 @@ extern "C" int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, i
     CU(e, cudaStreamSynchronize(st));
     if (total) memcpy(pos, e->h_cpos, (size_t)total * 4);
     if (n_m) memcpy(m_chars, e->h_mchars, (size_t)n_m);
+    return FN3_OK;
+}
+
+// ---- cluster statistics: consensus vote, MSA variant sites, alignment (fn3_cluster.cuh) --------------
+
+template <class T>
+static int ensure_dev(fn3_engine* e, T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return FN3_OK;
+    const size_t want = std::max<size_t>(std::max(need, *cap * 2), 1024);
+    if (*p) { cudaStreamSynchronize(e->q_stream); cudaFree(*p); }
+    *p = nullptr; *cap = 0;
+    CU(e, cudaMalloc(p, want * sizeof(T)));
+    *cap = want;
+    return FN3_OK;
+}
+
+static int ensure_votes(fn3_engine* e) {
+    if (e->d_votes) return FN3_OK;
+    const long long per_cta = (long long)FN3_SEL_THREADS * FN3_SEL_PER_THREAD;
+    e->sel_ctas = (int)((e->L + per_cta - 1) / per_cta);
+    e->vLpad = (long long)e->sel_ctas * per_cta;
+    CU(e, cudaMalloc(&e->d_votes, (size_t)e->vLpad * 5 * sizeof(uint32_t)));
+    CU(e, cudaMalloc(&e->d_sel_counts, (size_t)e->sel_ctas * 5 * sizeof(uint32_t)));
+    CU(e, cudaMalloc(&e->d_sel_totals, 8 * sizeof(uint32_t)));
+    CU(e, cudaHostAlloc(&e->h_sel_totals, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+    return FN3_OK;
+}
+
+// validate the rows against the host mirror, snapshot the head table, copy the list to d_rows (query_mu held)
+static int cluster_rows(fn3_engine* e, const int64_t* rows, int64_t n, bool reject_invalid, const char* who, HdrTable* ht) {
+    int rc;
+    if ((rc = ensure_rows(e, std::max<long long>(n, 1)))) return rc;
+    {
+        std::lock_guard<std::mutex> g(e->store_mu);
+        fill_hdr_table(e, *ht);
+        for (int64_t i = 0; i < n; ++i) {
+            const long long r = rows[i];
+            if (r < 0 || r >= e->n_rows) return set_err(e, FN3_ENOTFOUND, "%s: row %lld does not exist", who, r);
+            const uint8_t fl = e->h_flags[(size_t)r];
+            if (fl & 2) return set_err(e, FN3_ENOTFOUND, "%s: row %lld was removed", who, r);
+            if (reject_invalid && (fl & 1)) return set_err(e, FN3_EARG, "%s: row %lld is an invalid sample", who, r);
+            e->h_rows[i] = r;
+        }
+    }
+    if (n > 0) {
+        CU(e, cudaMemcpyAsync(e->d_rows, e->h_rows, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, e->q_stream));
+        e->h2d_bytes += n * (long long)sizeof(long long);
+    }
+    return FN3_OK;
+}
+
+static int grid_for(const fn3_engine* e, long long work_items, int threads) {
+    const long long want = (work_items + threads - 1) / threads;
+    return (int)std::max<long long>(1, std::min<long long>(want, (long long)e->sm_count * 8));
+}
+
+// count -> scan -> (host reads the list lengths) -> write; the selected positions stay in d_sel_out
+template <int MODE>
+static int run_select(fn3_engine* e, uint32_t thr, long long len[5], long long* total) {
+    const int NL = SelLists<MODE>::N;
+    cudaStream_t st = e->q_stream;
+    k_sel_count<MODE><<<e->sel_ctas, FN3_SEL_THREADS, 0, st>>>(e->d_votes, e->vLpad, thr, e->d_sel_counts);
+    k_sel_scan<<<1, 1024, 0, st>>>(e->d_sel_counts, e->d_sel_totals, e->sel_ctas, NL);
+    e->launches += 2;
+    CU(e, cudaGetLastError());
+    CU(e, cudaMemcpyAsync(e->h_sel_totals, e->d_sel_totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(e, cudaStreamSynchronize(st));
+    e->d2h_bytes += 8 * (long long)sizeof(uint32_t);
+    *total = 0;
+    for (int l = 0; l < 5; ++l) { len[l] = l < NL ? (long long)e->h_sel_totals[l] : 0; *total += len[l]; }
+    int rc;
+    if ((rc = ensure_dev(e, &e->d_sel_out, &e->sel_out_cap, (size_t)std::max<long long>(*total, 1)))) return rc;
+    if (*total > 0) {
+        k_sel_write<MODE><<<e->sel_ctas, FN3_SEL_THREADS, 0, st>>>(e->d_votes, e->vLpad, thr, e->d_sel_counts, e->d_sel_totals,
+                                                                   e->d_sel_out);
+        e->launches += 1;
+        CU(e, cudaGetLastError());
+    }
+    return FN3_OK;
+}
+
+static int fetch_selected(fn3_engine* e, long long total, int32_t* out, int64_t cap, const char* who) {
+    if (total > cap || (total > 0 && !out))
+        return set_err(e, FN3_ECAPACITY, "%s: output buffer holds %lld positions, %lld needed", who, (long long)cap, total);
+    if (total > 0) {
+        CU(e, cudaMemcpyAsync(out, e->d_sel_out, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, e->q_stream));
+        e->d2h_bytes += total * (long long)sizeof(int32_t);
+    }
+    CU(e, cudaStreamSynchronize(e->q_stream));
+    return FN3_OK;
+}
+
+static int consensus_tail(fn3_engine* e, int64_t min_votes, int32_t* pos, int64_t pos_cap, int32_t off[6], int64_t* n_pos,
+                          const char* who) {
+    long long len[5], total = 0;
+    const uint32_t thr = (uint32_t)std::min<int64_t>(min_votes, 0xffffffffll);
+    int rc = run_select<1>(e, thr, len, &total);
+    if (rc) return rc;
+    off[0] = 0;
+    for (int l = 0; l < 5; ++l) off[l + 1] = off[l] + (int32_t)len[l];
+    *n_pos = total;
+    return fetch_selected(e, total, pos, pos_cap, who);
+}
+
+extern "C" int fn3_consensus(fn3_engine* e, const int64_t* rows, int64_t n_rows, int64_t min_votes, int32_t* pos,
+                             int64_t pos_cap, int32_t off[6], int64_t* n_pos) {
+    if (!e || !off || !n_pos || n_rows < 0 || (n_rows > 0 && !rows) || min_votes < 1)
+        return set_err(e, FN3_EARG, "fn3_consensus: bad arguments (min_votes must be >= 1)");
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    int rc;
+    if ((rc = ensure_votes(e))) return rc;
+    HdrTable ht;
+    if ((rc = cluster_rows(e, rows, n_rows, false, "fn3_consensus", &ht))) return rc;
+    cudaStream_t st = e->q_stream;
+    CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * 5 * sizeof(uint32_t), st));
+    if (n_rows > 0) {
+        k_votes_rows<<<grid_for(e, n_rows * 32, 256), 256, 0, st>>>(e->d_rows, n_rows, ht, e->d_votes, e->vLpad, 1, e->pos_bits);
+        e->launches += 1;
+        CU(e, cudaGetLastError());
+    }
+    return consensus_tail(e, min_votes, pos, pos_cap, off, n_pos, "fn3_consensus");
+}
+
+extern "C" int fn3_consensus_lists(fn3_engine* e, int64_t n, const int32_t* pos_in, const int64_t* off_in, int64_t min_votes,
+                                   int32_t* pos, int64_t pos_cap, int32_t off[6], int64_t* n_pos) {
+    if (!e || !off || !n_pos || n < 0 || (n > 0 && !off_in) || min_votes < 1)
+        return set_err(e, FN3_EARG, "fn3_consensus_lists: bad arguments (min_votes must be >= 1)");
+    const long long total_in = n > 0 ? (long long)(off_in[6 * n] - off_in[0]) : 0;
+    if (total_in > 0 && !pos_in) return set_err(e, FN3_EARG, "fn3_consensus_lists: null lists");
+    for (int64_t l = 0; l < 6 * n; ++l) {
+        if (off_in[l + 1] < off_in[l]) return set_err(e, FN3_EARG, "fn3_consensus_lists: list offsets must be non-decreasing");
+        for (int64_t i = off_in[l]; i < off_in[l + 1]; ++i) {
+            if (pos_in[i] < 0 || (long long)pos_in[i] >= e->L) return set_err(e, FN3_EARG, "fn3_consensus_lists: position out of range");
+            if (i > off_in[l] && pos_in[i] <= pos_in[i - 1])
+                return set_err(e, FN3_EARG, "fn3_consensus_lists: positions must be strictly increasing within a list");
+        }
+    }
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    int rc;
+    if ((rc = ensure_votes(e))) return rc;
+    cudaStream_t st = e->q_stream;
+    CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * 5 * sizeof(uint32_t), st));
+    if (total_in > 0) {
+        if ((rc = ensure_dev(e, &e->d_lpos, &e->lpos_cap, (size_t)total_in))) return rc;
+        if ((rc = ensure_dev(e, &e->d_loff, &e->loff_cap, (size_t)(6 * n + 1)))) return rc;
+        std::vector<long long> rel((size_t)(6 * n + 1));
+        for (int64_t l = 0; l <= 6 * n; ++l) rel[(size_t)l] = (long long)(off_in[l] - off_in[0]);
+        CU(e, cudaMemcpyAsync(e->d_lpos, pos_in + off_in[0], (size_t)total_in * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(e, cudaMemcpyAsync(e->d_loff, rel.data(), rel.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CU(e, cudaStreamSynchronize(st));                       // `rel` is pageable and leaves scope
+        e->h2d_bytes += total_in * (long long)sizeof(int32_t) + (long long)rel.size() * 8;
+        k_votes_lists<<<grid_for(e, total_in, 256), 256, 0, st>>>(e->d_lpos, e->d_loff, 6 * n, total_in, e->d_votes, e->vLpad);
+        e->launches += 1;
+        CU(e, cudaGetLastError());
+    }
+    return consensus_tail(e, min_votes, pos, pos_cap, off, n_pos, "fn3_consensus_lists");
+}
+
+extern "C" int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t* sites, int64_t sites_cap,
+                             int64_t* n_sites) {
+    if (!e || !n_sites || n_rows < 0 || (n_rows > 0 && !rows)) return set_err(e, FN3_EARG, "fn3_msa_sites: bad arguments");
+    *n_sites = 0;
+    if (n_rows == 0) return FN3_OK;
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    int rc;
+    if ((rc = ensure_votes(e))) return rc;
+    HdrTable ht;
+    if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_sites", &ht))) return rc;
+    cudaStream_t st = e->q_stream;
+    CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * 4 * sizeof(uint32_t), st));
+    k_votes_rows<<<grid_for(e, n_rows * 32, 256), 256, 0, st>>>(e->d_rows, n_rows, ht, e->d_votes, e->vLpad, 0, e->pos_bits);
+    e->launches += 1;
+    CU(e, cudaGetLastError());
+    long long len[5], total = 0;
+    if ((rc = run_select<0>(e, (uint32_t)std::min<int64_t>(n_rows, 0xffffffffll), len, &total))) return rc;
+    *n_sites = total;
+    return fetch_selected(e, total, sites, sites_cap, "fn3_msa_sites");
+}
+
+extern "C" int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows, const int32_t* sites, int64_t n_sites,
+                             uint8_t* codes, int32_t* counts) {
+    if (!e || n_rows < 0 || n_sites < 0 || (n_rows > 0 && (!rows || !counts)) || (n_sites > 0 && !sites))
+        return set_err(e, FN3_EARG, "fn3_msa_align: bad arguments");
+    for (int64_t k = 0; k < n_sites; ++k) {
+        if (sites[k] < 0 || (long long)sites[k] >= e->L) return set_err(e, FN3_EARG, "fn3_msa_align: site out of range");
+        if (k && sites[k] <= sites[k - 1]) return set_err(e, FN3_EARG, "fn3_msa_align: sites must be strictly increasing");
+    }
+    if (n_rows == 0) return FN3_OK;
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    int rc;
+    HdrTable ht;
+    if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_align", &ht))) return rc;
+    cudaStream_t st = e->q_stream;
+    if ((rc = ensure_dev(e, &e->d_sites, &e->sites_cap, (size_t)std::max<int64_t>(n_sites, 1)))) return rc;
+    if ((rc = ensure_dev(e, &e->d_acounts, &e->acounts_cap, (size_t)n_rows * 4))) return rc;
+    const size_t ncodes = (size_t)n_rows * (size_t)n_sites;
+    const bool want_codes = codes != nullptr && ncodes > 0;
+    if (want_codes) {
+        if ((rc = ensure_dev(e, &e->d_codes, &e->codes_cap, ncodes))) return rc;
+        CU(e, cudaMemsetAsync(e->d_codes, 0, ncodes, st));
+    }
+    if (n_sites > 0) {
+        CU(e, cudaMemcpyAsync(e->d_sites, sites, (size_t)n_sites * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        e->h2d_bytes += n_sites * (long long)sizeof(int32_t);
+    }
+    k_align<<<grid_for(e, n_rows * 32, 256), 256, 0, st>>>(e->d_rows, n_rows, ht, e->d_sites, n_sites,
+                                                          want_codes ? e->d_codes : nullptr, e->d_acounts, e->pos_bits);
+    e->launches += 1;
+    CU(e, cudaGetLastError());
+    CU(e, cudaMemcpyAsync(counts, e->d_acounts, (size_t)n_rows * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (want_codes) CU(e, cudaMemcpyAsync(codes, e->d_codes, ncodes, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaStreamSynchronize(st));
+    e->d2h_bytes += n_rows * 16 + (want_codes ? (long long)ncodes : 0);
     return FN3_OK;
 }
 

@@ -253,6 +253,63 @@ class Engine:
             return None
         return (hit.dist, hit.n1, hit.n2, hit.nboth)
 
+    # -- cluster statistics ---------------------------------------------------------------
+    def _consensus_call(self, call):
+        """shared output protocol of fn3_consensus / fn3_consensus_lists -> (pos int32[], off int32[6])."""
+        off = np.zeros(6, dtype=np.int32)
+        npos = C.c_int64(0)
+        cap = 1 << 14
+        while True:
+            pos = np.empty(cap, dtype=np.int32)
+            rc = call(_ptr(pos, _i32p), cap, _ptr(off, _i32p), C.byref(npos))
+            if rc == N.FN3_ECAPACITY:
+                cap = int(npos.value)
+                continue
+            self._check(rc)
+            return pos[: npos.value].copy(), off
+
+    def consensus(self, rows, min_votes):
+        """per-list positions carried by >= min_votes of the stored rows -> (pos, off[6]) in list order A,C,G,T,N."""
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        return self._consensus_call(lambda p, cap, off, npos: self._lib.fn3_consensus(
+            self._h, _ptr(r, _i64p), r.size, int(min_votes), p, cap, off, npos))
+
+    def consensus_lists(self, pos_in, off_in, min_votes):
+        """the same vote over un-stored samples (pos concatenated, off int64[6n+1] as for append_bulk)."""
+        pos_in = _as_i32(pos_in)
+        off_in = np.ascontiguousarray(off_in, dtype=np.int64)
+        n = (off_in.size - 1) // 6
+        if off_in.size != 6 * n + 1:
+            raise ValueError("off must have 6*n+1 entries")
+        return self._consensus_call(lambda p, cap, off, npos: self._lib.fn3_consensus_lists(
+            self._h, n, _ptr(pos_in, _i32p), _ptr(off_in, _i64p), int(min_votes), p, cap, off, npos))
+
+    def msa_sites(self, rows):
+        """ordered variant positions of the (valid) stored rows -> int32[]."""
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        n_sites = C.c_int64(0)
+        cap = 1 << 14
+        while True:
+            sites = np.empty(cap, dtype=np.int32)
+            rc = self._lib.fn3_msa_sites(self._h, _ptr(r, _i64p), r.size, _ptr(sites, _i32p), cap, C.byref(n_sites))
+            if rc == N.FN3_ECAPACITY:
+                cap = int(n_sites.value)
+                continue
+            self._check(rc)
+            return sites[: n_sites.value].copy()
+
+    def msa_align(self, rows, sites, want_codes=True):
+        """-> (codes uint8[n, n_sites] or None, counts int32[n, 4] = |N|, |M|, N at sites, M at sites)."""
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        s = _as_i32(sites)
+        counts = np.zeros((r.size, 4), dtype=np.int32)
+        codes = np.zeros((r.size, s.size), dtype=np.uint8) if want_codes else None
+        rc = self._lib.fn3_msa_align(self._h, _ptr(r, _i64p), r.size, _ptr(s, _i32p), s.size,
+                                     _ptr(codes, _u8p) if codes is not None and codes.size else None,
+                                     _ptr(counts, _i32p))
+        self._check(rc)
+        return codes, counts
+
     # -- measurement ----------------------------------------------------------------------
     def profile_queries(self, query_rows, ceiling, flush_l2=False, count_bytes=False):
         """device-only timing of one-vs-all for each stored row in query_rows (bench.py's `value` leg)."""

@@ -1,14 +1,17 @@
-"""mixPORE / multi-sequence-alignment statistics of the reference's seqComparer (host side).
+"""mixPORE / multi-sequence-alignment statistics of the reference's seqComparer.
 
-Restates src/seqComparer.py:617-1128 (estimate_expected_*, multi_sequence_alignment, _msa) over the
-host copies of the sample dicts.  This is SURVEY.md §8(f)-3 ("next" row): the variant-site extraction and
-per-sample N/M counts are set operations over the same lists the device store holds; the binomial tests
-stay on the host (scipy).  Output keys, column names and value conventions follow the reference exactly,
-including its quirk that column 'expected_proportion2' carries expected_p3 (:1071-1072).
+Restates src/seqComparer.py:617-1128 (estimate_expected_*, multi_sequence_alignment, _msa).  This is SURVEY.md
+§8(f)-3: the variant-site extraction, the aligned characters and every N/M tally are computed by the device
+engine on its own rows (fn3_msa_sites / fn3_msa_align, csrc/fn3_cluster.cuh) — this module holds no set algebra
+over sample lists; what stays here is the reference's control flow, its float arithmetic (medians, proportions)
+and the four binomial tests (scipy).  Output keys, column names and value conventions follow the reference
+exactly, including its quirk that column 'expected_proportion2' carries expected_p3 (:1071-1072).
 """
 import numpy as np
 import pandas as pd
 from scipy.stats import binomtest
+
+_CODE_CHARS = np.frombuffer(b"?ACGTNM", dtype=np.uint8)      # fn3_msa_align codes 1..6; 0 = reference base
 
 
 def _binom_greater(x, n, p):
@@ -25,45 +28,48 @@ def estimate_expected_proportion(seqs):
     return np.median([s.count('N') for s in seqs]) / len(seqs[0])
 
 
-def _sampled_unknowns(sc, sample_size, exclude_guids, counter):
-    """shared loop of estimate_expected_unk / _unk_sites (:632-689): median over the first sample_size valid guids."""
+def _is_valid(sc, obj):
+    """what `_computeComparator` decides (:309-335) without expanding a patch: False = invalid sample"""
+    if not isinstance(obj, dict):
+        raise TypeError("Cannot use object of class {0} as a sequence".format(type(obj)))
+    if obj.get('invalid', 0) == 1:
+        return False
+    keys = set(obj.keys())
+    if keys == sc.compressed_sequence_keys or keys == sc.patch_and_consensus_keys:
+        return True
+    raise KeyError("Was passed a dictionary with keys {0} but cannot handle this".format(obj.keys()))
+
+
+def _sampled_unknowns(sc, sample_size, exclude_guids, sites, unk_type):
+    """shared loop of estimate_expected_unk / _unk_sites (:632-689): median, over the first sample_size valid
+    guids, of the N and/or M count (sites=None: whole sample, :648-652; else at the given sites, :678-681)."""
     guids = list(set(sc.seqProfile.keys()) - set(exclude_guids))
-    counts = []
-    for guid in guids:
-        try:
-            seq = sc._computeComparator(sc.seqProfile[guid])
-            counts.append(counter(seq))
-        except ValueError:
-            pass
-        if len(counts) >= sample_size:
-            break
-    if len(counts) >= sample_size:
-        return np.median(counts)
-    return None
+    with sc._lock:
+        rows = []
+        for guid in guids:
+            if _is_valid(sc, sc.seqProfile[guid]):
+                rows.append(sc._row_of[guid])
+            if len(rows) >= sample_size:
+                break
+    if len(rows) < sample_size or len(rows) == 0:
+        return None
+    at = np.empty(0, dtype=np.int32) if sites is None else np.asarray(sorted(sites), dtype=np.int32)
+    _, counts = sc.engine.msa_align(rows, at, want_codes=False)
+    col_n, col_m = (0, 1) if sites is None else (2, 3)
+    per_sample = np.zeros(len(rows), dtype=np.int64)
+    if unk_type in ('N', 'N_or_M'):
+        per_sample += counts[:, col_n]
+    if unk_type in ('M', 'N_or_M'):
+        per_sample += counts[:, col_m]
+    return np.median(per_sample.tolist())
 
 
 def estimate_expected_unk(sc, sample_size=30, exclude_guids=set(), unk_type='N'):
-    def counter(seq):
-        n = 0
-        if unk_type in ('N', 'N_or_M'):
-            n += len(seq['N'])
-        if unk_type in ('M', 'N_or_M'):
-            n += len(seq['M'])
-        return n
-    return _sampled_unknowns(sc, sample_size, exclude_guids, counter)
+    return _sampled_unknowns(sc, sample_size, exclude_guids, None, unk_type)
 
 
 def estimate_expected_unk_sites(sc, sample_size=30, sites=set(), exclude_guids=set(), unk_type='N'):
-    sites = set(sites)
-
-    def counter(seq):
-        n = 0
-        if unk_type in ('N', 'N_or_M'):
-            n += len(seq['N'].intersection(sites))
-        if unk_type in ('M', 'N_or_M'):
-            n += len(set(seq['M'].keys()).intersection(sites))
-        return n
-    return _sampled_unknowns(sc, sample_size, exclude_guids, counter)
+    return _sampled_unknowns(sc, sample_size, exclude_guids, set(sites), unk_type)
 
 
 def multi_sequence_alignment(sc, guids, output='dict', sample_size=30, expected_p1=None, uncertain_base_type='N'):
@@ -75,10 +81,9 @@ def multi_sequence_alignment(sc, guids, output='dict', sample_size=30, expected_
         sample_size = 30
     valid, invalid = [], []
     for guid in guids:
-        try:
-            sc._computeComparator(sc.seqProfile[guid])
+        if _is_valid(sc, sc.seqProfile[guid]):
             valid.append(guid)
-        except ValueError:
+        else:
             invalid.append(guid)
     if expected_p1 is None:
         expected_n1 = estimate_expected_unk(sc, sample_size=sample_size, exclude_guids=invalid)
@@ -89,42 +94,33 @@ def multi_sequence_alignment(sc, guids, output='dict', sample_size=30, expected_
 def msa(sc, valid_guids, invalid_guids, expected_p1, output, sample_size, uncertain_base_type='N'):
     """variant-site alignment + four one-sided binomial tests per sample (:804-1128)."""
     ref = sc.reference
-    seqs = {g: sc._computeComparator(sc.seqProfile[g]) for g in valid_guids}
+    if len(valid_guids) == 0:
+        return None
     all_unk = {'N': {}, 'M': {}, 'N_or_M': {}}
     align_unk = {'N': {}, 'M': {}, 'N_or_M': {}}
 
-    # steps 1-3: positions where the valid samples (reference base where a sample has no call) disagree
-    seen = {}
-    for g in valid_guids:
-        s = seqs[g]
-        all_unk['N'][g] = len(s['N'])
-        all_unk['M'][g] = len(s['M'])
-        all_unk['N_or_M'][g] = all_unk['N'][g] + all_unk['M'][g]
-        for base in ('A', 'C', 'T', 'G'):
-            for p in s[base]:
-                seen.setdefault(p, set()).add(base)
-    for g in valid_guids:
-        s = seqs[g]
-        for p in seen:
-            if not (p in s['A'] or p in s['C'] or p in s['T'] or p in s['G']):
-                seen[p].add(ref[p])
-    ordered = sorted(p for p, bases in seen.items() if len(bases) > 1)
-
-    # step 4: aligned strings (later keys win, as in the reference's A,C,T,G,N,M scan :941-948)
+    # steps 1-4 on the device: variant sites of these rows, then every row's character and N/M tallies there
+    with sc._lock:
+        rows = [sc._row_of[g] for g in valid_guids]
+    sites = sc.engine.msa_sites(rows)
+    codes, counts = sc.engine.msa_align(rows, sites, want_codes=True)
+    ordered = sites.tolist()
+    chars = _CODE_CHARS[codes]
+    if len(ordered):
+        ref_at = np.frombuffer(ref.encode('ascii'), dtype=np.uint8)[sites] if len(ordered) * 64 > len(ref) else \
+            np.frombuffer(''.join(ref[p] for p in ordered).encode('ascii'), dtype=np.uint8)
+        chars = np.where(codes == 0, ref_at[None, :], chars)
     guid2seq, guid2msa = {}, {}
-    for g in valid_guids:
-        s = seqs[g]
-        row = []
-        for p in ordered:
-            ch = ref[p]
-            for base in ('A', 'C', 'T', 'G', 'N'):
-                if p in s[base]:
-                    ch = base
-            if p in s['M']:
-                ch = 'M'
-            row.append(ch)
-        guid2seq[g] = row
-        guid2msa[g] = ''.join(row)
+    for i, g in enumerate(valid_guids):
+        text = chars[i].tobytes().decode('ascii')
+        guid2seq[g] = list(text)
+        guid2msa[g] = text
+        all_unk['N'][g] = int(counts[i, 0])
+        all_unk['M'][g] = int(counts[i, 1])
+        all_unk['N_or_M'][g] = all_unk['N'][g] + all_unk['M'][g]
+        align_unk['N'][g] = int(counts[i, 2])
+        align_unk['M'][g] = int(counts[i, 3])
+        align_unk['N_or_M'][g] = align_unk['N'][g] + align_unk['M'][g]
 
     # step 5: expectation at the aligned sites
     expected_n2 = estimate_expected_unk_sites(sc, sample_size=sample_size, exclude_guids=invalid_guids,
@@ -134,16 +130,10 @@ def msa(sc, valid_guids, invalid_guids, expected_p1, output, sample_size, uncert
     else:
         expected_p2 = expected_n2 / len(ordered)
 
-    if len(valid_guids) == 0:
-        return None
-
     p1, p2, p3, p4 = {}, {}, {}, {}
     observed, e1, e2, e3, e4 = {}, {}, {}, {}, {}
     for g in valid_guids:
         aligned = guid2msa[g]
-        for t in ('N', 'M'):
-            align_unk[t][g] = aligned.count(t)
-        align_unk['N_or_M'][g] = align_unk['N'][g] + align_unk['M'][g]
         x = align_unk[uncertain_base_type][g]
         n = len(aligned)
 

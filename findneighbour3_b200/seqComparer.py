@@ -18,6 +18,7 @@ persist() time instead of at the first comparison.
 """
 import hashlib
 import json
+import math
 import threading
 import uuid
 from collections import Counter
@@ -454,26 +455,49 @@ class seqComparer():
     # ------------------------------------------------------------------------------------------
     # reference API: double delta (host-RAM representation only; distances never see it)
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _min_votes(n_objects, cutoff_proportion):
+        """the reference keeps a position iff count >= len(list)*cutoff_proportion (:493-499); counts are
+        integers >= 1, so that is count >= max(1, smallest integer >= the float product)."""
+        return max(1, int(math.ceil(n_objects * cutoff_proportion)))
+
+    @staticmethod
+    def _consensus_dict(pos, off):
+        """engine output (lists A,C,G,T,N) -> the reference's consensus object"""
+        return {'A': set(pos[off[0]:off[1]].tolist()), 'C': set(pos[off[1]:off[2]].tolist()),
+                'T': set(pos[off[3]:off[4]].tolist()), 'G': set(pos[off[2]:off[3]].tolist()),
+                'N': set(pos[off[4]:off[5]].tolist())}
+
     def consensus(self, compressed_sequences, cutoff_proportion):
         """majority (>= cutoff_proportion) variant calls over a list of samples (:460-501).
 
-        As in the reference, the vote counts the *given* objects' own A/C/G/T/N sets (objects in patch
-        form contribute nothing, :485-486) and the threshold uses the full list length (:493)."""
+        The per-position vote and the threshold run on the device (fn3_consensus_lists).  As in the
+        reference, the vote counts the *given* objects' own A/C/G/T/N sets (objects in patch form
+        contribute nothing, :485-486) and the threshold uses the full list length (:493)."""
         any_valid = False
         for cs in compressed_sequences:
             if self._computeComparator(cs)['invalid'] == 0:
                 any_valid = True
         if not any_valid:
             return {'A': set(), 'C': set(), 'T': set(), 'G': set(), 'N': set()}
-        needed = len(compressed_sequences) * cutoff_proportion
-        out = {}
-        for item in _BASES5:
-            votes = Counter()
-            for cs in compressed_sequences:
-                if item in cs.keys():
-                    votes.update(cs[item])
-            out[item] = set(p for p, n in votes.items() if n >= needed)
-        return out
+        voters = [cs for cs in compressed_sequences if set(cs.keys()) == self.compressed_sequence_keys]
+        if len(voters) == 0:
+            return {'A': set(), 'C': set(), 'T': set(), 'G': set(), 'N': set()}
+        pos_in, off_in, _ = packing.pack_many(voters)
+        pos, off = self.engine.consensus_lists(pos_in, off_in, self._min_votes(len(compressed_sequences), cutoff_proportion))
+        return self._consensus_dict(pos, off)
+
+    def _consensus_of_stored(self, guids, cutoff_proportion):
+        """consensus() over stored samples without shipping their lists: the device votes on its own rows
+        (fn3_consensus).  Same quirks: a guid listed twice votes twice, samples currently held in patch
+        form do not vote, the threshold uses len(guids)."""
+        with self._lock:
+            rows = [self._row_of[g] for g in guids
+                    if set(self.seqProfile._d[g].keys()) == self.compressed_sequence_keys]
+        if len(rows) == 0:
+            return {'A': set(), 'C': set(), 'T': set(), 'G': set(), 'N': set()}
+        pos, off = self.engine.consensus(np.asarray(rows, dtype=np.int64), self._min_votes(len(guids), cutoff_proportion))
+        return self._consensus_dict(pos, off)
 
     def generate_patch(self, compressed_sequence, consensus):
         """difference between a sample and a consensus; empty sets are not stored (:503-524)."""
@@ -522,7 +546,8 @@ class seqComparer():
         """re-encode guid and its neighbours within snpCompressionCeiling against their consensus (:579-615).
 
         The neighbour scan is ONE device one-vs-all at ceiling snpCompressionCeiling (the reference does N
-        countDifferences_byKey calls, :584-592); a neighbour qualifies if dist < ceiling (:589)."""
+        countDifferences_byKey calls, :584-592); a neighbour qualifies if dist < ceiling (:589).  The
+        consensus vote runs on the device over the visited rows (fn3_consensus)."""
         visited_guids = [guid]
         visited_sequences = [self.seqProfile[guid]]
         found = self.neighbours(guid, None, self.snpCompressionCeiling)
@@ -538,7 +563,7 @@ class seqComparer():
                 visited_sequences.append(self.seqProfile[other])
                 visited_guids.append(other)
         if len(visited_sequences) > 1:
-            consensus = self.consensus(visited_sequences, cutoff_proportion)
+            consensus = self._consensus_of_stored(visited_guids, cutoff_proportion)
             consensus_md5 = self.compressed_sequence_hash(consensus)
             self.consensi[consensus_md5] = consensus
             for g in visited_guids:
@@ -549,7 +574,7 @@ class seqComparer():
         return visited_guids
 
     # ------------------------------------------------------------------------------------------
-    # reference API: mixPORE / MSA (host side)
+    # reference API: mixPORE / MSA: sites, alignment and N/M tallies on the device, tests on the host
     # ------------------------------------------------------------------------------------------
     def estimate_expected_proportion(self, seqs):
         from .msa import estimate_expected_proportion

@@ -192,6 +192,37 @@ int fn3_set_reference(fn3_engine* e, const char* reference, const int32_t* exclu
 int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_cap,
                  int32_t off[7], char* m_chars, int64_t m_cap, int64_t* n_pos);
 
+/* ---- cluster statistics on the device ------------------- */
+
+/* consensus(compressed_sequences, cutoff_proportion) (:460-501) over STORED rows: position p enters output list b
+ * (order A,C,G,T,N; off[0..5] are the 6 CSR offsets into pos) iff at least min_votes of rows[0..n_rows) carry p in
+ * their list b.  A row given twice votes twice (the reference counts the objects of its list one by one, :483-490);
+ * invalid rows vote for nothing.  The caller turns the reference's float threshold `len(list)*cutoff_proportion`
+ * (:493) into min_votes = max(1, smallest integer >= it) and leaves out the objects that the reference's vote
+ * ignores (those held in patch form, :485).  FN3_ECAPACITY with *n_pos = required if pos is too small. */
+int fn3_consensus(fn3_engine* e, const int64_t* rows, int64_t n_rows, int64_t min_votes,
+                  int32_t* pos, int64_t pos_cap, int32_t off[6], int64_t* n_pos);
+
+/* The same vote over samples that are NOT stored: n samples as in fn3_append_bulk (off_in has 6*n+1 entries;
+ * the M lists are ignored, as in the reference). */
+int fn3_consensus_lists(fn3_engine* e, int64_t n, const int32_t* pos_in, const int64_t* off_in, int64_t min_votes,
+                        int32_t* pos, int64_t pos_cap, int32_t off[6], int64_t* n_pos);
+
+/* _msa steps 1-3 (:895-931): the ordered variant positions of the valid stored rows rows[0..n_rows): positions at
+ * which the samples show more than one base, a sample without an A/C/G/T call there (N and M included) counting as
+ * the reference base.  Invalid rows are rejected (FN3_EARG; the reference raises ValueError, :320).
+ * FN3_ECAPACITY with *n_sites = required if sites is too small. */
+int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t* sites, int64_t sites_cap,
+                  int64_t* n_sites);
+
+/* _msa step 4 and the N/M tallies (:933-950, :905-908, :975-977), and estimate_expected_unk_sites (:664-689):
+ * for every row i and every site k (sites strictly increasing), codes[i*n_sites + k] = 0 reference base, 1..4
+ * A,C,G,T, 5 N, 6 M (a later list of the reference's scan order A,C,T,G,N,M wins, :941-948); counts[4*i..] =
+ * { |N_i|, |M_i|, N characters at the sites, M characters at the sites }.  codes may be NULL (counts only: the
+ * last two are then the plain intersections |N_i n sites|, |M_i n sites| of :678-681). */
+int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows, const int32_t* sites, int64_t n_sites,
+                  uint8_t* codes, int32_t* counts);
+
 /* ---- measurement hooks (bench.py only; no effect on results) -------------------- */
 
 /* Run the one-vs-all DEVICE work (query-map build + compare kernel, inputs already resident in HBM) once

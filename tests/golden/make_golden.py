@@ -14,6 +14,9 @@ Files
   collection.json     a family-structured synthetic collection in list form (findneighbour3_b200.synth) and
                       the reference's neighbour lists for every query at ceilings 12, 20 and 250
   consensus.json      consensus / patch / hash vectors (double delta, seqComparer.py:460-565)
+  msa.json            multi_sequence_alignment outputs on the reference's own test families (tests 45a-47c)
+  cluster.json        consensus votes, _msa sites / aligned strings / N-M tallies and estimate_expected_unk_sites on
+                      the collection of collection.json (`--cluster` regenerates only this file)
 """
 import json
 import os
@@ -340,10 +343,83 @@ def make_msa():
     dump("msa.json", out)
 
 
+def make_cluster():
+    """consensus() votes, _msa steps 1-4 and estimate_expected_unk_sites of the reference on the family-structured
+    collection of collection.json (N blocks, IUPAC M, invalid samples): the fixtures behind the device kernels of
+    csrc/fn3_cluster.cuh.  Everything here is independent of set iteration order: sample_size is set to the
+    number of valid stored samples, so the reference's "first sample_size guids of an unordered set" is all of them."""
+    with open(os.path.join(HERE, "collection.json")) as fh:
+        c = json.load(fh)
+    L = c["genome_length"]
+    ref = synth.reference_string(synth.random_reference(L, c["ref_seed"]))
+    pos, off, invalid = np.array(c["pos"], np.int32), np.array(c["off"], np.int64), np.array(c["invalid"], np.uint8)
+    n = invalid.size
+    excluded = synth.synthetic_mask(L, 2000, 12, seed=3)
+
+    def as_dict(i):
+        if invalid[i]:
+            return {"invalid": 1}
+        o = off[6 * i: 6 * i + 7]
+        d = {"invalid": 0}
+        for b, k in enumerate("ACGTN"):
+            d[k] = set(int(x) for x in pos[o[b]:o[b + 1]])
+        d["M"] = {int(x): "R" for x in pos[o[5]:o[6]]}
+        return d
+
+    sc = REF.seqComparer(reference=ref, maxNs=700, snpCeiling=20, excludePositions=set(np.flatnonzero(excluded).tolist()))
+    for i in range(n):
+        sc.persist(as_dict(i), "s%d" % i)
+    valid = [i for i in range(n) if not invalid[i]]
+    rnd = random.Random(11)
+    out = {"n_valid": len(valid), "consensus": [], "msa": [], "unk_sites": []}
+
+    # consensus: whole families, random mixtures, a member listed twice; thresholds incl. float-rounding traps
+    groups = [valid[:10], valid[10:22], rnd.sample(valid, 7), rnd.sample(valid, 15), valid[:3] + valid[:3],
+              [valid[4]], valid[30:40] + [valid[30]]]
+    for g in groups:
+        for cutoff in (0.0, 0.3, 0.5, 0.7, 0.8, 1.0):
+            cons = sc.consensus([sc.seqProfile["s%d" % i] for i in g], cutoff)
+            out["consensus"].append({"members": g, "cutoff": cutoff,
+                                     "got": {k: sorted(int(x) for x in v) for k, v in cons.items()}})
+
+    # _msa: selections with and without invalid members; each of the three uncertain_base_type settings
+    sels = [valid[:12], valid[12:20] + [i for i in range(n) if invalid[i]][:2], rnd.sample(valid, 9), valid[40:43],
+            [valid[7]], rnd.sample(range(n), 25)]
+    keep = ("variant_positions", "invalid_guids", "guid2msa_seq", "guid2allN", "guid2allM", "guid2allN_or_M",
+            "guid2alignN", "guid2alignM", "guid2alignN_or_M", "guid2expected_p2", "guid2expected_p1")
+    for sel, unk in zip(sels, ("N", "M", "N_or_M", "N", "M", "N_or_M")):
+        guids = ["s%d" % i for i in sel]
+        res = sc.multi_sequence_alignment(guids, output="dict", sample_size=len(valid), uncertain_base_type=unk)
+        clean = {}
+        for k in keep:
+            v = res[k]
+            if isinstance(v, dict):
+                clean[k] = {kk: (None if vv is None else (float(vv) if isinstance(vv, (float, np.floating)) else
+                                 (int(vv) if isinstance(vv, (int, np.integer)) else vv))) for kk, vv in v.items()}
+            else:
+                clean[k] = [int(x) if isinstance(x, (int, np.integer)) else x for x in v]
+        out["msa"].append({"select": guids, "unk": unk, "sample_size": len(valid), "got": clean})
+
+    # estimate_expected_unk / estimate_expected_unk_sites over everything stored
+    site_sets = [sorted(rnd.sample(range(L), 200)), out["msa"][0]["got"]["variant_positions"], []]
+    for sites in site_sets:
+        for unk in ("N", "M", "N_or_M"):
+            got = sc.estimate_expected_unk_sites(sample_size=len(valid), sites=set(sites), unk_type=unk)
+            out["unk_sites"].append({"sites": sites, "unk": unk, "sample_size": len(valid),
+                                     "got": None if got is None else float(got)})
+    out["unk"] = {unk: float(sc.estimate_expected_unk(sample_size=len(valid), unk_type=unk)) for unk in ("N", "M", "N_or_M")}
+    out["unk_too_few"] = sc.estimate_expected_unk(sample_size=len(valid) + 1, unk_type="N")
+    dump("cluster.json", out)
+
+
 if __name__ == "__main__":
+    if "--cluster" in sys.argv:
+        make_cluster()
+        sys.exit(0)
     make_msa()
     make_kat()
     make_compress()
     make_random_pairs()
     make_collection()
     make_consensus()
+    make_cluster()

@@ -476,3 +476,219 @@ def test_config1_incremental_through_the_class_full_genome():
             sub = coll.subset(np.arange(i + 1))
             assert got == c_oracle.one_vs_all(sub.pos, sub.off, sub.invalid, i, 20)
     assert sc.summarise_stored_items()["server|scstat|nSeqs"] == coll.n
+
+
+# ---------------------------------------------------------------------------------------------
+# (c) cluster statistics on the device: consensus vote, MSA sites / alignment / N-M tallies (csrc/fn3_cluster.cuh)
+# ---------------------------------------------------------------------------------------------
+def _cluster_class():
+    """the collection of collection.json persisted into the drop-in class under the guids cluster.json uses"""
+    from findneighbour3_b200 import synth
+    c = golden("collection.json")
+    pos, off, invalid = np.array(c["pos"], np.int32), np.array(c["off"], np.int64), np.array(c["invalid"], np.uint8)
+    L = c["genome_length"]
+    ref = synth.reference_string(synth.random_reference(L, c["ref_seed"]))
+    coll = synth.Collection(L, pos, off, invalid, np.zeros(invalid.size, np.int32))
+    excluded = set(np.flatnonzero(synth.synthetic_mask(L, 2000, 12, seed=3)).tolist())
+    sc = _sc(ref, 700, 20, excluded)
+    for i in range(coll.n):
+        sc.persist(coll.as_dict(i), "s%d" % i)
+    return sc, coll
+
+
+def test_cluster_golden_through_class():
+    """consensus(), multi_sequence_alignment(), estimate_expected_unk[_sites]() of the class — whose votes, variant
+    sites, aligned characters and tallies come from the device — against the unmodified reference's outputs."""
+    g = golden("cluster.json")
+    sc, coll = _cluster_class()
+    launches0 = sc.engine.launch_count()
+    for case in g["consensus"]:
+        objs = [sc.seqProfile["s%d" % i] for i in case["members"]]
+        got = sc.consensus(objs, case["cutoff"])
+        assert {k: sorted(v) for k, v in got.items()} == case["got"], (case["members"], case["cutoff"])
+        stored = sc._consensus_of_stored(["s%d" % i for i in case["members"]], case["cutoff"])
+        assert stored == got
+    for case in g["msa"]:
+        want = case["got"]
+        res = sc.multi_sequence_alignment(case["select"], output="dict", sample_size=case["sample_size"],
+                                          uncertain_base_type=case["unk"])
+        assert list(res["variant_positions"]) == want["variant_positions"]
+        assert sorted(res["invalid_guids"]) == sorted(want["invalid_guids"])
+        for key in ("guid2msa_seq", "guid2allN", "guid2allM", "guid2allN_or_M", "guid2alignN", "guid2alignM",
+                    "guid2alignN_or_M", "guid2expected_p1", "guid2expected_p2"):
+            assert res[key] == want[key], (case["select"][:3], key)
+        for s, text in res["guid2msa_seq"].items():
+            assert res["guid2sequence"][s] == list(text)
+    for case in g["unk_sites"]:
+        got = sc.estimate_expected_unk_sites(sample_size=case["sample_size"], sites=set(case["sites"]), unk_type=case["unk"])
+        assert got == case["got"]
+    for unk, want in g["unk"].items():
+        assert sc.estimate_expected_unk(sample_size=g["n_valid"], unk_type=unk) == want
+    assert sc.estimate_expected_unk(sample_size=g["n_valid"] + 1, unk_type="N") is None
+    assert sc.engine.launch_count() > launches0          # the statistics above were computed by kernels
+
+
+@pytest.mark.parametrize("shape", ["high_nm", "tiny_genome", "tb_like"])
+def test_cluster_engine_vs_port(shape):
+    """fn3_consensus / fn3_consensus_lists / fn3_msa_sites / fn3_msa_align through the C-ABI on seeded synthetic
+    collections against the Python-set restatement (oracle/cluster_port.py, pinned by cluster.json)."""
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.engine import Engine
+    from oracle import cluster_port as cp
+    if shape == "high_nm":
+        coll = _synthetic(5, 14, 120000, 31, k1=800, s=5.0, n_blocks=30, n_mean=9000, m_mean=400, rule="any",
+                          max_ns=40000, p_invalid=0.05)
+    elif shape == "tiny_genome":
+        coll = _synthetic(5, 8, 31, 9, k1=3, s=1.0, n_blocks=2, n_mean=4, m_mean=2, rule="any", p_invalid=0.1)
+    else:
+        coll = _synthetic(6, 20, 600000, 8, k1=500, s=3.0, n_blocks=20, n_mean=4000, m_mean=3, rule="any")
+    L = coll.genome_length
+    ref = synth.reference_string(synth.random_reference(L, 77))
+    dicts = [coll.as_dict(i) for i in range(coll.n)]
+    valid = [i for i in range(coll.n) if not coll.invalid[i]]
+    eng = Engine(L, 0)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    rng = np.random.default_rng(5)
+    groups = [valid[:9], list(rng.choice(valid, size=min(len(valid), 17), replace=False)), valid[:2] + valid[:2], [valid[-1]],
+              valid]
+    # --- consensus: stored rows and shipped lists give the reference's vote
+    for gsel in groups:
+        for min_votes in sorted({1, 2, max(1, len(gsel) // 2), max(1, (4 * len(gsel) + 4) // 5), len(gsel), len(gsel) + 1}):
+            want = {}
+            for item in ("A", "C", "G", "T", "N"):
+                votes = {}
+                for i in gsel:
+                    for p in dicts[i][item]:
+                        votes[p] = votes.get(p, 0) + 1
+                want[item] = sorted(p for p, v in votes.items() if v >= min_votes)
+            pos, off = eng.consensus(gsel, min_votes)
+            got = {k: pos[off[b]:off[b + 1]].tolist() for b, k in enumerate("ACGTN")}
+            assert got == want, (shape, len(gsel), min_votes)
+            sub = coll.subset(gsel)
+            pos2, off2 = eng.consensus_lists(sub.pos, sub.off, min_votes)
+            assert np.array_equal(pos, pos2) and np.array_equal(off, off2)
+        for cutoff in (0.5, 0.7, 0.8):                       # the float threshold of the reference, via the port
+            from findneighbour3_b200.seqComparer import seqComparer
+            want = cp.consensus([dicts[i] for i in gsel], cutoff)
+            pos, off = eng.consensus(gsel, seqComparer._min_votes(len(gsel), cutoff))
+            assert seqComparer._consensus_dict(pos, off) == want
+    # an invalid row votes for nothing
+    bad = [i for i in range(coll.n) if coll.invalid[i]]
+    if bad:
+        pos, off = eng.consensus(valid[:4] + bad[:1], 1)
+        pos2, off2 = eng.consensus(valid[:4], 1)
+        assert np.array_equal(pos, pos2) and np.array_equal(off, off2)
+        with pytest.raises(ValueError):
+            eng.msa_sites(valid[:3] + bad[:1])
+    # --- MSA: sites, aligned characters, tallies
+    for gsel in groups:
+        samples = [dicts[i] for i in gsel]
+        ordered = cp.variant_positions(ref, samples)
+        sites = eng.msa_sites(gsel)
+        assert sites.tolist() == ordered, (shape, len(gsel))
+        codes, counts = eng.msa_align(gsel, sites, want_codes=True)
+        lut = np.frombuffer(b"?ACGTNM", dtype=np.uint8)
+        ref_at = np.frombuffer(ref.encode(), dtype=np.uint8)[sites]
+        chars = np.where(codes == 0, ref_at[None, :], lut[codes])
+        for j, i in enumerate(gsel):
+            aligned = cp.aligned_string(ref, dicts[i], ordered)
+            assert chars[j].tobytes().decode() == aligned
+            assert tuple(int(x) for x in counts[j]) == cp.tallies(dicts[i], aligned)
+        # counts-only form at foreign sites (estimate_expected_unk_sites) and with no sites at all
+        foreign = np.unique(rng.integers(0, L, size=min(L, 300))).astype(np.int32)
+        for at in (foreign, np.empty(0, np.int32)):
+            none, c2 = eng.msa_align(gsel, at, want_codes=False)
+            assert none is None
+            sset = set(at.tolist())
+            for j, i in enumerate(gsel):
+                assert tuple(int(x) for x in c2[j]) == (len(dicts[i]["N"]), len(dicts[i]["M"]),
+                                                        cp.unknowns_at_sites(dicts[i], sset, "N"),
+                                                        cp.unknowns_at_sites(dicts[i], sset, "M"))
+    # removed rows are refused
+    eng.remove(valid[0])
+    with pytest.raises(KeyError):
+        eng.msa_sites(valid[:3])
+    with pytest.raises(KeyError):
+        eng.consensus(valid[:3], 1)
+    with pytest.raises(ValueError):
+        eng.msa_align(valid[1:3], np.array([5, 5], np.int32))        # sites must be strictly increasing
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# (d) BASELINE.json configurations at their full sizes
+# ---------------------------------------------------------------------------------------------
+def test_config2_full_size_50k_sampled_queries_vs_oracle():
+    """BASELINE.json configs[1] at full size: 50 000 TB-shaped samples (L = 4 411 532) resident on one GPU.
+    Sampled stored queries, fresh inserts (fn3_insert_query) and un-stored queries (fn3_lists_vs_all) are checked
+    bit-exact against the C oracle over ALL 50 000 candidates; the all-vs-all edges of sampled block rows at 12 SNV
+    must equal the one-vs-all results (checksum over the whole matrix is compared between two tile widths in bench)."""
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.engine import Engine
+    from oracle import c_oracle
+    mask = synth.synthetic_mask(synth.TB_LENGTH, synth.TB_EXCLUDED, synth.TB_EXCLUDED_RUNS)
+    coll = synth.make_collection(1000, 50, seed=2, excluded=mask)
+    assert coll.n == 50000 and coll.genome_length == 4411532
+    eng = Engine(coll.genome_length, 0)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    rng = np.random.default_rng(3)
+    nthreads = max(1, min(16, os.cpu_count() or 1))
+    queries = [int(q) for q in rng.choice(coll.n, size=12, replace=False)]
+    for ceiling in (20, 12, 250):
+        for q in queries[: (12 if ceiling == 20 else 4)]:
+            want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, q, ceiling, nthreads=nthreads)
+            assert hits_to_dict(eng.one_vs_all(q, ceiling)) == want, (ceiling, q)
+            if not coll.invalid[q]:
+                p, o, inv = coll.lists(q)
+                got = hits_to_dict(eng.lists_vs_all(p, o, inv, ceiling))
+                assert got.pop(q)[0] == 0                    # the un-stored copy of q finds q itself at distance 0
+                assert got == want
+    # block rows of the all-vs-all matrix: rows r with r % 4000 == 7
+    edges = eng.all_vs_all(12, upper_only=False, stride=4000, phase=7)
+    got = {}
+    for e in edges:
+        got.setdefault(int(e["row1"]), {})[int(e["row2"])] = (int(e["dist"]), int(e["n1"]), int(e["n2"]), int(e["nboth"]))
+    for r in range(7, coll.n, 4000):
+        want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, r, 12, nthreads=nthreads)
+        assert got.get(r, {}) == want, r
+    # streaming inserts on top of the full store (configs[4] flow on one GPU): relatives of stored samples
+    fresh = synth.make_collection(3, 4, seed=9001, excluded=mask)
+    both = synth.concat(coll, fresh)                         # the oracle sees the first row+1 samples of this
+    for i in range(fresh.n):
+        p, o, inv = fresh.lists(i)
+        row, hits = eng.insert_query(p, o, inv, 20)
+        assert row == coll.n + i
+        want = c_oracle.one_vs_all(both.pos, both.off[: 6 * (row + 1) + 1], both.invalid[: row + 1], row, 20,
+                                   nthreads=nthreads)
+        assert hits_to_dict(hits) == want
+    eng.close()
+
+
+@pytest.mark.parametrize("organism", ["salm", "ngon"])
+def test_config4_high_n_and_mixed_collections(organism):
+    """BASELINE.json configs[3]: S. enterica-shaped (L = 4 857 432, SALM-exclude-sized mask) and N. gonorrhoeae-shaped
+    (L = 2 232 025, no mask) collections with tens of thousands of N and hundreds of IUPAC positions per sample, some
+    invalid through maxNs = 130 000: mixture-aware mcompare counts (dist, n1, n2, nboth) vs the C oracle."""
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.engine import Engine
+    from oracle import c_oracle
+    if organism == "salm":
+        L = 4857432
+        mask = synth.synthetic_mask(L, 51897, 58, seed=44)
+        coll = synth.make_collection(40, 25, genome_length=L, seed=4, k1=5000, s=5.0, n_blocks=60, n_mean=30000, m_mean=300,
+                                     rule="any", n_lognormal_sigma=0.9, max_ns=130000, excluded=mask, ref_seed=4)
+    else:
+        L = 2232025
+        coll = synth.make_collection(40, 25, genome_length=L, seed=5, k1=3000, s=5.0, n_blocks=50, n_mean=20000, m_mean=1000,
+                                     rule="any", n_lognormal_sigma=0.9, max_ns=130000, p_invalid=0.02, ref_seed=5)
+    eng = Engine(L, 0)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    rng = np.random.default_rng(8)
+    nthreads = max(1, min(16, os.cpu_count() or 1))
+    n_checked = 0
+    for q in rng.choice(coll.n, size=10, replace=False):
+        want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, int(q), 20, nthreads=nthreads)
+        assert hits_to_dict(eng.one_vs_all(int(q), 20)) == want
+        n_checked += len(want)
+    assert n_checked > 0
+    eng.close()

@@ -110,3 +110,58 @@ def test_collection_port_sampled():
         got = port.neighbours(store, {}, q, 20)
         want = {r[0]: tuple(r[1:]) for r in g["neighbours"]["20"][str(q)]}
         assert got == want
+
+
+# ---------------------------------------------------------------------------------------------
+# consensus vote / MSA set algebra (oracle/cluster_port.py) against the reference's outputs (cluster.json)
+# ---------------------------------------------------------------------------------------------
+def _cluster_store():
+    from findneighbour3_b200 import synth
+    c = golden("collection.json")
+    pos, off, invalid = np.array(c["pos"], np.int32), np.array(c["off"], np.int64), np.array(c["invalid"], np.uint8)
+    ref = synth.reference_string(synth.random_reference(c["genome_length"], c["ref_seed"]))
+    store = {}
+    for i in range(invalid.size):
+        if invalid[i]:
+            store["s%d" % i] = {"invalid": 1}
+            continue
+        o = off[6 * i: 6 * i + 7]
+        d = {"invalid": 0}
+        for b, k in enumerate("ACGTN"):
+            d[k] = set(int(x) for x in pos[o[b]:o[b + 1]])
+        d["M"] = {int(x): "R" for x in pos[o[5]:o[6]]}
+        store["s%d" % i] = d
+    return ref, store
+
+
+def test_cluster_port_matches_reference():
+    from oracle import cluster_port as cp
+    g = golden("cluster.json")
+    ref, store = _cluster_store()
+    valid = [k for k, v in store.items() if v["invalid"] == 0]
+    assert len(valid) == g["n_valid"]
+    for case in g["consensus"]:
+        got = cp.consensus([store["s%d" % i] for i in case["members"]], case["cutoff"])
+        assert {k: sorted(v) for k, v in got.items()} == case["got"], (case["members"], case["cutoff"])
+    for case in g["msa"]:
+        want = case["got"]
+        sel = [s for s in case["select"] if store[s]["invalid"] == 0]
+        assert sorted(s for s in case["select"] if store[s]["invalid"] == 1) == sorted(want["invalid_guids"])
+        samples = [store[s] for s in sel]
+        ordered = cp.variant_positions(ref, samples)
+        assert ordered == want["variant_positions"]
+        for s in sel:
+            aligned = cp.aligned_string(ref, store[s], ordered)
+            assert aligned == want["guid2msa_seq"][s]
+            assert cp.tallies(store[s], aligned) == (want["guid2allN"][s], want["guid2allM"][s], want["guid2alignN"][s],
+                                                     want["guid2alignM"][s])
+        e2 = cp.expected_unknowns([store[s] for s in valid if s not in want["invalid_guids"]], set(ordered), case["unk"])
+        for s in sel:
+            if len(ordered) == 0:
+                assert want["guid2expected_p2"][s] is None
+            else:
+                assert want["guid2expected_p2"][s] == e2 / len(ordered)
+    for case in g["unk_sites"]:
+        assert cp.expected_unknowns([store[s] for s in valid], set(case["sites"]), case["unk"]) == case["got"]
+    for unk, want in g["unk"].items():
+        assert cp.expected_unknowns([store[s] for s in valid], None, unk) == want

@@ -54,19 +54,18 @@ __global__ void __launch_bounds__(256) k_votes_lists(const int32_t* __restrict__
 }
 
 // ---- ordered selection of positions from the vote planes ------------------------------------------------
-// MODE 0 (_msa step 3): ONE list — p is a variant site iff the samples show more than one base there, the reference
-//   base included whenever some sample has no A/C/G/T call at p (:916-931): two different called bases, or one
-//   called base carried by fewer than all `thr` samples.
+// MODE 0 (_msa steps 1-3): ONE list — p is a variant site iff the samples show more than one base there, the reference
+//   base (refcode[p]: 0..3 = A,C,G,T) included whenever some of the `thr` samples has no A/C/G/T call at p (:916-931).
 // MODE 1 (consensus, :492-500): FIVE lists — p enters list b iff cnt[b][p] >= thr (thr >= 1).
 template <int MODE> struct SelLists { static const int N = MODE == 0 ? 1 : 5; };
 
 template <int MODE>
-__device__ __forceinline__ void sel_flags(const uint32_t* __restrict__ cnt, long long Lpad, long long p0, uint32_t thr,
-                                          uint32_t flags[SelLists<MODE>::N]) {
+__device__ __forceinline__ void sel_flags(const uint32_t* __restrict__ cnt, const uint8_t* __restrict__ refcode, long long Lpad,
+                                          long long p0, uint32_t thr, uint32_t flags[SelLists<MODE>::N]) {
     if (MODE == 0) {
-        uint32_t nb[FN3_SEL_PER_THREAD], tot[FN3_SEL_PER_THREAD];
+        uint32_t seen[FN3_SEL_PER_THREAD], tot[FN3_SEL_PER_THREAD];
 #pragma unroll
-        for (int i = 0; i < FN3_SEL_PER_THREAD; ++i) { nb[i] = 0u; tot[i] = 0u; }
+        for (int i = 0; i < FN3_SEL_PER_THREAD; ++i) { seen[i] = 0u; tot[i] = 0u; }
 #pragma unroll
         for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -74,12 +73,17 @@ __device__ __forceinline__ void sel_flags(const uint32_t* __restrict__ cnt, long
                 const uint4 v = __ldcg(reinterpret_cast<const uint4*>(cnt + (long long)b * Lpad + p0) + k);
                 const uint32_t c[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { nb[4 * k + j] += c[j] != 0u; tot[4 * k + j] += c[j]; }
+                for (int j = 0; j < 4; ++j) { seen[4 * k + j] |= (uint32_t)(c[j] != 0u) << b; tot[4 * k + j] += c[j]; }
             }
+        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(refcode + p0));
+        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
         uint32_t f = 0u;
 #pragma unroll
-        for (int i = 0; i < FN3_SEL_PER_THREAD; ++i)
-            if (nb[i] >= 2u || (nb[i] == 1u && tot[i] < thr)) f |= 1u << i;
+        for (int i = 0; i < FN3_SEL_PER_THREAD; ++i) {
+            uint32_t m = seen[i];
+            if (tot[i] < thr) m |= 1u << ((rw[i >> 2] >> (8 * (i & 3))) & 3u);     // somebody shows the reference base
+            if (__popc(m) > 1) f |= 1u << i;
+        }
         flags[0] = f;
     } else {
 #pragma unroll
@@ -99,12 +103,12 @@ __device__ __forceinline__ void sel_flags(const uint32_t* __restrict__ cnt, long
 
 // counts[cta * NL + l] = number of selected positions of list l in the CTA's 4096 positions
 template <int MODE>
-__global__ void __launch_bounds__(FN3_SEL_THREADS) k_sel_count(const uint32_t* __restrict__ cnt, long long Lpad, uint32_t thr,
-                                                                uint32_t* __restrict__ counts) {
+__global__ void __launch_bounds__(FN3_SEL_THREADS) k_sel_count(const uint32_t* __restrict__ cnt, const uint8_t* __restrict__ refcode,
+                                                                long long Lpad, uint32_t thr, uint32_t* __restrict__ counts) {
     const int NL = SelLists<MODE>::N;
     const long long p0 = ((long long)blockIdx.x * FN3_SEL_THREADS + threadIdx.x) * FN3_SEL_PER_THREAD;
     uint32_t flags[NL];
-    sel_flags<MODE>(cnt, Lpad, p0, thr, flags);
+    sel_flags<MODE>(cnt, refcode, Lpad, p0, thr, flags);
     __shared__ uint32_t sm[NL][FN3_SEL_THREADS / 32];
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -136,14 +140,14 @@ __global__ void __launch_bounds__(1024) k_sel_scan(uint32_t* __restrict__ counts
 
 // out: the NL lists one behind the other (list l starts at totals[0] + .. + totals[l-1]), each in position order
 template <int MODE>
-__global__ void __launch_bounds__(FN3_SEL_THREADS) k_sel_write(const uint32_t* __restrict__ cnt, long long Lpad, uint32_t thr,
-                                                                const uint32_t* __restrict__ counts,
+__global__ void __launch_bounds__(FN3_SEL_THREADS) k_sel_write(const uint32_t* __restrict__ cnt, const uint8_t* __restrict__ refcode,
+                                                                long long Lpad, uint32_t thr, const uint32_t* __restrict__ counts,
                                                                 const uint32_t* __restrict__ totals, int32_t* __restrict__ out) {
     const int NL = SelLists<MODE>::N;
     __shared__ uint32_t ws[33];
     const long long p0 = ((long long)blockIdx.x * FN3_SEL_THREADS + threadIdx.x) * FN3_SEL_PER_THREAD;
     uint32_t flags[NL];
-    sel_flags<MODE>(cnt, Lpad, p0, thr, flags);
+    sel_flags<MODE>(cnt, refcode, Lpad, p0, thr, flags);
     uint32_t start = 0;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {

@@ -125,6 +125,7 @@ struct fn3_engine {
 
     // cluster statistics (fn3_consensus*, fn3_msa_*): vote planes + selection scratch, allocated on first use
     uint32_t* d_votes = nullptr; long long vLpad = 0; int sel_ctas = 0;
+    uint8_t* d_refcode = nullptr;          // reference base codes 0..3, unmasked (fn3_set_reference; needed by fn3_msa_sites)
     uint32_t* d_sel_counts = nullptr; uint32_t* d_sel_totals = nullptr; uint32_t* h_sel_totals = nullptr;   // pinned
     int32_t* d_sel_out = nullptr; size_t sel_out_cap = 0;
     int32_t* d_sites = nullptr; size_t sites_cap = 0;
@@ -348,7 +349,7 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->h_ctotals) cudaFreeHost(e->h_ctotals);
     if (e->h_cpos) cudaFreeHost(e->h_cpos);
     if (e->h_mchars) cudaFreeHost(e->h_mchars);
-    cudaFree(e->d_votes); cudaFree(e->d_sel_counts); cudaFree(e->d_sel_totals); cudaFree(e->d_sel_out);
+    cudaFree(e->d_refcode); cudaFree(e->d_votes); cudaFree(e->d_sel_counts); cudaFree(e->d_sel_totals); cudaFree(e->d_sel_out);
     cudaFree(e->d_sites); cudaFree(e->d_codes); cudaFree(e->d_acounts); cudaFree(e->d_lpos); cudaFree(e->d_loff);
     if (e->h_sel_totals) cudaFreeHost(e->h_sel_totals);
     if (e->in_stream) cudaStreamDestroy(e->in_stream);
@@ -1246,12 +1247,13 @@ extern "C" int fn3_set_reference(fn3_engine* e, const char* reference, const int
     const long long per_cta = (long long)FN3_CMP_THREADS * FN3_CMP_PER_THREAD;
     e->cmp_ctas = (int)((e->L + per_cta - 1) / per_cta);
     e->Lpad = (long long)e->cmp_ctas * per_cta;
-    std::vector<uint8_t> rm((size_t)e->Lpad, 0);
+    std::vector<uint8_t> rm((size_t)e->Lpad, 0), rcode((size_t)e->Lpad, 0);
     for (long long i = 0; i < e->L; ++i) {
         const char c = reference[i];
         if (c != 'A' && c != 'C' && c != 'G' && c != 'T')
             return set_err(e, FN3_EARG, "fn3_set_reference: reference holds a character other than ACGT at %lld", i);
         rm[(size_t)i] = (uint8_t)c;
+        rcode[(size_t)i] = (uint8_t)(c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3);
     }
     for (int64_t i = 0; i < n_excluded; ++i) {
         if (excluded[i] < 0 || excluded[i] >= e->L) return set_err(e, FN3_EARG, "fn3_set_reference: excluded position out of range");
@@ -1270,6 +1272,12 @@ extern "C" int fn3_set_reference(fn3_engine* e, const char* reference, const int
         memset(e->h_seq, 0, (size_t)e->Lpad);
     }
     CU(e, cudaMemcpy(e->d_refmask, rm.data(), (size_t)e->Lpad, cudaMemcpyHostToDevice));
+    {
+        // the unmasked base codes travel under query_mu: fn3_msa_sites reads them on q_stream
+        std::lock_guard<std::mutex> q(e->query_mu);
+        if (!e->d_refcode) CU(e, cudaMalloc(&e->d_refcode, (size_t)e->Lpad));
+        CU(e, cudaMemcpy(e->d_refcode, rcode.data(), (size_t)e->Lpad, cudaMemcpyHostToDevice));
+    }
     CU(e, cudaMemsetAsync(e->d_seq, 0, (size_t)e->Lpad, e->in_stream));
     CU(e, cudaStreamSynchronize(e->in_stream));
     return FN3_OK;
@@ -1379,7 +1387,7 @@ template <int MODE>
 static int run_select(fn3_engine* e, uint32_t thr, long long len[5], long long* total) {
     const int NL = SelLists<MODE>::N;
     cudaStream_t st = e->q_stream;
-    k_sel_count<MODE><<<e->sel_ctas, FN3_SEL_THREADS, 0, st>>>(e->d_votes, e->vLpad, thr, e->d_sel_counts);
+    k_sel_count<MODE><<<e->sel_ctas, FN3_SEL_THREADS, 0, st>>>(e->d_votes, e->d_refcode, e->vLpad, thr, e->d_sel_counts);
     k_sel_scan<<<1, 1024, 0, st>>>(e->d_sel_counts, e->d_sel_totals, e->sel_ctas, NL);
     e->launches += 2;
     CU(e, cudaGetLastError());
@@ -1391,7 +1399,7 @@ static int run_select(fn3_engine* e, uint32_t thr, long long len[5], long long* 
     int rc;
     if ((rc = ensure_dev(e, &e->d_sel_out, &e->sel_out_cap, (size_t)std::max<long long>(*total, 1)))) return rc;
     if (*total > 0) {
-        k_sel_write<MODE><<<e->sel_ctas, FN3_SEL_THREADS, 0, st>>>(e->d_votes, e->vLpad, thr, e->d_sel_counts, e->d_sel_totals,
+        k_sel_write<MODE><<<e->sel_ctas, FN3_SEL_THREADS, 0, st>>>(e->d_votes, e->d_refcode, e->vLpad, thr, e->d_sel_counts, e->d_sel_totals,
                                                                    e->d_sel_out);
         e->launches += 1;
         CU(e, cudaGetLastError());
@@ -1485,6 +1493,7 @@ extern "C" int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows,
     if (n_rows == 0) return FN3_OK;
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
+    if (!e->d_refcode) return set_err(e, FN3_EARG, "fn3_msa_sites: call fn3_set_reference first (the variant-site rule needs the reference bases)");
     int rc;
     if ((rc = ensure_votes(e))) return rc;
     HdrTable ht;

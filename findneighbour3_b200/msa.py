@@ -102,13 +102,13 @@ def msa(sc, valid_guids, invalid_guids, expected_p1, output, sample_size, uncert
     # steps 1-4 on the device: variant sites of these rows, then every row's character and N/M tallies there
     with sc._lock:
         rows = [sc._row_of[g] for g in valid_guids]
-    sites = sc.engine.msa_sites(rows)
-    codes, counts = sc.engine.msa_align(rows, sites, want_codes=True)
+    eng = sc._engine_with_reference()
+    sites = eng.msa_sites(rows)
+    codes, counts = eng.msa_align(rows, sites, want_codes=True)
     ordered = sites.tolist()
     chars = _CODE_CHARS[codes]
     if len(ordered):
-        ref_at = np.frombuffer(ref.encode('ascii'), dtype=np.uint8)[sites] if len(ordered) * 64 > len(ref) else \
-            np.frombuffer(''.join(ref[p] for p in ordered).encode('ascii'), dtype=np.uint8)
+        ref_at = np.frombuffer(''.join(ref[p] for p in ordered).encode('ascii'), dtype=np.uint8)
         chars = np.where(codes == 0, ref_at[None, :], chars)
     guid2seq, guid2msa = {}, {}
     for i, g in enumerate(valid_guids):

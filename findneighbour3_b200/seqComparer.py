@@ -123,6 +123,15 @@ class seqComparer():
             self._engine = Engine(len(self.reference), self._device)     # raises if libfn3.so / a GPU is missing
         return self._engine
 
+    def _engine_with_reference(self):
+        """the engine, with the reference sequence and the mask uploaded (device compress and the MSA site rule need them)"""
+        eng = self.engine
+        with self._lock:
+            if not self._ref_uploaded:
+                eng.set_reference(self.reference, self.excluded)
+                self._ref_uploaded = True
+        return eng
+
     def _lists_of(self, obj):
         """any stored representation -> (pos, off, invalid) for the engine; raises like _computeComparator (:309-335)."""
         if not isinstance(obj, dict):
@@ -258,10 +267,7 @@ class seqComparer():
                 len(sequence), len(self.reference)))
         if len(self.reference) == 0:
             raise TypeError("reference cannot be of zero length")
-        eng = self.engine
-        if not self._ref_uploaded:
-            eng.set_reference(self.reference, self.excluded)
-            self._ref_uploaded = True
+        eng = self._engine_with_reference()
         # one byte per character; anything outside latin-1 becomes '?', which (like every non-ACGTN-
         # character) is a mixed base; its real character is read back from `sequence` below (:296-298)
         pos, off, _ = eng.compress(sequence.encode('latin-1', 'replace'))

@@ -548,6 +548,11 @@ def test_cluster_engine_vs_port(shape):
     valid = [i for i in range(coll.n) if not coll.invalid[i]]
     eng = Engine(L, 0)
     eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    with pytest.raises(ValueError):
+        eng.msa_sites(valid[:3])                             # the site rule needs the reference bases
+    # NB a reference other than the one the collection was generated against: stored bases may EQUAL the reference
+    # base here, which the reference's rule (a set of bases per position, :916-931) treats as one base
+    eng.set_reference(ref)
     rng = np.random.default_rng(5)
     groups = [valid[:9], list(rng.choice(valid, size=min(len(valid), 17), replace=False)), valid[:2] + valid[:2], [valid[-1]],
               valid]

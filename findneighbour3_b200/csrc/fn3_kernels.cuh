@@ -18,6 +18,14 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint32_t* p) {
     return r;
 }
 
+__device__ __forceinline__ uint4 ld_head_v4(const uint4* p) {
+    // volatile: ptxas must not sink these loads below the early-exit tests of the fingerprint loop (it does so with
+    // plain loads, turning one memory round trip into up to four dependent ones); they are served by L2
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t lowmask(uint32_t k) { return (1u << k) - 1u; }    // k in 0..31
 
 // block-wide exclusive scan of one value per thread (blockDim.x multiple of 32, <= 1024);
@@ -279,6 +287,101 @@ __device__ __forceinline__ void rank3(const QView& qv, uint32_t x, uint32_t& rD,
 
 struct Tally { int S1, qdefV, qdefU, nNc, nNU, nNM; bool dead; };
 
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+#ifndef FN3_STREAM_V1
+// One warp streams one candidate row against the query (all 32 lanes must call).
+// The V words (A,C,G,T positions) and the run words (N, M) are handled by separate loops: V words 256 per warp step
+// with two 128-bit loads per lane and the next step in flight; run words one per lane, the first 32 of them requested
+// before the V loop starts.  (Handling both kinds in one loop made every lane of a mixed step walk through the V code
+// AND the run code for each of its 8 words: ~970 warp instructions per 500-word row; profiles/README.md.)
+template <bool COUNT>
+__device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __restrict__ d, uint32_t e0, uint32_t e1,
+                                            uint32_t e2, uint32_t e3, uint32_t e4, uint32_t e5, int k, int pos_bits,
+                                            uint32_t pmask, int lane, unsigned long long& touched) {
+    Tally t; t.S1 = 0; t.qdefV = 0; t.qdefU = 0; t.nNc = 0; t.nNU = 0; t.nNM = 0; t.dead = false;
+    uint32_t r0 = 0u;
+    if (e3 + (uint32_t)lane < e5) { r0 = ld_stream_u32(d + e3 + lane); if (COUNT) touched += 4; }
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+    if ((uint32_t)lane * 4u < e3) { c0 = ld_stream_v4(d + lane * 4); if (COUNT) touched += 16; }
+    if ((uint32_t)lane * 4u + 128u < e3) { c1 = ld_stream_v4(d + lane * 4 + 128); if (COUNT) touched += 16; }
+    for (uint32_t base = 0; base < e3; base += 256) {
+        const uint32_t idx = base + lane * 4;
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        if (idx + 256u < e3) { n0 = ld_stream_v4(d + idx + 256); if (COUNT) touched += 16; }
+        if (idx + 384u < e3) { n1 = ld_stream_v4(d + idx + 384); if (COUNT) touched += 16; }
+        const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        int mism = 0;
+        if (base + 256u <= e3) {                                // warp-uniform: a full step
+#ifdef FN3_STREAM_V3
+            // all 8 bitmap tests first (independent LDS, no branches); the rare words whose block the query touches
+            // are then looked up one by one in a loop that most warps skip
+            uint32_t tm = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tm |= touched_bit(qv, w[j]) << j;
+            mism = 8 - __popc(tm);
+            while (tm) {
+                const int j = __ffs(tm) - 1;
+                tm &= tm - 1u;
+                const uint32_t lo4 = (j & 2) ? ((j & 1) ? c0.w : c0.z) : ((j & 1) ? c0.y : c0.x);
+                const uint32_t hi4 = (j & 2) ? ((j & 1) ? c1.w : c1.z) : ((j & 1) ? c1.y : c1.x);
+                const uint32_t wj = (j & 4) ? hi4 : lo4;
+                const uint32_t r = look_touched(qv, wj, idx + (j & 3) + ((j >> 2) << 7), e0, e1, e2);
+                mism += r & 1u;
+                t.qdefV += r >> 1;
+            }
+#else
+            // (a branch-free variant — all 8 bitmap tests first, touched words afterwards — measured slower on
+            //  B200: more registers, spills at 64 regs/thread, 57 vs 42 us at ceiling 250; profiles/README.md)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (touched_bit(qv, w[j])) {
+                    const uint32_t r = look_touched(qv, w[j], idx + (j & 3) + ((j >> 2) << 7), e0, e1, e2);
+                    mism += r & 1u;
+                    t.qdefV += r >> 1;
+                } else mism += 1;
+            }
+#endif
+        } else {                                                // the last, partial step
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t ii = idx + (j & 3) + ((j >> 2) << 7);
+                if (ii < e3) {
+                    if (touched_bit(qv, w[j])) {
+                        const uint32_t r = look_touched(qv, w[j], ii, e0, e1, e2);
+                        mism += r & 1u;
+                        t.qdefV += r >> 1;
+                    } else mism += 1;
+                }
+            }
+        }
+        t.S1 += __reduce_add_sync(0xffffffffu, mism);
+        if (t.S1 > k) { t.dead = true; return t; }
+        c0 = n0; c1 = n1;
+    }
+    // run words: [start, start+len) of N (below e4) or M; what the query holds inside each run comes from two rank lookups
+    for (uint32_t rb = e3; rb < e5; rb += 32) {                 // warp-uniform
+        const uint32_t ii = rb + lane;
+        uint32_t x = r0;
+        if (rb != e3 && ii < e5) { x = ld_stream_u32(d + ii); if (COUNT) touched += 4; }
+        if (ii < e5) {
+            const uint32_t s = x & pmask;
+            const uint32_t len = (pos_bits >= 32) ? 1u : ((x >> pos_bits) + 1u);
+            const bool isN = ii < e4;
+            uint32_t aD, aU, aM, bD, bU, bM;
+            rank3(qv, s, aD, aU, aM, isN);
+            rank3(qv, s + len, bD, bU, bM, isN);
+            t.qdefU += (int)(bD - aD);
+            if (isN) { t.nNc += (int)len; t.nNU += (int)(bU - aU); t.nNM += (int)(bM - aM); }
+        }
+    }
+    return t;
+}
+#else
 // One warp streams one candidate row against the query (all 32 lanes must call).
 template <bool COUNT>
 __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __restrict__ d, uint32_t e0, uint32_t e1,
@@ -337,6 +440,8 @@ __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __r
     }
     return t;
 }
+
+#endif
 
 // STREAM variant pre-pass on the row's 16-bit fingerprints (stored behind its list words): a V position whose coarse
 // block the query does not touch at all is a certain mismatch, so once their count exceeds the ceiling the pair is
@@ -411,38 +516,6 @@ __device__ __forceinline__ void signal_done(const CompareParams& p) {
     }
 }
 
-// phase A loads of one work unit (32 candidates: a tile of the full scan, or 32 strided entries of an explicit list):
-// header and fingerprints of this lane's candidate, requested together — ONE memory round trip.
-struct HeadRegs { uint4 h0, h1, f[4]; long long row; bool have; };
-
-__device__ __forceinline__ HeadRegs load_head(const CompareParams& p, const QuerySlot& qs, long long u, long long units,
-                                              int lane, int tshift) {
-    HeadRegs r;
-    r.h0 = make_uint4(0, 0, 0, 0); r.h1 = r.h0; r.row = -1; r.have = false;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) r.f[j] = r.h0;
-    const unsigned char* tile = nullptr;
-    int tl = lane;
-    if (p.rows) {
-        const long long ci = u + (long long)lane * units;
-        if (ci < p.n_list) { r.row = p.rows[ci]; tile = tile_of(p.hdr, r.row, tl); }
-    } else {
-        const long long chunk = u >> tshift, lt = u & ((1ll << tshift) - 1);
-        r.row = (chunk << p.hdr.shift) + fn3_row_of(lt, lane, p.hdr.sb_shift);
-        tile = p.hdr.chunk[chunk] + lt * FN3_TILE_BYTES;
-        if (r.row >= p.n_rows) r.row = -1;
-    }
-    if (r.row >= 0 && r.row != qs.exclude && r.row > qs.skip_le) {
-        const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
-        const uint4* fp = reinterpret_cast<const uint4*>(tile + FN3_TILE_FP_OFF + tl * 16);
-        r.h0 = __ldg(hp); r.h1 = __ldg(hp + 1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r.f[j] = __ldg(fp + j * 32);
-        r.have = true;
-    }
-    return r;
-}
-
 #ifndef FN3_Q_MINB
 #define FN3_Q_MINB 2
 #endif
@@ -466,9 +539,9 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     // FILTER: work unit = 32 candidates.  Consecutive units (tiles hold consecutively inserted rows, i.e. relatives)
     // go to different CTAs, so that the few surviving candidates of a family are streamed on different SMs.
     // (Requesting the first unit's heads before the query build was measured: no gain, +58 registers.)
-    const long long units = !FILTER ? 0 : p.rows ? (p.n_list + 31) >> 5
-                            : ((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
-    const long long u0 = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const uint32_t units = !FILTER ? 0u : p.rows ? (uint32_t)((p.n_list + 31) >> 5)
+                           : (uint32_t)(((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5));
+    const uint32_t u0 = (uint32_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     uint32_t nVq, nUq, nMq;
     QView qv;
     if (QMODE == 1) {
@@ -497,15 +570,38 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
 
     if (FILTER) {
         // upper triangle: superblocks that hold only rows <= skip_le cannot contain a candidate
-        const long long ufirst = (p.rows || qs.skip_le < 0) ? 0
-                                 : ((qs.skip_le + 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
-        for (long long u = ufirst + u0; u < units; u += nwarps) {
+        const int exclude = (int)qs.exclude, skip_le = (int)qs.skip_le;
+        const uint32_t ufirst = (p.rows || skip_le < 0) ? 0u
+                                : (((uint32_t)skip_le + 1u) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
+        const uint32_t ustep = gridDim.x * (FN3_Q_THREADS / 32);
+        const int sb_shift = p.hdr.sb_shift, gs = sb_shift - 5;
+        const uint32_t gmask = (1u << gs) - 1u, tmask = (1u << tshift) - 1u, n_rows32 = (uint32_t)p.n_rows;
+        for (uint32_t u = ufirst + u0; u < units; u += ustep) {
             // ---- phase A: one thread per candidate, on the candidate's head ---------------------
-            const HeadRegs hr = load_head(p, qs, u, units, lane, tshift);
-            const uint4 h0 = hr.h0, h1 = hr.h1;
-            const long long row = hr.row;
+            // Unit = 32 candidates (a head tile of the full scan, or 32 strided entries of an explicit list).  All row /
+            // unit arithmetic is 32-bit (a store holds at most FN3_MAX_HDR_CHUNKS << 20 = 2^25 rows): with 64-bit units
+            // and runtime shifts the address computation cost as many instructions as the fingerprint tests it feeds.
+            const unsigned char* tile = nullptr;
+            int tl = lane, row = -1;
+            if (p.rows) {
+                const long long ci = (long long)u + (long long)lane * units;
+                if (ci < p.n_list) { row = (int)p.rows[ci]; tile = tile_of(p.hdr, row, tl); }
+            } else {
+                // u = global tile index: chunk = u >> tshift, tile inside the chunk = the low bits; row as in fn3_row_of
+                const uint32_t r = ((u >> gs) << sb_shift) + ((uint32_t)lane << gs) + (u & gmask);
+                tile = p.hdr.chunk[u >> tshift] + (size_t)(u & tmask) * FN3_TILE_BYTES;
+                row = r < n_rows32 ? (int)r : -1;
+            }
+            uint4 h0, h1;                                  // header of this lane's candidate (read by phase B if it passes)
             bool pass = false;
-            if (hr.have) {
+            if (row >= 0 && row != exclude && row > skip_le) {
+                // header and fingerprints requested together, coalesced across the warp: ONE memory round trip
+                const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
+                const uint4* fp = reinterpret_cast<const uint4*>(tile + FN3_TILE_FP_OFF + tl * 16);
+                h0 = ld_head_v4(hp); h1 = ld_head_v4(hp + 1);
+                uint4 f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = ld_head_v4(fp + j * 32);
                 if (COUNT) touched += 96;
                 if ((h0.x | h0.y) != 0u) {                 // data pointer 0: invalid or removed candidate
                     // a fingerprint whose coarse block the query does not touch is a certain mismatch; padded
@@ -514,7 +610,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (S > k) break;                                          // already proven: not a neighbour
-                        const uint32_t w[4] = {hr.f[j].x, hr.f[j].y, hr.f[j].z, hr.f[j].w};
+                        const uint32_t w[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             S += 2 - (int)qv.cmap[w[i] & 0xffffu] - (int)qv.cmap[w[i] >> 16];
@@ -532,7 +628,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
                 const uint32_t e0 = __shfl_sync(0xffffffffu, h0.z, src), e1 = __shfl_sync(0xffffffffu, h0.w, src);
                 const uint32_t e2 = __shfl_sync(0xffffffffu, h1.x, src), e3 = __shfl_sync(0xffffffffu, h1.y, src);
                 const uint32_t e4 = __shfl_sync(0xffffffffu, h1.z, src), e5 = __shfl_sync(0xffffffffu, h1.w, src);
-                const long long crow = __shfl_sync(0xffffffffu, row, src);
+                const long long crow = (long long)__shfl_sync(0xffffffffu, row, src);
                 const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)dhi << 32) | dlo);
                 const Tally t = stream_row<COUNT>(qv, d, e0, e1, e2, e3, e4, e5, k, pos_bits, pmask, lane, touched);
                 emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, crow, lane);

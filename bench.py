@@ -589,6 +589,37 @@ def main():
                   "GBps_host_to_lists": coll.genome_length / t_c / 1e9,
                   "note": "fn3_compress through ctypes: 4.4 MB sequence host->device, 3 kernels, lists device->host"}
 
+    # ---- leg 5 (extra): cluster statistics on the device: consensus vote over 250 stored rows,
+    # MSA variant sites + alignment + N/M tallies of a 50-sample cluster -------------------------------------------
+    cluster = None
+    if args.allvsall and world == 1:
+        fam = np.flatnonzero((coll.family == coll.family[0]) & (coll.invalid == 0))[:50]
+        rows250 = np.flatnonzero(coll.invalid == 0)[:250]
+        sites = eng.msa_sites(fam)
+        eng.msa_align(fam, sites)
+        eng.consensus(rows250, 200)
+        reps = 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sites = eng.msa_sites(fam)
+        t_sites = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.msa_align(fam, sites)
+        t_align = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cpos, coff = eng.consensus(rows250, 200)
+        t_cons = (time.perf_counter() - t0) / reps
+        L = int(coll.genome_length)
+        cluster = {"msa_rows": int(fam.size), "msa_sites": int(sites.size), "msa_sites_ms": 1e3 * t_sites,
+                   "msa_align_ms": 1e3 * t_align, "consensus_rows": int(rows250.size), "consensus_min_votes": 200,
+                   "consensus_positions": int(cpos.size), "consensus_ms": 1e3 * t_cons,
+                   "plane_bytes_msa": 4 * 4 * L * 3, "plane_bytes_consensus": 5 * 4 * L * 3,
+                   "msa_sites_GBps": 4 * 4 * L * 3 / t_sites / 1e9, "consensus_GBps": 5 * 4 * L * 3 / t_cons / 1e9,
+                   "note": "fn3_msa_sites / fn3_msa_align / fn3_consensus through ctypes, wall clock per call incl. host "
+                           "synchronisations; plane bytes = vote planes cleared once and scanned twice (count, write)"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -613,6 +644,8 @@ def main():
         line["all_vs_all"] = ava
     if ingest is not None:
         line["ingest"] = ingest
+    if cluster is not None:
+        line["cluster_statistics"] = cluster
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_python_port(coll, fresh[W:], ceiling, args.cpu_seconds)

@@ -84,6 +84,7 @@ struct fn3_engine {
     int qstate_slots = 0;
     int nw = 0, ncw = 0, n_blk = 0, fshift = 5;   // bitmap words, coarse map words, 32-position blocks, fingerprint shift
     uint16_t fp_pad = 0;                   // coarse id carried by padded fingerprints (its map byte is always 1)
+    uint16_t fp_dead = 0;                  // coarse id carried by the heads of invalid / removed rows (its map byte is always 0)
     int max_smem = 0;                      // opt-in dynamic shared memory per CTA
     int stage_limit = 0;                   // = max_smem, or 0 to force the global-memory query variants
     int q_static_smem = 0;                 // static shared memory of k_query
@@ -275,7 +276,9 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
     e->sb_shift = std::min(13, e->hdr_shift);                   // 8192-row superblocks: neighbours in insertion
                                                                 // order sit 256 tiles apart
     e->debug_stop = (int)env_ll("FN3_DEBUG_STOP", 0);
-    e->n_slots = (int)env_ll("FN3_SLOTS", 128);               // queries per all-vs-all tile (one k_query launch)
+    // queries per all-vs-all tile (one k_query launch): one per SM, so that with two CTAs per query every resident CTA
+    // slot of the GPU (2 per SM) is filled by one wave — 148 on a B200 (128 left 40 of the 296 slots idle)
+    e->n_slots = (int)env_ll("FN3_SLOTS", e->sm_count);
     if (e->n_slots < 1) e->n_slots = 1;
     if (e->n_slots > FN3_MAX_SLOTS) e->n_slots = FN3_MAX_SLOTS;
 
@@ -289,8 +292,9 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         e->fshift = 5;
         while (((genome_length - 1) >> e->fshift) + 2 > 16383) ++e->fshift;  // <= 16 K coarse blocks: a 16 KB byte map
         const long long n_coarse = ((genome_length - 1) >> e->fshift) + 2;   // + the block rank(L) may fall in
-        e->ncw = (int)((((n_coarse + 1) + 3) / 4 + 7) & ~7ll);               // bytes / 4, + 1 for the pad id
-        e->fp_pad = (uint16_t)(e->ncw * 4 - 1);
+        e->ncw = (int)((((n_coarse + 2) + 3) / 4 + 7) & ~7ll);               // bytes / 4, + 2 for the pad and dead ids
+        e->fp_pad = (uint16_t)(e->ncw * 4 - 1);                              // byte always 1: never a mismatch
+        e->fp_dead = (uint16_t)(e->ncw * 4 - 2);                             // byte always 0: always a mismatch
         QueryState& q = e->qstate;
         memset(&q, 0, sizeof q);
         q.ent_stride = (long long)e->n_blk + 1;
@@ -498,7 +502,11 @@ static void finish_row(const fn3_engine* e, uint32_t* dst, size_t words, size_t 
 // header + 16-bit fingerprints (position >> fshift) of the row's first V words (fn3_types.h)
 static void fill_head(const fn3_engine* e, RowHead& hd, const RowHdr& h, const uint32_t* words) {
     hd.hdr = h;
-    const uint32_t nv = h.data ? std::min<uint32_t>(h.end[3], FN3_HEAD_FP) : 0u;
+    if (!h.data) {                         // invalid (or removed) row: 32 certain mismatches, the filter never lets it pass
+        for (uint32_t i = 0; i < FN3_HEAD_FP; ++i) hd.fp[i] = e->fp_dead;
+        return;
+    }
+    const uint32_t nv = std::min<uint32_t>(h.end[3], FN3_HEAD_FP);
     for (uint32_t i = 0; i < nv; ++i) hd.fp[i] = (uint16_t)(words[i] >> e->fshift);
     for (uint32_t i = nv; i < FN3_HEAD_FP; ++i) hd.fp[i] = e->fp_pad;
 }
@@ -671,9 +679,15 @@ extern "C" int fn3_remove(fn3_engine* e, int64_t row) {
     if (e->h_flags[(size_t)row] & 2) return FN3_OK;          // removing twice is silent (seqComparer.py:131-134)
     CU(e, cudaSetDevice(e->device));
     RowHdr dead; memset(&dead, 0, sizeof dead);
-    // queries may be in flight on q_stream: a header flips atomically per 32-byte sector store at worst
-    // between two comparisons, which is the reference's own semantics for remove-during-mcompare.
-    CU(e, cudaMemcpyAsync(hdr_addr(e, row), &dead, sizeof dead, cudaMemcpyHostToDevice, e->copy_stream));
+    RowHead dead_head;
+    fill_head(e, dead_head, dead, nullptr);           // zero header + fingerprints that always mismatch
+    // queries may be in flight on q_stream: they see the old head, or the dead fingerprints (filtered out), or old
+    // fingerprints with the zero header (skipped when the header is read) — the reference's own semantics for
+    // remove-during-mcompare.
+    HdrTable ht; fill_hdr_table(e, ht);
+    k_put_head<<<1, 1, 0, e->copy_stream>>>(dead_head, row, ht);
+    e->launches += 1;
+    CU(e, cudaGetLastError());
     CU(e, cudaStreamSynchronize(e->copy_stream));
     if (e->h_flags[(size_t)row] & 1) e->n_invalid--;
     e->h_flags[(size_t)row] |= 2;
@@ -1061,7 +1075,7 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     QueryJob job; job.ceiling = ceiling;
     fill_hdr_table(e, job.ht);
     job.n_rows = row;                                // candidates: every earlier row
-    if (!invalid) { job.commit_head = &head; job.commit_row = row; }   // an invalid row's head stays zero
+    job.commit_head = &head; job.commit_row = row;   // an invalid row's head too: zero header, fingerprints that always mismatch
     set_slot0(e, h, row, row);
     e->slot_blocks[0] = nblk;
     return run_one_vs_all(e, job, nullptr, 0, out, cap, n_out);

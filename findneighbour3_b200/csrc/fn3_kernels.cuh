@@ -96,6 +96,9 @@ __device__ __forceinline__ void put_head(const HdrTable& ht, long long row, cons
     hdr[0] = src[0];
 }
 
+// one head by value (fn3_remove: zero header + fingerprints that always mismatch)
+__global__ void k_put_head(const RowHead h, long long row, const HdrTable ht) { put_head(ht, row, h); }
+
 // bulk append: heads arrive in row order, go to their tiles
 __global__ void k_scatter_heads(const RowHead* __restrict__ src, long long first_row, long long n, const HdrTable ht) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -576,62 +579,117 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
         const uint32_t ustep = gridDim.x * (FN3_Q_THREADS / 32);
         const int sb_shift = p.hdr.sb_shift, gs = sb_shift - 5;
         const uint32_t gmask = (1u << gs) - 1u, tmask = (1u << tshift) - 1u, n_rows32 = (uint32_t)p.n_rows;
-        for (uint32_t u = ufirst + u0; u < units; u += ustep) {
-            // ---- phase A: one thread per candidate, on the candidate's head ---------------------
-            // Unit = 32 candidates (a head tile of the full scan, or 32 strided entries of an explicit list).  All row /
-            // unit arithmetic is 32-bit (a store holds at most FN3_MAX_HDR_CHUNKS << 20 = 2^25 rows): with 64-bit units
-            // and runtime shifts the address computation cost as many instructions as the fingerprint tests it feeds.
-            const unsigned char* tile = nullptr;
-            int tl = lane, row = -1;
+        // Unit = 32 candidates (a head tile of the full scan, or 32 strided entries of an explicit list).  All row / unit
+        // arithmetic is 32-bit (a store holds at most FN3_MAX_HDR_CHUNKS << 20 = 2^25 rows): with 64-bit units and runtime
+        // shifts the address computation cost as many instructions as the fingerprint tests it feeds.
+        // -> this lane's candidate in unit uu: its tile, its lane in the tile, its row (-1: none, self, or below the triangle)
+        auto locate = [&](uint32_t uu, const unsigned char*& tile, int& tl) -> int {
+            int row = -1;
+            tl = lane; tile = nullptr;
             if (p.rows) {
-                const long long ci = (long long)u + (long long)lane * units;
+                const long long ci = (long long)uu + (long long)lane * units;
                 if (ci < p.n_list) { row = (int)p.rows[ci]; tile = tile_of(p.hdr, row, tl); }
             } else {
-                // u = global tile index: chunk = u >> tshift, tile inside the chunk = the low bits; row as in fn3_row_of
-                const uint32_t r = ((u >> gs) << sb_shift) + ((uint32_t)lane << gs) + (u & gmask);
-                tile = p.hdr.chunk[u >> tshift] + (size_t)(u & tmask) * FN3_TILE_BYTES;
+                // uu = global tile index: chunk = uu >> tshift, tile inside the chunk = the low bits; row as in fn3_row_of
+                const uint32_t r = ((uu >> gs) << sb_shift) + ((uint32_t)lane << gs) + (uu & gmask);
+                tile = p.hdr.chunk[uu >> tshift] + (size_t)(uu & tmask) * FN3_TILE_BYTES;
                 row = r < n_rows32 ? (int)r : -1;
             }
-            uint4 h0, h1;                                  // header of this lane's candidate (read by phase B if it passes)
-            bool pass = false;
-            if (row >= 0 && row != exclude && row > skip_le) {
-                // header and fingerprints requested together, coalesced across the warp: ONE memory round trip
+            return (row != exclude && row > skip_le) ? row : -1;
+        };
+        // certain mismatches among 8 fingerprints: a fingerprint whose coarse block the query does not touch at all.
+        // Padded fingerprints (rows with fewer than 32 V words) carry an id whose byte is always 1; the heads of invalid
+        // and removed rows carry an id whose byte is always 0, so they never pass and their header is never read.
+        const uint8_t* cm = qv.cmap;
+        auto count8 = [&](const uint4& g) -> int {
+            const uint32_t w[4] = {g.x, g.y, g.z, g.w};
+            int s = 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s -= (int)cm[w[i] & 0xffffu] + (int)cm[w[i] >> 16];
+            return s;
+        };
+        // the groups beyond the eager ones, for the rare candidate that has not been ruled out yet
+        auto rest = [&](int S, const uint4* fp, int from) -> bool {
+            for (int j = from; j < 4 && S <= k; ++j) { S += count8(ld_head_v4(fp + j * 32)); if (COUNT) touched += 16; }
+            return S <= k;
+        };
+        // ---- phase B: one warp per surviving candidate ---------------------------------------------------
+        // Two candidate slots per thread, A and B (the single-candidate path passes B = nothing).  The survivor's header
+        // either sits in its lane's registers already (single-candidate path: HAVE_HDR, nine shuffles) or is fetched now.
+        auto survivors = [&](bool passA, int rowA, bool passB, int rowB, const bool HAVE_HDR, const uint4& ha0, const uint4& ha1) {
+            uint32_t aliveA = __ballot_sync(0xffffffffu, passA), aliveB = __ballot_sync(0xffffffffu, passB);
+            if (p.debug_stop == 2) { aliveA = 0u; aliveB = 0u; }
+            while (aliveA | aliveB) {
+                const bool fromA = aliveA != 0u;
+                const uint32_t m = fromA ? aliveA : aliveB;
+                const int src = __ffs(m) - 1;
+                if (fromA) aliveA &= aliveA - 1u; else aliveB &= aliveB - 1u;
+                const int crow = __shfl_sync(0xffffffffu, fromA ? rowA : rowB, src);
+                uint4 h0, h1;
+                if (HAVE_HDR) {
+                    h0.x = __shfl_sync(0xffffffffu, ha0.x, src); h0.y = __shfl_sync(0xffffffffu, ha0.y, src);
+                    h0.z = __shfl_sync(0xffffffffu, ha0.z, src); h0.w = __shfl_sync(0xffffffffu, ha0.w, src);
+                    h1.x = __shfl_sync(0xffffffffu, ha1.x, src); h1.y = __shfl_sync(0xffffffffu, ha1.y, src);
+                    h1.z = __shfl_sync(0xffffffffu, ha1.z, src); h1.w = __shfl_sync(0xffffffffu, ha1.w, src);
+                } else {
+                    int tl;
+                    const unsigned char* tile = tile_of(p.hdr, crow, tl);
+                    const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
+                    h0 = __ldcg(hp); h1 = __ldcg(hp + 1);                  // all lanes, one address: a broadcast
+                    if (COUNT && lane == 0) touched += 32;
+                }
+                if ((h0.x | h0.y) == 0u) continue;                          // removed while its fingerprints were still live
+                const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
+                const Tally t = stream_row<COUNT>(qv, d, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, k, pos_bits, pmask, lane, touched);
+                emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, (long long)crow, lane);
+            }
+        };
+        // ---- phase A: one thread per candidate, on the fingerprints of the candidate's head ---------------
+        // k + 1 certain mismatches need ceil((k + 1) / 8) groups of 8 fingerprints: those are requested together (one memory
+        // round trip; volatile loads, see ld_head_v4), the others only by a candidate that is still alive after them.
+        const int geager = min(4, (k >> 3) + 1);
+        if (geager <= 2) {
+            // low ceilings (all-vs-all at 12 SNV): two groups suffice, so every thread takes TWO candidates per iteration —
+            // twice the loads in flight per warp, 32 bytes per candidate instead of 96
+            for (uint32_t u = ufirst + u0; u < units; u += 2u * ustep) {
+                const unsigned char *tA, *tB = nullptr;
+                int tlA, tlB = 0;
+                const int rowA = locate(u, tA, tlA);
+                const int rowB = (u + ustep < units) ? locate(u + ustep, tB, tlB) : -1;
+                const uint4* fA = reinterpret_cast<const uint4*>(tA + FN3_TILE_FP_OFF + tlA * 16);
+                const uint4* fB = reinterpret_cast<const uint4*>(tB + FN3_TILE_FP_OFF + tlB * 16);
+                uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+                if (rowA >= 0) { a0 = ld_head_v4(fA); a1 = ld_head_v4(fA + 32); if (COUNT) touched += 32; }
+                if (rowB >= 0) { b0 = ld_head_v4(fB); b1 = ld_head_v4(fB + 32); if (COUNT) touched += 32; }
+                bool passA = false, passB = false;
+                if (rowA >= 0) passA = rest(count8(a0) + count8(a1), fA, 2);
+                if (rowB >= 0) passB = rest(count8(b0) + count8(b1), fB, 2);
+                survivors(passA, rowA, passB, rowB, false, a0, a0);
+            }
+        } else {
+            // one-vs-all at ceiling 20: one candidate per thread; its header travels with the fingerprints (one round trip,
+            // and a surviving candidate is streamed without a second, dependent fetch)
+            for (uint32_t u = ufirst + u0; u < units; u += ustep) {
+                const unsigned char* tile;
+                int tl;
+                const int row = locate(u, tile, tl);
                 const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
                 const uint4* fp = reinterpret_cast<const uint4*>(tile + FN3_TILE_FP_OFF + tl * 16);
-                h0 = ld_head_v4(hp); h1 = ld_head_v4(hp + 1);
-                uint4 f[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) f[j] = ld_head_v4(fp + j * 32);
-                if (COUNT) touched += 96;
-                if ((h0.x | h0.y) != 0u) {                 // data pointer 0: invalid or removed candidate
-                    // a fingerprint whose coarse block the query does not touch is a certain mismatch; padded
-                    // fingerprints (rows with fewer than 32 V words) carry an id whose byte is always 1
-                    int S = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (S > k) break;                                          // already proven: not a neighbour
-                        const uint32_t w[4] = {f[j].x, f[j].y, f[j].z, f[j].w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            S += 2 - (int)qv.cmap[w[i] & 0xffffu] - (int)qv.cmap[w[i] >> 16];
+                uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
+                bool pass = false;
+                if (row >= 0) {
+                    h0 = ld_head_v4(hp); h1 = ld_head_v4(hp + 1);
+                    const uint4 f0 = ld_head_v4(fp), f1 = ld_head_v4(fp + 32), f2 = ld_head_v4(fp + 64);
+                    if (geager == 4) {
+                        const uint4 f3 = ld_head_v4(fp + 96);
+                        if (COUNT) touched += 96;
+                        pass = count8(f0) + count8(f1) + count8(f2) + count8(f3) <= k;
+                    } else {
+                        if (COUNT) touched += 80;
+                        pass = rest(count8(f0) + count8(f1) + count8(f2), fp, 3);
                     }
-                    pass = S <= k;
                 }
-            }
-            // ---- phase B: one warp per surviving candidate ----------------------------------------
-            uint32_t alive = __ballot_sync(0xffffffffu, pass);
-            if (p.debug_stop == 2) alive = 0u;
-            while (alive) {
-                const int src = __ffs(alive) - 1;
-                alive &= alive - 1u;
-                const uint32_t dlo = __shfl_sync(0xffffffffu, h0.x, src), dhi = __shfl_sync(0xffffffffu, h0.y, src);
-                const uint32_t e0 = __shfl_sync(0xffffffffu, h0.z, src), e1 = __shfl_sync(0xffffffffu, h0.w, src);
-                const uint32_t e2 = __shfl_sync(0xffffffffu, h1.x, src), e3 = __shfl_sync(0xffffffffu, h1.y, src);
-                const uint32_t e4 = __shfl_sync(0xffffffffu, h1.z, src), e5 = __shfl_sync(0xffffffffu, h1.w, src);
-                const long long crow = (long long)__shfl_sync(0xffffffffu, row, src);
-                const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)dhi << 32) | dlo);
-                const Tally t = stream_row<COUNT>(qv, d, e0, e1, e2, e3, e4, e5, k, pos_bits, pmask, lane, touched);
-                emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, crow, lane);
+                survivors(pass, row, false, -1, true, h0, h1);
             }
         }
     } else {

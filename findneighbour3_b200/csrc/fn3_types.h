@@ -85,7 +85,7 @@ struct __align__(32) EdgeRec {     // device-side survivor record (== fn3_edge)
     int dist, n1, n2, nboth;
 };
 
-#define FN3_MAX_SLOTS 128
+#define FN3_MAX_SLOTS 256
 
 struct CompareParams {
     HdrTable hdr;

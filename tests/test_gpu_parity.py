@@ -421,10 +421,14 @@ def test_msa_golden():
         assert len(df.index) == len(want["guid2msa_seq"])
 
 
-def test_all_vs_all_batched_tiles_vs_one_vs_all():
+@pytest.mark.parametrize("slots", [8, None])
+def test_all_vs_all_batched_tiles_vs_one_vs_all(slots, monkeypatch):
     """all-vs-all queues many query tiles between host synchronisations and grows its edge buffer on overflow:
-    on a collection with more than FN3_SLOT_RING tiles its edges must equal the union of one-vs-all results."""
+    on a collection with more than FN3_SLOT_RING tiles (8 queries per tile -> 60 tiles) and with the default tile width
+    its edges must equal the union of one-vs-all results."""
     from findneighbour3_b200.engine import Engine
+    if slots:
+        monkeypatch.setenv("FN3_SLOTS", str(slots))
     coll = _synthetic(12, 40, 300000, 71, k1=200, s=2.0, n_blocks=6, n_mean=1500, m_mean=2, rule="any", p_invalid=0.02)
     eng = Engine(coll.genome_length, 0)
     eng.append_bulk(coll.pos, coll.off, coll.invalid)

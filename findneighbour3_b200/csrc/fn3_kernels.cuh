@@ -645,12 +645,12 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
             }
         };
         // ---- phase A: one thread per candidate, on the fingerprints of the candidate's head ---------------
-        // k + 1 certain mismatches need ceil((k + 1) / 8) groups of 8 fingerprints: those are requested together (one memory
-        // round trip; volatile loads, see ld_head_v4), the others only by a candidate that is still alive after them.
-        const int geager = min(4, (k >> 3) + 1);
-        if (geager <= 2) {
-            // low ceilings (all-vs-all at 12 SNV): two groups suffice, so every thread takes TWO candidates per iteration —
-            // twice the loads in flight per warp, 32 bytes per candidate instead of 96
+        // k + 1 certain mismatches need ceil((k + 1) / 8) groups of 8 fingerprints.
+        if (k < 16) {
+            // low ceilings (all-vs-all at 12 SNV): the first two groups settle nearly every candidate, so they alone are
+            // requested up front (one memory round trip; volatile loads, see ld_head_v4) and every thread takes TWO candidates
+            // per iteration — twice the loads in flight per warp, 32 bytes per candidate instead of 96.  The other groups are
+            // read only by a candidate that is still alive, the header only by a survivor.
             for (uint32_t u = ufirst + u0; u < units; u += 2u * ustep) {
                 const unsigned char *tA, *tB = nullptr;
                 int tlA, tlB = 0;
@@ -667,8 +667,8 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
                 survivors(passA, rowA, passB, rowB, false, a0, a0);
             }
         } else {
-            // one-vs-all at ceiling 20: one candidate per thread; its header travels with the fingerprints (one round trip,
-            // and a surviving candidate is streamed without a second, dependent fetch)
+            // one-vs-all at ceiling 20: one candidate per thread; its header and all 32 fingerprints travel together (one
+            // round trip, and a surviving candidate is streamed without a second, dependent fetch)
             for (uint32_t u = ufirst + u0; u < units; u += ustep) {
                 const unsigned char* tile;
                 int tl;
@@ -679,15 +679,11 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
                 bool pass = false;
                 if (row >= 0) {
                     h0 = ld_head_v4(hp); h1 = ld_head_v4(hp + 1);
-                    const uint4 f0 = ld_head_v4(fp), f1 = ld_head_v4(fp + 32), f2 = ld_head_v4(fp + 64);
-                    if (geager == 4) {
-                        const uint4 f3 = ld_head_v4(fp + 96);
-                        if (COUNT) touched += 96;
-                        pass = count8(f0) + count8(f1) + count8(f2) + count8(f3) <= k;
-                    } else {
-                        if (COUNT) touched += 80;
-                        pass = rest(count8(f0) + count8(f1) + count8(f2), fp, 3);
-                    }
+                    const uint4 f0 = ld_head_v4(fp), f1 = ld_head_v4(fp + 32), f2 = ld_head_v4(fp + 64), f3 = ld_head_v4(fp + 96);
+                    if (COUNT) touched += 96;
+                    int S = count8(f0) + count8(f1) + count8(f2);
+                    if (S <= k) S += count8(f3);
+                    pass = S <= k;
                 }
                 survivors(pass, row, false, -1, true, h0, h1);
             }

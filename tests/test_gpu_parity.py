@@ -532,7 +532,7 @@ def test_cluster_golden_through_class():
     assert sc.engine.launch_count() > launches0          # the statistics above were computed by kernels
 
 
-@pytest.mark.parametrize("shape", ["high_nm", "tiny_genome", "tb_like"])
+@pytest.mark.parametrize("shape", ["high_nm", "tiny_genome", "tb_like", "tb_full_genome"])
 def test_cluster_engine_vs_port(shape):
     """fn3_consensus / fn3_consensus_lists / fn3_msa_sites / fn3_msa_align through the C-ABI on seeded synthetic
     collections against the Python-set restatement (oracle/cluster_port.py, pinned by cluster.json)."""
@@ -544,6 +544,9 @@ def test_cluster_engine_vs_port(shape):
                           max_ns=40000, p_invalid=0.05)
     elif shape == "tiny_genome":
         coll = _synthetic(5, 8, 31, 9, k1=3, s=1.0, n_blocks=2, n_mean=4, m_mean=2, rule="any", p_invalid=0.1)
+    elif shape == "tb_full_genome":                          # L = 4 411 532: 88 MB of vote planes, 1 078 selection CTAs
+        coll = synth.make_collection(3, 20, seed=12, m_mean=4, rule="any",
+                                     excluded=synth.synthetic_mask(synth.TB_LENGTH, synth.TB_EXCLUDED, synth.TB_EXCLUDED_RUNS))
     else:
         coll = _synthetic(6, 20, 600000, 8, k1=500, s=3.0, n_blocks=20, n_mean=4000, m_mean=3, rule="any")
     L = coll.genome_length
@@ -700,4 +703,44 @@ def test_config4_high_n_and_mixed_collections(organism):
         assert hits_to_dict(eng.one_vs_all(int(q), 20)) == want
         n_checked += len(want)
     assert n_checked > 0
+    eng.close()
+
+
+def test_low_ceiling_filter_with_removed_and_invalid_rows():
+    """ceilings below 16 take the two-candidates-per-thread filter that reads fingerprints only: removed and invalid
+    rows (heads carrying the reserved always-mismatching id) never come back, in one-vs-all, all-vs-all and after a
+    fused insert of an invalid sample; every result checked against the C oracle on the surviving store."""
+    from findneighbour3_b200.engine import Engine
+    from oracle import c_oracle
+    coll = _synthetic(10, 30, 400000, 91, k1=300, s=2.0, n_blocks=8, n_mean=2000, m_mean=3, rule="any", p_invalid=0.05)
+    eng = Engine(coll.genome_length, 0)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    rng = np.random.default_rng(4)
+    valid = np.flatnonzero(coll.invalid == 0)
+    removed = set(int(r) for r in rng.choice(valid, size=25, replace=False))
+    for r in removed:
+        eng.remove(r)
+    inv2 = coll.invalid.copy()
+    inv2[list(removed)] = 1                                  # for the oracle a removed row is a row without distances
+    row, hits = eng.insert_query(None, None, True, 12)       # an invalid sample: stored, no neighbours, never a candidate
+    assert row == coll.n and len(hits) == 0
+    for ceiling in (0, 5, 12, 15):
+        for q in rng.choice(valid, size=8, replace=False):
+            q = int(q)
+            if q in removed:
+                with pytest.raises(KeyError):
+                    eng.one_vs_all(q, ceiling)
+                continue
+            want = c_oracle.one_vs_all(coll.pos, coll.off, inv2, q, ceiling, nthreads=4)
+            assert hits_to_dict(eng.one_vs_all(q, ceiling)) == want, (ceiling, q)
+    edges = eng.all_vs_all(12, upper_only=False)
+    got = {}
+    for e in edges:
+        got.setdefault(int(e["row1"]), {})[int(e["row2"])] = (int(e["dist"]), int(e["n1"]), int(e["n2"]), int(e["nboth"]))
+    assert not (set(got) & removed) and coll.n not in got
+    for q in range(coll.n):
+        if inv2[q]:
+            assert q not in got
+        else:
+            assert got.get(q, {}) == c_oracle.one_vs_all(coll.pos, coll.off, inv2, q, 12, nthreads=4), q
     eng.close()

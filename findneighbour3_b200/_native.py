@@ -34,11 +34,10 @@ class Stats(C.Structure):
                 ("t_enqueue_ns", C.c_int64), ("t_wait_ns", C.c_int64), ("n_timed", C.c_int64)]
 
 
-_i32p = C.POINTER(C.c_int32)
-_i64p = C.POINTER(C.c_int64)
-_u8p = C.POINTER(C.c_uint8)
-_f32p = C.POINTER(C.c_float)
+# array arguments (int32_t*, int64_t*, uint8_t*, float*) are declared void*: the callers pass plain integer addresses of
+# numpy buffers (engine._ptr) — building a typed ctypes pointer per argument costs ~3.6 us, a third of an insert+query call
 _vp = C.c_void_p
+_i32p = _i64p = _u8p = _f32p = _vp
 
 # name -> (restype, argtypes); mirrors include/fn3.h one to one
 SIGNATURES = {
@@ -49,18 +48,18 @@ SIGNATURES = {
     "fn3_append": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, _i64p]),
     "fn3_append_bulk": (C.c_int, [_vp, C.c_int64, _i32p, _i64p, _u8p, _i64p]),
     "fn3_remove": (C.c_int, [_vp, C.c_int64]),
-    "fn3_stats_get": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "fn3_stats_get": (C.c_int, [_vp, _vp]),
     "fn3_row_get": (C.c_int, [_vp, C.c_int64, _i32p, C.c_int64, _i32p, _i32p, _i64p]),
-    "fn3_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, _i64p, C.c_int64, C.POINTER(Hit), C.c_int64, _i64p]),
-    "fn3_insert_query": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, C.POINTER(Hit), C.c_int64, _i64p]),
+    "fn3_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, _i64p, C.c_int64, _vp, C.c_int64, _i64p]),
+    "fn3_insert_query": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, _vp, C.c_int64, _i64p]),
     "fn3_lists_vs_all": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, C.c_int64,
-                                   C.POINTER(Hit), C.c_int64, _i64p]),
+                                   _vp, C.c_int64, _i64p]),
     "fn3_all_vs_all": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
-                                 C.POINTER(Edge), C.c_int64, _i64p]),
-    "fn3_all_vs_all_fetch": (C.c_int, [_vp, C.POINTER(Edge), C.c_int64, _i64p]),
-    "fn3_pair": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(Hit), _i32p]),
+                                 _vp, C.c_int64, _i64p]),
+    "fn3_all_vs_all_fetch": (C.c_int, [_vp, _vp, C.c_int64, _i64p]),
+    "fn3_pair": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, _vp, _i32p]),
     "fn3_pair_lists": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, _i32p, _i32p, C.c_int32, C.c_int32,
-                                 C.POINTER(Hit), _i32p]),
+                                 _vp, _i32p]),
     "fn3_set_reference": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64]),
     "fn3_compress": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64, _i32p, C.c_char_p, C.c_int64, _i64p]),
     "fn3_consensus": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),

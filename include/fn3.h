@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FN3_ABI_VERSION 1
+#define FN3_ABI_VERSION 2   /* 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align */
 
 /* status codes */
 #define FN3_OK          0

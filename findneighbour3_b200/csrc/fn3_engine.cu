@@ -37,6 +37,7 @@ static_assert(sizeof(EdgeRec) == sizeof(fn3_edge), "EdgeRec/fn3_edge mismatch");
 #include "fn3_kernels.cuh"
 #include "fn3_compress.cuh"
 #include "fn3_cluster.cuh"
+#include "fn3_pickle.h"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -560,8 +561,7 @@ static void fill_hdr_table(fn3_engine* e, HdrTable& t);
 
 // run fn(lo, hi) over [0, n) on up to `max_threads` host threads (bulk append: validation and packing are per-row work)
 template <class F>
-static void parallel_rows(long long n, int max_threads, F fn) {
-    const long long min_rows = 2048;
+static void parallel_rows(long long n, int max_threads, F fn, long long min_rows = 2048) {
     int nt = (int)std::min<long long>(max_threads, (n + min_rows - 1) / min_rows);
     if (nt <= 1) { fn(0ll, n); return; }
     std::vector<std::thread> th;
@@ -1588,6 +1588,41 @@ extern "C" int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows,
     if (want_codes) CU(e, cudaMemcpyAsync(codes, e->d_codes, ncodes, cudaMemcpyDeviceToHost, st));
     CU(e, cudaStreamSynchronize(st));
     e->d2h_bytes += n_rows * 16 + (want_codes ? (long long)ncodes : 0);
+    return FN3_OK;
+}
+
+// ---- wire format: the reference's GridFS pickles -> packed lists (fn3_pickle.h) --------------------------
+
+extern "C" int fn3_unpickle_samples(int64_t n, const uint8_t* blobs, const int64_t* blob_off, int32_t* pos, int64_t pos_cap,
+                                    int64_t* off, uint8_t* status, int64_t* n_pos) {
+    if (n < 0 || !blob_off || !off || !status || !n_pos || (n > 0 && !blobs)) return FN3_EARG;
+    for (int64_t i = 0; i < n; ++i) if (blob_off[i + 1] < blob_off[i]) return FN3_EARG;
+    const int host_threads = (int)std::max<long long>(1, std::min<long long>(env_ll("FN3_HOST_THREADS", 16),
+                                                                             (long long)std::thread::hardware_concurrency()));
+    // pass 1 (host threads): parse every pickle into its own lists; pass 2: lay them out one behind the other
+    std::vector<fn3pickle::Parsed> parsed((size_t)n);
+    parallel_rows(n, host_threads, [&](long long lo, long long hi) {
+        for (long long i = lo; i < hi; ++i)
+            status[i] = (uint8_t)fn3pickle::parse_sample(blobs + blob_off[i], blob_off[i + 1] - blob_off[i], parsed[(size_t)i]);
+    }, 32);
+    int64_t total = 0;
+    off[0] = 0;
+    for (int64_t i = 0; i < n; ++i)
+        for (int l = 0; l < 6; ++l) {
+            if (status[i] == 0) total += (int64_t)parsed[(size_t)i].list[l].size();
+            off[6 * i + l + 1] = total;
+        }
+    *n_pos = total;
+    if (total > pos_cap || (total > 0 && !pos)) return FN3_ECAPACITY;
+    parallel_rows(n, host_threads, [&](long long lo, long long hi) {
+        for (long long i = lo; i < hi; ++i) {
+            if (status[i] != 0) continue;
+            for (int l = 0; l < 6; ++l) {
+                const std::vector<int32_t>& v = parsed[(size_t)i].list[l];
+                if (!v.empty()) memcpy(pos + off[6 * i + l], v.data(), v.size() * sizeof(int32_t));
+            }
+        }
+    }, 256);
     return FN3_OK;
 }
 

@@ -28,18 +28,6 @@ def estimate_expected_proportion(seqs):
     return np.median([s.count('N') for s in seqs]) / len(seqs[0])
 
 
-def _is_valid(sc, obj):
-    """what `_computeComparator` decides (:309-335) without expanding a patch: False = invalid sample"""
-    if not isinstance(obj, dict):
-        raise TypeError("Cannot use object of class {0} as a sequence".format(type(obj)))
-    if obj.get('invalid', 0) == 1:
-        return False
-    keys = set(obj.keys())
-    if keys == sc.compressed_sequence_keys or keys == sc.patch_and_consensus_keys:
-        return True
-    raise KeyError("Was passed a dictionary with keys {0} but cannot handle this".format(obj.keys()))
-
-
 def _sampled_unknowns(sc, sample_size, exclude_guids, sites, unk_type):
     """shared loop of estimate_expected_unk / _unk_sites (:632-689): median, over the first sample_size valid
     guids, of the N and/or M count (sites=None: whole sample, :648-652; else at the given sites, :678-681)."""
@@ -47,7 +35,7 @@ def _sampled_unknowns(sc, sample_size, exclude_guids, sites, unk_type):
     with sc._lock:
         rows = []
         for guid in guids:
-            if _is_valid(sc, sc.seqProfile[guid]):
+            if sc._stored_kind(guid) != 'invalid':            # (no unpickling of lazily loaded samples)
                 rows.append(sc._row_of[guid])
             if len(rows) >= sample_size:
                 break
@@ -81,7 +69,9 @@ def multi_sequence_alignment(sc, guids, output='dict', sample_size=30, expected_
         sample_size = 30
     valid, invalid = [], []
     for guid in guids:
-        if _is_valid(sc, sc.seqProfile[guid]):
+        if guid not in sc.seqProfile:
+            raise KeyError(guid)
+        if sc._stored_kind(guid) != 'invalid':
             valid.append(guid)
         else:
             invalid.append(guid)

@@ -5,6 +5,9 @@ Reference formats (src/seqComparer.py:81-84):
   patch_and_consensus  {'consensus_md5': md5, 'patch': {'+': {b:set}, '-': {b:set}, 'M': dict}}          (:503-548)
 Engine format (include/fn3.h): six sorted int32 lists A,C,G,T,N,M concatenated + 7 offsets.
 """
+import ctypes as C
+import hashlib
+
 import numpy as np
 
 LIST_ORDER = ("A", "C", "G", "T", "N", "M")
@@ -72,5 +75,34 @@ def pack_many(objs):
 def content_key(pos, off, invalid):
     """cheap identity of a sample's expanded content (used to make re-persist of identical content a no-op)."""
     if invalid:
-        return ("invalid",)
-    return (bytes(np.asarray(off, dtype=np.int32).data), bytes(np.asarray(pos, dtype=np.int32).data))
+        return b"invalid"
+    h = hashlib.blake2b(np.ascontiguousarray(off, dtype=np.int32).tobytes(), digest_size=16)
+    h.update(np.ascontiguousarray(pos, dtype=np.int32).tobytes())
+    return h.digest()
+
+
+def unpickle_many(blobs):
+    """The reference's stored samples — pickle.dumps(obj, protocol=2), src/mongoStore.py:344-363 — parsed natively
+    (libfn3 fn3_unpickle_samples, host threads, no Python objects) into the engine's bulk format.
+
+    -> (pos int32[], off int64[6n+1], status uint8[n]): status 0 = valid sample, 1 = {'invalid': 1},
+    2 = not a plain compressed_sequence pickle (its lists are empty; unpickle it with `pickle.loads`)."""
+    from . import _native as N
+    lib = N.load()
+    n = len(blobs)
+    if n == 0:
+        return np.empty(0, dtype=np.int32), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.uint8)
+    boff = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum(np.fromiter((len(b) for b in blobs), dtype=np.int64, count=n), out=boff[1:])
+    joined = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    cap = max(1, int(boff[-1]) // 2)                    # an integer takes at least two bytes of pickle
+    pos = np.empty(cap, dtype=np.int32)
+    off = np.zeros(6 * n + 1, dtype=np.int64)
+    status = np.zeros(n, dtype=np.uint8)
+    n_pos = C.c_int64(0)
+    rc = lib.fn3_unpickle_samples(n, joined.ctypes.data if joined.size else None, boff.ctypes.data, pos.ctypes.data, cap,
+                                  off.ctypes.data, status.ctypes.data if n else None, C.byref(n_pos))
+    if rc != N.FN3_OK:
+        raise RuntimeError("fn3_unpickle_samples failed (%d)" % rc)
+    return pos[: n_pos.value], off, status

@@ -19,6 +19,7 @@ persist() time instead of at the first comparison.
 import hashlib
 import json
 import math
+import pickle
 import threading
 import uuid
 from collections import Counter
@@ -32,15 +33,29 @@ from .engine import Engine
 _BASES5 = ("A", "C", "T", "G", "N")
 
 
+class _LazyPickle:
+    """a sample still in its stored form (the reference's GridFS pickle); becomes a dict on first access"""
+    __slots__ = ("blob", "invalid")
+
+    def __init__(self, blob, invalid):
+        self.blob = blob
+        self.invalid = invalid
+
+
 class _Profile(MutableMapping):
-    """`seqProfile`: guid -> sample dict.  Assignments and deletions keep the device store in step."""
+    """`seqProfile`: guid -> sample dict.  Assignments and deletions keep the device store in step.
+    Samples loaded by persist_pickles() stay pickled until somebody asks for their dict."""
 
     def __init__(self, owner):
         self._owner = owner
         self._d = {}
 
     def __getitem__(self, k):
-        return self._d[k]
+        v = self._d[k]
+        if type(v) is _LazyPickle:
+            v = pickle.loads(v.blob)
+            self._d[k] = v
+        return v
 
     def __setitem__(self, k, v):
         self._owner._store_put(k, v)
@@ -149,6 +164,8 @@ class seqComparer():
         pos, off, invalid = self._lists_of(obj)
         key = packing.content_key(pos, off, invalid)
         with self._lock:
+            if guid in self._row_of and self._key_of.get(guid) is None:       # loaded by persist_pickles: key not computed yet
+                self._key_of[guid] = packing.content_key(*self._lists_of(self.seqProfile[guid]))
             if guid in self._row_of and self._key_of.get(guid) == key:
                 self.seqProfile._d[guid] = obj   # same expanded content (e.g. re-encoded as a patch): host-only change
                 return
@@ -195,6 +212,53 @@ class seqComparer():
             self._key_of[g] = packing.content_key(p, f, bad)
             self.seqProfile._d[g] = o
 
+    def persist_pickles(self, blobs, guids):
+        """Start-up reload straight from the stored form (findNeighbour3-server.py:358-362 reads GridFS pickles written by
+        mongoStore.py:344-363, `pickle.dumps(obj, protocol=2)`): the pickles are parsed natively into the packed lists
+        (fn3_unpickle_samples, host threads) and appended in one bulk copy — no dict of Python sets is built per
+        sample; `seqProfile[guid]` unpickles a sample the first time it is asked for.  Pickles that are not plain
+        compressed sequences (patch form) take the ordinary route."""
+        blobs, guids = list(blobs), list(guids)
+        n = len(blobs)
+        pos, off, status = packing.unpickle_many(blobs)
+        objs = [None] * n
+        other = np.flatnonzero(status == 2)
+        invalid = (status == 1).astype(np.uint8)
+        if other.size:
+            lens = np.diff(off).reshape(n, 6)
+            pieces, at = [], 0
+            for i in other:
+                i = int(i)
+                objs[i] = pickle.loads(blobs[i])
+                p, f, bad = self._lists_of(objs[i])
+                pieces.append(pos[at:off[6 * i]])
+                pieces.append(p)
+                at = off[6 * i]
+                lens[i] = np.diff(f)
+                invalid[i] = 1 if bad else 0
+            pieces.append(pos[at:])
+            pos = np.concatenate(pieces)
+            off = np.concatenate([[0], np.cumsum(lens.ravel())]).astype(np.int64)
+        with self._lock:
+            for g in guids:
+                if g in self._row_of:
+                    self._drop_row(g)
+            first = self.engine.append_bulk(pos, off, invalid)
+            for i, g in enumerate(guids):
+                self._row_of[g] = first + i
+                self._guid_of[first + i] = g
+                self._key_of[g] = None                   # computed if the guid is ever persisted again
+                self.seqProfile._d[g] = objs[i] if objs[i] is not None else _LazyPickle(blobs[i], bool(invalid[i]))
+
+    def _stored_kind(self, guid):
+        """'invalid' | 'compressed' | 'patch' for a stored guid, without unpickling a lazily loaded sample"""
+        v = self.seqProfile._d[guid]
+        if type(v) is _LazyPickle:
+            return 'invalid' if v.invalid else 'compressed'
+        if 'invalid' in v and v['invalid'] == 1:
+            return 'invalid'
+        return 'patch' if set(v.keys()) == self.patch_and_consensus_keys else 'compressed'
+
     # ------------------------------------------------------------------------------------------
     # reference API: store
     # ------------------------------------------------------------------------------------------
@@ -238,11 +302,11 @@ class seqComparer():
         """counts stored sequences by kind (:199-219)."""
         out = {'server|scstat|nSeqs': len(self.seqProfile), 'server|scstat|nConsensi': len(self.consensi),
                'server|scstat|nInvalid': 0, 'server|scstat|nCompressed': 0, 'server|scstat|nRecompressed': 0}
-        for guid in self.seqProfile.keys():
-            obj = self.seqProfile[guid]
-            if 'invalid' in obj and obj['invalid'] == 1:
+        for guid in list(self.seqProfile.keys()):
+            kind = self._stored_kind(guid)               # (an invalid sample also counts as "compressed", :213-217)
+            if kind == 'invalid':
                 out['server|scstat|nInvalid'] += 1
-            if set(obj.keys()) == self.patch_and_consensus_keys:
+            if kind == 'patch':
                 out['server|scstat|nRecompressed'] += 1
             else:
                 out['server|scstat|nCompressed'] += 1
@@ -498,8 +562,7 @@ class seqComparer():
         (fn3_consensus).  Same quirks: a guid listed twice votes twice, samples currently held in patch
         form do not vote, the threshold uses len(guids)."""
         with self._lock:
-            rows = [self._row_of[g] for g in guids
-                    if set(self.seqProfile._d[g].keys()) == self.compressed_sequence_keys]
+            rows = [self._row_of[g] for g in guids if self._stored_kind(g) == 'compressed']
         if len(rows) == 0:
             return {'A': set(), 'C': set(), 'T': set(), 'G': set(), 'N': set()}
         pos, off = self.engine.consensus(np.asarray(rows, dtype=np.int64), self._min_votes(len(guids), cutoff_proportion))

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FN3_ABI_VERSION 2   /* 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align */
+#define FN3_ABI_VERSION 2   /* 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align, fn3_unpickle_samples */
 
 /* status codes */
 #define FN3_OK          0
@@ -222,6 +222,18 @@ int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t* s
  * last two are then the plain intersections |N_i n sites|, |M_i n sites| of :678-681). */
 int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows, const int32_t* sites, int64_t n_sites,
                   uint8_t* codes, int32_t* counts);
+
+/* ---- wire format: the reference's stored samples --------------------- */
+
+/* findNeighbour3 keeps every sample in GridFS as pickle.dumps(obj, protocol=2) of its compressed_sequence dict
+ * (mongoStore.py:344-363) and reloads all of them at start-up (findNeighbour3-server.py:358-362).  Turn n such pickles
+ * (blob i = blobs[blob_off[i] .. blob_off[i+1]) ) straight into the packed form fn3_append_bulk takes, on host threads,
+ * without creating Python objects: pos / off[6n+1] as there; status[i] = 0 parsed, valid sample; 1 parsed,
+ * {'invalid': 1}; 2 not a plain compressed_sequence pickle (patch_and_consensus form, numpy scalars, other opcodes) —
+ * its six lists are left empty and the caller unpickles it itself.  No engine is involved (pure host function).
+ * pos_cap in elements (sum of blob sizes / 2 always suffices); FN3_ECAPACITY with *n_pos = required if too small. */
+int fn3_unpickle_samples(int64_t n, const uint8_t* blobs, const int64_t* blob_off, int32_t* pos, int64_t pos_cap,
+                         int64_t* off, uint8_t* status, int64_t* n_pos);
 
 /* ---- measurement hooks (bench.py only; no effect on results) -------------------- */
 

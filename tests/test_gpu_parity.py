@@ -744,3 +744,40 @@ def test_low_ceiling_filter_with_removed_and_invalid_rows():
         else:
             assert got.get(q, {}) == c_oracle.one_vs_all(coll.pos, coll.off, inv2, q, 12, nthreads=4), q
     eng.close()
+
+
+def test_persist_pickles_start_up_reload():
+    """start-up reload from the reference's stored form (pickle protocol 2 per sample, mongoStore.py:344-363): natively
+    parsed samples (valid, invalid), one in patch form (unpickled the ordinary way), lazily materialised host dicts;
+    neighbours must equal the reference's (collection.json) and a plain persist() reload."""
+    import pickle
+    g = golden("collection.json")
+    sc, coll = _cluster_class()                           # ordinary persist(), used as the twin
+    want20 = {int(q): {r[0]: tuple(r[1:]) for r in rows} for q, rows in g["neighbours"]["20"].items()}
+    # re-encode one family member as a patch in the twin, so that one stored object is NOT a plain compressed sequence
+    q0 = max(want20, key=lambda k: len(want20[k]))
+    sc.snpCompressionCeiling = 20
+    sc.compress_relative_to_consensus("s%d" % q0, 0.8)
+    kinds = [sc._stored_kind("s%d" % i) for i in range(coll.n)]
+    assert "patch" in kinds and "invalid" in kinds and "compressed" in kinds
+    guids = ["s%d" % i for i in range(coll.n)]
+    blobs = [pickle.dumps(sc.seqProfile[gu], protocol=2) for gu in guids]
+    sc2 = _sc(sc.reference, 700, 20, sc.excluded)
+    sc2.consensi = dict(sc.consensi)
+    sc2.persist_pickles(blobs, guids)
+    assert sc2.engine.stats()["n_rows"] == coll.n
+    assert sc2.summarise_stored_items() == sc.summarise_stored_items()
+    lazy = sum(1 for v in sc2.seqProfile._d.values() if type(v).__name__ == "_LazyPickle")
+    assert lazy == kinds.count("compressed") + kinds.count("invalid")
+    for q in list(want20)[::7] + [q0]:
+        got = {int(r[1][1:]): tuple(r[2:6]) for r in sc2.mcompare("s%d" % q) if r[2] is not None}
+        assert got == want20[q], q
+    assert sc2.seqProfile["s%d" % q0] == sc.seqProfile["s%d" % q0]
+    some = next(i for i in range(coll.n) if kinds[i] == "compressed")
+    assert sc2.seqProfile["s%d" % some] == coll.as_dict(some)          # materialised on demand, identical content
+    n_before = sc2.engine.stats()["n_rows"]
+    sc2.persist(coll.as_dict(some), "s%d" % some)                      # identical content: no new device row
+    assert sc2.engine.stats()["n_rows"] == n_before
+    res = sc2.multi_sequence_alignment(guids[:10], output="dict", sample_size=5)
+    ref_res = sc.multi_sequence_alignment(guids[:10], output="dict", sample_size=5)
+    assert res["variant_positions"] == ref_res["variant_positions"] and res["guid2msa_seq"] == ref_res["guid2msa_seq"]

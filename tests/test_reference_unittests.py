@@ -1,0 +1,51 @@
+"""not-gpu, build-container only (needs /root/reference): the REFERENCE'S OWN unit tests for class seqComparer
+(src/seqComparer.py:1130-2257, 65 unittest.TestCase classes) executed against the drop-in class
+findneighbour3_b200.seqComparer.seqComparer.
+
+The class under test is the product's host layer (API surface, exception types, return shapes, double-delta and MSA
+control flow).  Its device engine is replaced here by the oracle-backed stand-in of tests/fake_engine.py — this box has
+no GPU; the CUDA engine itself is checked against golden vectors of the same reference in tests/test_gpu_parity.py.
+"""
+import unittest
+
+import pytest
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference checkout not present")
+
+# needs files the reference checkout does not ship: ../reference/NC_000962.fasta, TB-exclude-adaptive.txt
+NEEDS_MISSING_FILES = {"test_seqComparer_45"}
+
+
+def _run_reference_tests(monkeypatch):
+    import findneighbour3_b200.seqComparer as dropin
+    from fake_engine import OracleEngine
+    monkeypatch.setattr(dropin, "Engine", lambda genome_length, device=0: OracleEngine(genome_length))
+    ref = ref_shim.load_reference_module("seqComparer")
+    original = ref.seqComparer
+    results = {}
+    try:
+        ref.seqComparer = dropin.seqComparer          # the tests look the class up as a module global
+        for name in sorted(dir(ref)):
+            obj = getattr(ref, name)
+            if isinstance(obj, type) and issubclass(obj, unittest.TestCase) and name.startswith("test_"):
+                res = unittest.TestResult()
+                unittest.defaultTestLoader.loadTestsFromTestCase(obj).run(res)
+                results[name] = res
+    finally:
+        ref.seqComparer = original
+    return results
+
+
+def test_reference_unit_tests_pass_against_the_drop_in_class(monkeypatch):
+    results = _run_reference_tests(monkeypatch)
+    assert len(results) >= 60
+    bad = {}
+    for name, res in results.items():
+        if name in NEEDS_MISSING_FILES:
+            continue
+        if res.errors or res.failures:
+            bad[name] = (res.errors + res.failures)[0][1].strip().splitlines()[-1]
+    assert not bad, "\n".join("%s: %s" % kv for kv in sorted(bad.items()))
+    assert sum(r.testsRun for r in results.values()) >= 60

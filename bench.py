@@ -623,6 +623,27 @@ def main():
                    "note": "fn3_msa_sites / fn3_msa_align / fn3_consensus through ctypes, wall clock per call incl. host "
                            "synchronisations; plane bytes = vote planes cleared once and scanned twice (count, write)"}
 
+    # ---- leg 6 (extra): start-up reload from the reference's stored form (pickle protocol 2 per sample):
+    # native parse (fn3_unpickle_samples, host threads) vs pickle.loads + packing of the same 2 000 samples ----------
+    reload_leg = None
+    if args.allvsall and world == 1:
+        import pickle
+        from findneighbour3_b200 import packing
+        idx = np.flatnonzero(coll.invalid == 0)[:2000]
+        blobs = [pickle.dumps(coll.as_dict(int(i)), protocol=2) for i in idx]
+        packing.unpickle_many(blobs[:64])
+        t0 = time.perf_counter()
+        p_n, o_n, st_n = packing.unpickle_many(blobs)
+        t_native = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        p_p, o_p, inv_p = packing.pack_many([pickle.loads(b) for b in blobs])
+        t_python = time.perf_counter() - t0
+        assert np.array_equal(p_n, p_p) and np.array_equal(o_n, o_p) and not st_n.any()
+        reload_leg = {"samples": int(idx.size), "pickle_bytes_mean": float(np.mean([len(b) for b in blobs])),
+                      "native_samples_per_s": idx.size / t_native, "python_samples_per_s": idx.size / t_python,
+                      "speedup": t_python / t_native, "host_threads": min(16, os.cpu_count() or 1),
+                      "note": "packing.unpickle_many (fn3_unpickle_samples) vs pickle.loads + packing.pack_many; identical output"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -649,6 +670,8 @@ def main():
         line["ingest"] = ingest
     if cluster is not None:
         line["cluster_statistics"] = cluster
+    if reload_leg is not None:
+        line["reload_from_pickles"] = reload_leg
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_python_port(coll, fresh[W:], ceiling, args.cpu_seconds)

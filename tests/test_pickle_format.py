@@ -85,3 +85,34 @@ def test_native_unpickle_python2_style_pickle():
     pos, off, status = packing.unpickle_many([blob])
     assert status.tolist() == [0]
     assert [pos[off[b]:off[b + 1]].tolist() for b in range(6)] == [[5, 10000], [], [], [], [2, 100000], [9]]
+
+
+def test_native_unpickle_survives_damaged_input():
+    """mutated / truncated pickles: never a crash; whatever is still read as a valid sample equals what Python reads"""
+    rnd = random.Random(1)
+    base = {"A": {1, 5, 300, 70000}, "C": set(), "G": {7}, "T": {9, 10}, "N": set(range(1000, 2500)),
+            "M": {9000: "R", 12000: "R", 40000: "y"}, "invalid": 0}
+    b0 = pickle.dumps(base, protocol=2)
+    blobs = []
+    for _ in range(3000):
+        b = bytearray(b0)
+        for _ in range(rnd.choice((1, 1, 2, 3, 8))):
+            op = rnd.randrange(4)
+            if op == 0:
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+            elif op == 1 and len(b) > 1:
+                del b[rnd.randrange(len(b))]
+            elif op == 2:
+                b.insert(rnd.randrange(len(b) + 1), rnd.randrange(256))
+            else:
+                b = b[: max(1, rnd.randrange(len(b) + 1))]
+        blobs.append(bytes(b))
+    pos, off, status = packing.unpickle_many(blobs)
+    assert set(status.tolist()) <= {0, 1, 2} and (status == 2).sum() > 2000
+    for i in np.flatnonzero(status == 0):
+        try:
+            o = pickle.loads(blobs[i])
+            want = [sorted(o[k]) for k in "ACGTN"] + [sorted(o["M"].keys())]
+        except Exception:
+            continue
+        assert [pos[off[6 * i + b]:off[6 * i + b + 1]].tolist() for b in range(6)] == want

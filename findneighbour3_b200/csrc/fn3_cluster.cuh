@@ -14,26 +14,27 @@
 // planes: cnt[b * Lpad + p] = number of given samples that carry position p in list b (0..3 = A,C,G,T; 4 = N).
 // A sample given twice votes twice (the reference counts the objects of its list one by one, :483-490).
 
-// stored rows: one warp per row, lanes stride the row's words; N run words are expanded (want_n)
-__global__ void __launch_bounds__(256) k_votes_rows(const long long* __restrict__ rows, long long n, const HdrTable ht,
-                                                    uint32_t* __restrict__ cnt, long long Lpad, int want_n, int pos_bits) {
-    const int lane = threadIdx.x & 31;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+// stored rows: one CTA per row, threads stride the row's words; N run words are expanded (want_n).
+// (One warp per row — 16 dependent load->atomic rounds per lane, 7 CTAs for a 50-row cluster — took 14.7 us: latency.)
+#define FN3_VOTE_THREADS 256
+__global__ void __launch_bounds__(FN3_VOTE_THREADS) k_votes_rows(const long long* __restrict__ rows, long long n, const HdrTable ht,
+                                                                 uint32_t* __restrict__ cnt, long long Lpad, int want_n, int pos_bits) {
+    const uint32_t tid = threadIdx.x;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
-    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
         int tl;
         const unsigned char* tile = tile_of(ht, rows[i], tl);
         const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
-        const uint4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1);
+        const uint4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1);          // every thread, one address: a broadcast
         if ((h0.x | h0.y) == 0u) continue;                       // invalid sample: it has no lists (:485)
         const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
         const uint32_t e0 = h0.z, e1 = h0.w, e2 = h1.x, e3 = h1.y, e4 = h1.z;
-        for (uint32_t w = lane; w < e3; w += 32) {
+        for (uint32_t w = tid; w < e3; w += FN3_VOTE_THREADS) {
             const uint32_t b = (w >= e0) + (w >= e1) + (w >= e2);
             atomicAdd(&cnt[(long long)b * Lpad + d[w]], 1u);
         }
         if (want_n)
-            for (uint32_t w = e3 + lane; w < e4; w += 32) {
+            for (uint32_t w = e3 + tid; w < e4; w += FN3_VOTE_THREADS) {
                 const uint32_t x = d[w], s = x & pmask, len = (pos_bits >= 32) ? 1u : ((x >> pos_bits) + 1u);
                 for (uint32_t j = 0; j < len; ++j) atomicAdd(&cnt[4ll * Lpad + s + j], 1u);
             }

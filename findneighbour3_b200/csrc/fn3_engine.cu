@@ -1487,7 +1487,7 @@ extern "C" int fn3_consensus(fn3_engine* e, const int64_t* rows, int64_t n_rows,
     cudaStream_t st = e->q_stream;
     CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * 5 * sizeof(uint32_t), st));
     if (n_rows > 0) {
-        k_votes_rows<<<grid_for(e, n_rows * 32, 256), 256, 0, st>>>(e->d_rows, n_rows, ht, e->d_votes, e->vLpad, 1, e->pos_bits);
+        k_votes_rows<<<(unsigned)std::min<long long>(n_rows, (long long)e->sm_count * 8), FN3_VOTE_THREADS, 0, st>>>(e->d_rows, n_rows, ht, e->d_votes, e->vLpad, 1, e->pos_bits);
         e->launches += 1;
         CU(e, cudaGetLastError());
     }
@@ -1544,7 +1544,7 @@ extern "C" int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows,
     if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_sites", &ht))) return rc;
     cudaStream_t st = e->q_stream;
     CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * 4 * sizeof(uint32_t), st));
-    k_votes_rows<<<grid_for(e, n_rows * 32, 256), 256, 0, st>>>(e->d_rows, n_rows, ht, e->d_votes, e->vLpad, 0, e->pos_bits);
+    k_votes_rows<<<(unsigned)std::min<long long>(n_rows, (long long)e->sm_count * 8), FN3_VOTE_THREADS, 0, st>>>(e->d_rows, n_rows, ht, e->d_votes, e->vLpad, 0, e->pos_bits);
     e->launches += 1;
     CU(e, cudaGetLastError());
     long long len[5], total = 0;

@@ -65,6 +65,7 @@ SIGNATURES = {
     "fn3_consensus": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),
     "fn3_consensus_lists": (C.c_int, [_vp, C.c_int64, _i32p, _i64p, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),
     "fn3_msa_sites": (C.c_int, [_vp, _i64p, C.c_int64, _i32p, C.c_int64, _i64p]),
+    "fn3_msa_sites_rule": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int32, _i32p, C.c_int64, _i64p]),
     "fn3_msa_align": (C.c_int, [_vp, _i64p, C.c_int64, _i32p, C.c_int64, _u8p, _i32p]),
     "fn3_unpickle_samples": (C.c_int, [C.c_int64, _u8p, _i64p, _i32p, C.c_int64, _i64p, _u8p, _i64p]),
     "fn3_profile_queries": (C.c_int, [_vp, _i64p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i64p, _i64p]),

@@ -58,12 +58,15 @@ __global__ void __launch_bounds__(256) k_votes_lists(const int32_t* __restrict__
 // MODE 0 (_msa steps 1-3): ONE list — p is a variant site iff the samples show more than one base there, the reference
 //   base (refcode[p]: 0..3 = A,C,G,T) included whenever some of the `thr` samples has no A/C/G/T call at p (:916-931).
 // MODE 1 (consensus, :492-500): FIVE lists — p enters list b iff cnt[b][p] >= thr (thr >= 1).
-template <int MODE> struct SelLists { static const int N = MODE == 0 ? 1 : 5; };
+// MODE 2 (seqComparer_mt._msa step 2, src/seqComparer_mt.py:1127-1137): MODE 0, except that a sample's N at p also
+//   "accounts for" p — the reference base is added only when some sample has neither a base call nor an N there
+//   (needs the N plane: k_votes_rows with want_n).
+template <int MODE> struct SelLists { static const int N = MODE == 1 ? 5 : 1; };
 
 template <int MODE>
 __device__ __forceinline__ void sel_flags(const uint32_t* __restrict__ cnt, const uint8_t* __restrict__ refcode, long long Lpad,
                                           long long p0, uint32_t thr, uint32_t flags[SelLists<MODE>::N]) {
-    if (MODE == 0) {
+    if (MODE != 1) {
         uint32_t seen[FN3_SEL_PER_THREAD], tot[FN3_SEL_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < FN3_SEL_PER_THREAD; ++i) { seen[i] = 0u; tot[i] = 0u; }
@@ -75,6 +78,12 @@ __device__ __forceinline__ void sel_flags(const uint32_t* __restrict__ cnt, cons
                 const uint32_t c[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { seen[4 * k + j] |= (uint32_t)(c[j] != 0u) << b; tot[4 * k + j] += c[j]; }
+            }
+        if (MODE == 2)
+#pragma unroll
+            for (int k = 0; k < FN3_SEL_PER_THREAD / 4; ++k) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(cnt + 4ll * Lpad + p0) + k);
+                tot[4 * k] += v.x; tot[4 * k + 1] += v.y; tot[4 * k + 2] += v.z; tot[4 * k + 3] += v.w;
             }
         const uint4 rv = __ldg(reinterpret_cast<const uint4*>(refcode + p0));
         const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};

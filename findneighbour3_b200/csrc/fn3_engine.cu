@@ -1530,9 +1530,10 @@ extern "C" int fn3_consensus_lists(fn3_engine* e, int64_t n, const int32_t* pos_
     return consensus_tail(e, min_votes, pos, pos_cap, off, n_pos, "fn3_consensus_lists");
 }
 
-extern "C" int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t* sites, int64_t sites_cap,
-                             int64_t* n_sites) {
-    if (!e || !n_sites || n_rows < 0 || (n_rows > 0 && !rows)) return set_err(e, FN3_EARG, "fn3_msa_sites: bad arguments");
+extern "C" int fn3_msa_sites_rule(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t rule, int32_t* sites,
+                                  int64_t sites_cap, int64_t* n_sites) {
+    if (!e || !n_sites || n_rows < 0 || (n_rows > 0 && !rows) || (rule != FN3_SITES_CALLS && rule != FN3_SITES_CALLS_OR_N))
+        return set_err(e, FN3_EARG, "fn3_msa_sites: bad arguments");
     *n_sites = 0;
     if (n_rows == 0) return FN3_OK;
     std::lock_guard<std::mutex> q(e->query_mu);
@@ -1543,14 +1544,21 @@ extern "C" int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows,
     HdrTable ht;
     if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_sites", &ht))) return rc;
     cudaStream_t st = e->q_stream;
-    CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * 4 * sizeof(uint32_t), st));
-    k_votes_rows<<<(unsigned)std::min<long long>(n_rows, (long long)e->sm_count * 8), FN3_VOTE_THREADS, 0, st>>>(e->d_rows, n_rows, ht, e->d_votes, e->vLpad, 0, e->pos_bits);
+    const int planes = rule == FN3_SITES_CALLS_OR_N ? 5 : 4;          // the N plane only where the rule reads it
+    CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * planes * sizeof(uint32_t), st));
+    k_votes_rows<<<(unsigned)std::min<long long>(n_rows, (long long)e->sm_count * 8), FN3_VOTE_THREADS, 0, st>>>(e->d_rows, n_rows, ht, e->d_votes, e->vLpad, planes == 5, e->pos_bits);
     e->launches += 1;
     CU(e, cudaGetLastError());
     long long len[5], total = 0;
-    if ((rc = run_select<0>(e, (uint32_t)std::min<int64_t>(n_rows, 0xffffffffll), len, &total))) return rc;
+    const uint32_t thr = (uint32_t)std::min<int64_t>(n_rows, 0xffffffffll);
+    if ((rc = rule == FN3_SITES_CALLS_OR_N ? run_select<2>(e, thr, len, &total) : run_select<0>(e, thr, len, &total))) return rc;
     *n_sites = total;
     return fetch_selected(e, total, sites, sites_cap, "fn3_msa_sites");
+}
+
+extern "C" int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t* sites, int64_t sites_cap,
+                             int64_t* n_sites) {
+    return fn3_msa_sites_rule(e, rows, n_rows, FN3_SITES_CALLS, sites, sites_cap, n_sites);
 }
 
 extern "C" int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows, const int32_t* sites, int64_t n_sites,

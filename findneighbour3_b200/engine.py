@@ -297,14 +297,16 @@ class Engine:
         return self._consensus_call(lambda p, cap, off, npos: self._lib.fn3_consensus_lists(
             self._h, n, _ptr(pos_in, _i32p), _ptr(off_in, _i64p), int(min_votes), p, cap, off, npos))
 
-    def msa_sites(self, rows):
-        """ordered variant positions of the (valid) stored rows -> int32[]."""
+    def msa_sites(self, rows, n_is_call=False):
+        """ordered variant positions of the (valid) stored rows -> int32[].  n_is_call: the older rule of
+        seqComparer_mt._msa, where an N also accounts for a position (FN3_SITES_CALLS_OR_N)."""
         r = np.ascontiguousarray(rows, dtype=np.int64)
         n_sites = C.c_int64(0)
         cap = 1 << 14
         while True:
             sites = np.empty(cap, dtype=np.int32)
-            rc = self._lib.fn3_msa_sites(self._h, _ptr(r, _i64p), r.size, _ptr(sites, _i32p), cap, C.byref(n_sites))
+            rc = self._lib.fn3_msa_sites_rule(self._h, _ptr(r, _i64p), r.size, 1 if n_is_call else 0, _ptr(sites, _i32p), cap,
+                                              C.byref(n_sites))
             if rc == N.FN3_ECAPACITY:
                 cap = int(n_sites.value)
                 continue

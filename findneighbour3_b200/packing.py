@@ -35,7 +35,8 @@ def pack_compressed(obj):
     the keys) and stay in the host copy of the dict."""
     if is_invalid(obj):
         return np.empty(0, dtype=np.int32), np.zeros(7, dtype=np.int32), True
-    parts = [_sorted_i32(obj[k]) if k != "M" else _sorted_i32(obj["M"].keys()) for k in LIST_ORDER]
+    # (the older seqComparer_mt sample type has no 'M' key, src/seqComparer_mt.py:474: an empty M list)
+    parts = [_sorted_i32(obj[k]) if k != "M" else _sorted_i32(obj.get("M", {}).keys()) for k in LIST_ORDER]
     off = np.zeros(7, dtype=np.int32)
     off[1:] = np.cumsum([p.size for p in parts])
     pos = np.concatenate(parts) if off[6] else np.empty(0, dtype=np.int32)

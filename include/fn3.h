@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FN3_ABI_VERSION 2   /* 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align, fn3_unpickle_samples */
+#define FN3_ABI_VERSION 3   /* 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align, fn3_unpickle_samples; 3: + fn3_msa_sites_rule */
 
 /* status codes */
 #define FN3_OK          0
@@ -214,6 +214,15 @@ int fn3_consensus_lists(fn3_engine* e, int64_t n, const int32_t* pos_in, const i
  * FN3_ECAPACITY with *n_sites = required if sites is too small. */
 int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t* sites, int64_t sites_cap,
                   int64_t* n_sites);
+
+/* The same with the rule of the caller's class stated: FN3_SITES_CALLS is fn3_msa_sites (seqComparer._msa,
+ * src/seqComparer.py:916-931); FN3_SITES_CALLS_OR_N is the older seqComparer_mt._msa (src/seqComparer_mt.py:1127-1137),
+ * where a sample's N at a position also accounts for it: the reference base joins the bases seen at p only when
+ * some sample has neither an A/C/G/T call nor an N at p. */
+#define FN3_SITES_CALLS       0
+#define FN3_SITES_CALLS_OR_N  1
+int fn3_msa_sites_rule(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t rule, int32_t* sites,
+                       int64_t sites_cap, int64_t* n_sites);
 
 /* _msa step 4 and the N/M tallies (:933-950, :905-908, :975-977), and estimate_expected_unk_sites (:664-689):
  * for every row i and every site k (sites strictly increasing), codes[i*n_sites + k] = 0 reference base, 1..4

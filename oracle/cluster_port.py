@@ -30,9 +30,10 @@ def consensus(samples, cutoff_proportion):
     return out
 
 
-def variant_positions(reference, samples):
+def variant_positions(reference, samples, n_is_call=False):
     """_msa steps 1-3 (:910-931): positions where the samples show more than one base, a sample with no
-    A/C/T/G call at the position standing for the reference base."""
+    A/C/T/G call at the position standing for the reference base.  n_is_call: the older rule of
+    src/seqComparer_mt.py:1127-1137, where a sample's N at the position also accounts for it."""
     seen = {}
     for s in samples:
         for base in ("A", "C", "T", "G"):
@@ -40,7 +41,7 @@ def variant_positions(reference, samples):
                 seen.setdefault(p, set()).add(base)
     for s in samples:
         for p in seen:
-            if not (p in s["A"] or p in s["C"] or p in s["T"] or p in s["G"]):
+            if not (p in s["A"] or p in s["C"] or p in s["T"] or p in s["G"] or (n_is_call and p in s["N"])):
                 seen[p].add(reference[p])
     return sorted(p for p, bases in seen.items() if len(bases) > 1)
 

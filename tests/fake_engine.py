@@ -160,12 +160,12 @@ class OracleEngine:
             dicts.append({k: set(int(x) for x in pos_in[o[b]:o[b + 1]]) for b, k in enumerate("ACGTN")})
         return self._vote(dicts, min_votes)
 
-    def msa_sites(self, rows):
+    def msa_sites(self, rows, n_is_call=False):
         from oracle import cluster_port as cp
         dicts = [self._dict_of(int(r)) for r in rows]
         if any(d is None for d in dicts):
             raise ValueError("invalid sample")
-        return np.array(cp.variant_positions(self._ref, dicts), dtype=np.int32)
+        return np.array(cp.variant_positions(self._ref, dicts, n_is_call), dtype=np.int32)
 
     def msa_align(self, rows, sites, want_codes=True):
         from oracle import cluster_port as cp

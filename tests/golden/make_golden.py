@@ -17,6 +17,9 @@ Files
   msa.json            multi_sequence_alignment outputs on the reference's own test families (tests 45a-47c)
   cluster.json        consensus votes, _msa sites / aligned strings / N-M tallies and estimate_expected_unk_sites on
                       the collection of collection.json (`--cluster` regenerates only this file)
+  mt.json             the older threaded class (src/seqComparer_mt.py, unmodified) on the same collection without its
+                      M lists: compress, both mcompare conventions, consensus / patches / recompression, the
+                      three-test MSA and estimate_expected_N[_sites] (`--mt` regenerates only this file)
 """
 import json
 import os
@@ -412,7 +415,115 @@ def make_cluster():
     dump("cluster.json", out)
 
 
+def make_mt():
+    """The older class `seqComparer_mt.seqComparer`: N-only samples and distances, the two
+    mcompare conventions (single thread: skips the query, cut-off snpCompressionCeiling, lists; threads: includes the
+    query, cut-off snpCeiling, tuples), {'add','subtract'} patches, the MSA whose site rule lets N account for a
+    position.  Order-independent by construction (results keyed by guid, sample_size = all valid samples)."""
+    MT = ref_shim.load_reference_module("seqComparer_mt")
+    with open(os.path.join(HERE, "collection.json")) as fh:
+        c = json.load(fh)
+    L = c["genome_length"]
+    ref = synth.reference_string(synth.random_reference(L, c["ref_seed"]))
+    pos, off, invalid = np.array(c["pos"], np.int32), np.array(c["off"], np.int64), np.array(c["invalid"], np.uint8)
+    n = invalid.size
+    excluded = set(np.flatnonzero(synth.synthetic_mask(L, 2000, 12, seed=3)).tolist())
+
+    def as_dict(i):
+        if invalid[i]:
+            return {"invalid": 1}
+        o = off[6 * i: 6 * i + 7]
+        d = {"invalid": 0}
+        for b, k in enumerate("ACGTN"):
+            d[k] = set(int(x) for x in pos[o[b]:o[b + 1]])
+        return d
+
+    def setlist(d):
+        return {k: sorted(int(x) for x in v) for k, v in d.items()}
+
+    def rows_of(res):
+        return sorted([r[1], r[2], r[3], r[4], r[5], None if r[6] is None else len(r[6]), None if r[7] is None else len(r[7]),
+                       None if r[8] is None else sorted(int(x) for x in r[8])[:5]] for r in res)
+
+    valid = [i for i in range(n) if not invalid[i]]
+    rnd = random.Random(23)
+    out = {"mcompare": [], "msa": [], "consensus": [], "compress": []}
+
+    def store(cpu, ceiling, comp):
+        sc = MT.seqComparer(reference=ref, maxNs=700, snpCeiling=ceiling, snpCompressionCeiling=comp, cpuCount=cpu,
+                            excludePositions=excluded)
+        for i in range(n):
+            sc.persist(as_dict(i), "s%d" % i)
+        return sc
+
+    queries = valid[:3] + [i for i in range(n) if invalid[i]][:1] + rnd.sample(valid, 4)
+    for cpu, ceiling, comp in ((1, 20, 250), (1, 12, 40), (1, 20, None), (3, 20, 250), (2, 12, 250)):
+        sc = store(cpu, ceiling, comp)
+        for q in queries:
+            res = sc.mcompare("s%d" % q)
+            kind = sorted(set(type(r).__name__ for r in res))
+            out["mcompare"].append({"cpuCount": cpu, "snpCeiling": ceiling, "snpCompressionCeiling": comp, "query": "s%d" % q,
+                                    "row_type": kind, "rows": rows_of(res)})
+        subset = ["s%d" % i for i in rnd.sample(range(n), 20)]
+        res = sc.mcompare("s%d" % valid[5], subset)
+        out["mcompare"].append({"cpuCount": cpu, "snpCeiling": ceiling, "snpCompressionCeiling": comp, "query": "s%d" % valid[5],
+                                "guids": subset, "row_type": sorted(set(type(r).__name__ for r in res)), "rows": rows_of(res)})
+
+    sc = store(1, 20, 250)
+    out["summary"] = sc.summarise_stored_items()
+    sels = [valid[:12], valid[12:20] + [i for i in range(n) if invalid[i]][:2], rnd.sample(valid, 9), valid[40:43], [valid[7]],
+            rnd.sample(range(n), 25)]
+    for sel in sels:
+        guids = ["s%d" % i for i in sel]
+        res = sc.multi_sequence_alignment(guids, output="dict", sample_size=len(valid))
+        clean = {}
+        for k, v in res.items():
+            if k == "guid2sequence":
+                continue
+            if isinstance(v, dict):
+                clean[k] = {kk: (None if vv is None else (float(vv) if isinstance(vv, (float, np.floating)) else
+                                 (int(vv) if isinstance(vv, (int, np.integer)) else vv))) for kk, vv in v.items()}
+            else:
+                clean[k] = [int(x) if isinstance(x, (int, np.integer)) else x for x in v]
+        df = sc.multi_sequence_alignment(guids, output="df", sample_size=len(valid))
+        out["msa"].append({"select": guids, "sample_size": len(valid), "got": clean, "columns": list(df.columns),
+                           "p_value3_column": {g: (None if v is None or v != v else float(v)) for g, v in df["p_value3"].items()}})
+    out["expected_N"] = float(sc.estimate_expected_N(sample_size=len(valid)))
+    out["expected_N_too_few"] = sc.estimate_expected_N(sample_size=len(valid) + 1)
+    out["expected_N_sites"] = float(sc.estimate_expected_N_sites(sample_size=len(valid), sites=set(out["msa"][0]["got"]["variant_positions"])))
+
+    groups = [valid[:10], valid[10:22], rnd.sample(valid, 7), valid[:3] + valid[:3]]
+    for g in groups:
+        for cutoff in (0.3, 0.5, 0.8, 1.0):
+            cons = sc.consensus([sc.seqProfile["s%d" % i] for i in g], cutoff)
+            member = sc.seqProfile["s%d" % g[0]]
+            patch = sc.generate_patch(member, cons)
+            back = sc.apply_patch(patch, cons)
+            assert back == member
+            out["consensus"].append({"members": g, "cutoff": cutoff, "got": setlist(cons), "hash": sc.compressed_sequence_hash(cons),
+                                     "patch_of_first": {k: setlist(v) for k, v in patch.items()}})
+    seed = "s%d" % valid[0]
+    visited = sc.compress_relative_to_consensus(seed)
+    out["recompress"] = {"seed": seed, "visited": sorted(visited), "n_consensi": len(sc.consensi),
+                         "summary": sc.summarise_stored_items(),
+                         "patches": {g: {k: setlist(v) for k, v in sc.seqProfile[g]["patch"].items()} for g in sorted(visited)[:6]},
+                         "neighbours_after": rows_of(sc.mcompare(seed))}
+
+    small = MT.seqComparer(reference="ACTGACTG", maxNs=3, snpCeiling=10, excludePositions={7})
+    for seq in ("ACTGACTG", "NCTGACTA", "A-TGACTG", "CCCCCCCC", "NNNNACTG", "ACTGNNNN", "ACTRACTG", "ACTGACTR", "ACTQACTG"):
+        try:
+            got = small.compress(seq)
+            got = {"invalid": 1} if got.get("invalid") == 1 else dict(setlist({k: got[k] for k in "ACGTN"}), invalid=0)
+            out["compress"].append({"seq": seq, "got": got, "roundtrip": None if got["invalid"] else small.uncompress(small.compress(seq))})
+        except KeyError as ex:
+            out["compress"].append({"seq": seq, "raises": "KeyError", "arg": ex.args[0]})
+    dump("mt.json", out)
+
+
 if __name__ == "__main__":
+    if "--mt" in sys.argv:
+        make_mt()
+        sys.exit(0)
     if "--cluster" in sys.argv:
         make_cluster()
         sys.exit(0)
@@ -423,3 +534,4 @@ if __name__ == "__main__":
     make_collection()
     make_consensus()
     make_cluster()
+    make_mt()

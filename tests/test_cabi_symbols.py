@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), "libfn3.so does not export %s" % name
     assert set(_native.SIGNATURES) == set(declared_symbols())
-    assert lib.fn3_abi_version() == 2
+    assert lib.fn3_abi_version() == 3
 
 
 def _has_gpu():

@@ -598,6 +598,8 @@ def test_cluster_engine_vs_port(shape):
         ordered = cp.variant_positions(ref, samples)
         sites = eng.msa_sites(gsel)
         assert sites.tolist() == ordered, (shape, len(gsel))
+        # the older rule of seqComparer_mt._msa (an N also accounts for a position): fn3_msa_sites_rule
+        assert eng.msa_sites(gsel, n_is_call=True).tolist() == cp.variant_positions(ref, samples, n_is_call=True)
         codes, counts = eng.msa_align(gsel, sites, want_codes=True)
         lut = np.frombuffer(b"?ACGTNM", dtype=np.uint8)
         ref_at = np.frombuffer(ref.encode(), dtype=np.uint8)[sites]

@@ -588,9 +588,26 @@ def main():
             for sq in seqs:
                 eng.compress(sq)
         t_c = (time.perf_counter() - t0) / (5 * len(seqs))
+        # the server's whole insert data path from the sequence string (findNeighbour3-server.py:511-530) in one call:
+        # composition histogram + compress + maxNs decision + persist + one-vs-all (fn3_ingest_query); and the
+        # stand-alone device histogram behind the NucleicAcid drop-in (fn3_byte_histogram)
+        from findneighbour3_b200.engine import byte_histogram
+        eng.ingest_query(seqs[0], 130000, args.ceiling)
+        byte_histogram(seqs[0], local)
+        t0 = time.perf_counter()
+        for sq in seqs:
+            eng.ingest_query(sq, 130000, args.ceiling)
+        t_i = (time.perf_counter() - t0) / len(seqs)
+        t0 = time.perf_counter()
+        for sq in seqs:
+            byte_histogram(sq, local)
+        t_h = (time.perf_counter() - t0) / len(seqs)
         ingest = {"compress_ms_per_sequence": 1e3 * t_c, "sequence_bytes": int(coll.genome_length),
                   "GBps_host_to_lists": coll.genome_length / t_c / 1e9,
-                  "note": "fn3_compress through ctypes: 4.4 MB sequence host->device, 3 kernels, lists device->host"}
+                  "ingest_query_ms_per_sequence": 1e3 * t_i, "byte_histogram_ms_per_sequence": 1e3 * t_h,
+                  "note": "fn3_compress through ctypes: 4.4 MB sequence host->device, 3 kernels, lists device->host; "
+                          "ingest_query = composition histogram + compress + persist + one-vs-all from the same copy "
+                          "(fn3_ingest_query); byte_histogram = NucleicAcid.examine's counts (fn3_byte_histogram)"}
 
     # ---- leg 5 (extra): cluster statistics on the device: consensus vote over 250 stored rows,
     # MSA variant sites + alignment + N/M tallies of a 50-sample cluster -------------------------------------------

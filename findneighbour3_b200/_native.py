@@ -62,6 +62,9 @@ SIGNATURES = {
                                  _vp, _i32p]),
     "fn3_set_reference": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64]),
     "fn3_compress": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64, _i32p, C.c_char_p, C.c_int64, _i64p]),
+    "fn3_ingest_query": (C.c_int, [_vp, C.c_char_p, C.c_int64, C.c_int32, _i64p, _i32p, C.c_int64, _i32p, C.c_char_p, C.c_int64,
+                                   _i64p, _i32p, _i64p, _vp, C.c_int64, _i64p]),
+    "fn3_byte_histogram": (C.c_int, [C.c_int32, _u8p, C.c_int64, _i64p]),
     "fn3_consensus": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),
     "fn3_consensus_lists": (C.c_int, [_vp, C.c_int64, _i32p, _i64p, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),
     "fn3_msa_sites": (C.c_int, [_vp, _i64p, C.c_int64, _i32p, C.c_int64, _i64p]),

@@ -114,3 +114,52 @@ __global__ void __launch_bounds__(FN3_CMP_THREADS) k_compress_write(const uint8_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// composition counts: NucleicAcid.examine (src/NucleicAcid.py:50-58) counts 18 characters with one bytes.count() pass
+// each; here one pass over the sequence yields the whole 256-bin byte histogram.
+// ------------------------------------------------------------------------------------------
+// Sequences are ~25 % each of A,C,G,T plus N and '-': those six are counted in registers (byte-wise SIMD compare +
+// popcount; a shared-memory atomic per byte would serialise on four addresses), everything else — rare — goes to a
+// shared 256-bin histogram.  hist: 256 x u64, zeroed by the caller.
+#define FN3_HIST_THREADS 256
+
+__global__ void __launch_bounds__(FN3_HIST_THREADS) k_byte_hist(const uint8_t* __restrict__ bytes, long long n,
+                                                                unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0u;                                   // FN3_HIST_THREADS == 256
+    __syncthreads();
+    const uint32_t key[6] = {0x41414141u, 0x43434343u, 0x47474747u, 0x54545454u, 0x4e4e4e4eu, 0x2d2d2d2du};   // A C G T N -
+    uint32_t cnt[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+    const long long n16 = n >> 4;
+    const uint4* v = reinterpret_cast<const uint4*>(bytes);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(v + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t known = 0u;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const uint32_t m = __vcmpeq4(w[k], key[c]);  // 0xff in every byte that matches
+                cnt[c] += (uint32_t)__popc(m) >> 3;
+                known |= m;
+            }
+            if (known != 0xffffffffu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((known >> (8 * j)) & 0xffu) == 0u) atomicAdd(&sh[(w[k] >> (8 * j)) & 0xffu], 1u);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)                // the last n % 16 bytes
+        for (long long i = n16 << 4; i < n; ++i) atomicAdd(&sh[bytes[i]], 1u);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const uint32_t t = __reduce_add_sync(0xffffffffu, cnt[c]);
+        if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sh[key[c] & 0xffu], t);
+    }
+    __syncthreads();
+    const uint32_t mine = sh[threadIdx.x];
+    if (mine) atomicAdd(&hist[threadIdx.x], (unsigned long long)mine);
+}

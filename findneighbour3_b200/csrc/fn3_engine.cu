@@ -125,6 +125,7 @@ struct fn3_engine {
     int32_t* d_cpos = nullptr; uint32_t* d_ccounts = nullptr; uint32_t* d_ctotals = nullptr;
     uint8_t* h_seq = nullptr; uint32_t* h_ctotals = nullptr;   // pinned
     int32_t* h_cpos = nullptr; size_t h_cpos_cap = 0; uint8_t* h_mchars = nullptr; size_t h_mchars_cap = 0;   // pinned
+    unsigned long long* d_hist = nullptr; unsigned long long* h_hist = nullptr;   // byte histogram of the sequence (fn3_ingest_query)
 
     // cluster statistics (fn3_consensus*, fn3_msa_*): vote planes + selection scratch, allocated on first use
     uint32_t* d_votes = nullptr; long long vLpad = 0; int sel_ctas = 0;
@@ -355,6 +356,8 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     if (e->h_ctotals) cudaFreeHost(e->h_ctotals);
     if (e->h_cpos) cudaFreeHost(e->h_cpos);
     if (e->h_mchars) cudaFreeHost(e->h_mchars);
+    cudaFree(e->d_hist);
+    if (e->h_hist) cudaFreeHost(e->h_hist);
     cudaFree(e->d_refcode); cudaFree(e->d_votes); cudaFree(e->d_sel_counts); cudaFree(e->d_sel_totals); cudaFree(e->d_sel_out);
     cudaFree(e->d_sites); cudaFree(e->d_codes); cudaFree(e->d_acounts); cudaFree(e->d_lpos); cudaFree(e->d_loff);
     if (e->h_sel_totals) cudaFreeHost(e->h_sel_totals);
@@ -1327,15 +1330,16 @@ extern "C" int fn3_set_reference(fn3_engine* e, const char* reference, const int
     return FN3_OK;
 }
 
-extern "C" int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_cap, int32_t off[7],
-                            char* m_chars, int64_t m_cap, int64_t* n_pos) {
-    if (!e || !sequence || !off || !n_pos) return set_err(e, FN3_EARG, "fn3_compress: bad arguments");
-    std::lock_guard<std::mutex> g(e->ingest_mu);
-    if (!e->d_refmask) return set_err(e, FN3_EARG, "fn3_compress: call fn3_set_reference first");
+// compress() proper (ingest_mu held): sequence -> device lists -> caller's buffers; optionally the byte histogram of the
+// same device copy of the sequence (hist: 256 counts, or NULL)
+static int compress_locked(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_cap, int32_t off[7],
+                           char* m_chars, int64_t m_cap, int64_t* n_pos, int64_t* hist, const char* who) {
+    if (!e->d_refmask) return set_err(e, FN3_EARG, "%s: call fn3_set_reference first", who);
     CU(e, cudaSetDevice(e->device));
     cudaStream_t st = e->in_stream;
     memcpy(e->h_seq, sequence, (size_t)e->L);
     CU(e, cudaMemcpyAsync(e->d_seq, e->h_seq, (size_t)e->L, cudaMemcpyHostToDevice, st));
+    e->h2d_bytes += e->L;
     k_compress_count<<<e->cmp_ctas, FN3_CMP_THREADS, 0, st>>>(e->d_seq, e->d_refmask, e->d_ccounts);
     k_compress_scan<<<1, 32, 0, st>>>(e->d_ccounts, e->d_ctotals, e->cmp_ctas);
     k_compress_write<<<e->cmp_ctas, FN3_CMP_THREADS, 0, st>>>(e->d_seq, e->d_refmask, e->d_ccounts, e->d_ctotals,
@@ -1343,14 +1347,28 @@ extern "C" int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, i
     e->launches += 3;
     CU(e, cudaGetLastError());
     CU(e, cudaMemcpyAsync(e->h_ctotals, e->d_ctotals, 6 * 4, cudaMemcpyDeviceToHost, st));
+    if (hist) {
+        if (!e->d_hist) {
+            CU(e, cudaMalloc(&e->d_hist, 256 * sizeof(unsigned long long)));
+            CU(e, cudaHostAlloc(&e->h_hist, 256 * sizeof(unsigned long long), cudaHostAllocDefault));
+        }
+        CU(e, cudaMemsetAsync(e->d_hist, 0, 256 * sizeof(unsigned long long), st));
+        const long long chunks = (e->L + 16ll * FN3_HIST_THREADS - 1) / (16ll * FN3_HIST_THREADS);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(chunks, (long long)e->sm_count * 8));
+        k_byte_hist<<<grid, FN3_HIST_THREADS, 0, st>>>(e->d_seq, e->L, e->d_hist);
+        e->launches += 1;
+        CU(e, cudaGetLastError());
+        CU(e, cudaMemcpyAsync(e->h_hist, e->d_hist, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    }
     CU(e, cudaStreamSynchronize(st));
+    if (hist) for (int b = 0; b < 256; ++b) hist[b] = (int64_t)e->h_hist[b];
     long long total = 0;
     off[0] = 0;
     for (int c = 0; c < 6; ++c) { total += e->h_ctotals[c]; off[c + 1] = (int32_t)total; }
     const long long n_m = e->h_ctotals[5];
     *n_pos = total;
     if (total > pos_cap || n_m > m_cap || (total > 0 && !pos) || (n_m > 0 && !m_chars))
-        return set_err(e, FN3_ECAPACITY, "fn3_compress: need room for %lld positions and %lld mixed characters", total, n_m);
+        return set_err(e, FN3_ECAPACITY, "%s: need room for %lld positions and %lld mixed characters", who, total, n_m);
     if ((size_t)total > e->h_cpos_cap) {
         if (e->h_cpos) cudaFreeHost(e->h_cpos);
         e->h_cpos = nullptr; e->h_cpos_cap = 0;
@@ -1368,8 +1386,79 @@ extern "C" int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, i
     if (total) CU(e, cudaMemcpyAsync(e->h_cpos, e->d_cpos, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
     if (n_m) CU(e, cudaMemcpyAsync(e->h_mchars, e->d_mchars, (size_t)n_m, cudaMemcpyDeviceToHost, st));
     CU(e, cudaStreamSynchronize(st));
+    e->d2h_bytes += total * 4 + n_m + 24 + (hist ? 2048 : 0);
     if (total) memcpy(pos, e->h_cpos, (size_t)total * 4);
     if (n_m) memcpy(m_chars, e->h_mchars, (size_t)n_m);
+    return FN3_OK;
+}
+
+extern "C" int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_cap, int32_t off[7],
+                            char* m_chars, int64_t m_cap, int64_t* n_pos) {
+    if (!e || !sequence || !off || !n_pos) return set_err(e, FN3_EARG, "fn3_compress: bad arguments");
+    std::lock_guard<std::mutex> g(e->ingest_mu);
+    return compress_locked(e, sequence, pos, pos_cap, off, m_chars, m_cap, n_pos, nullptr, "fn3_compress");
+}
+
+extern "C" int fn3_ingest_query(fn3_engine* e, const char* sequence, int64_t max_ns, int32_t ceiling, int64_t* hist,
+                                int32_t* pos, int64_t pos_cap, int32_t off[7], char* m_chars, int64_t m_cap, int64_t* n_pos,
+                                int32_t* invalid, int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out) {
+    if (!e || !sequence || !off || !n_pos || !invalid || !out_row || !n_out || (cap > 0 && !out))
+        return set_err(e, FN3_EARG, "fn3_ingest_query: bad arguments");
+    *n_out = 0; *out_row = -1; *invalid = 0;
+    {
+        std::lock_guard<std::mutex> g(e->ingest_mu);
+        const int rc = compress_locked(e, sequence, pos, pos_cap, off, m_chars, m_cap, n_pos, hist, "fn3_ingest_query");
+        if (rc) return rc;                                   // nothing was stored (FN3_ECAPACITY: *n_pos = required)
+    }
+    *invalid = (int64_t)(off[6] - off[4]) > max_ns ? 1 : 0;  // len(N) + len(M) > maxNs (:301): stored without its lists
+    return fn3_insert_query(e, pos, off, *invalid, ceiling, out_row, out, cap, n_out);
+}
+
+// NucleicAcid.examine's character counts (src/NucleicAcid.py:50-58) for a string of any length, without an engine: one
+// small context per device (stream, staging, 256 counters), created on first use.
+struct HistCtx {
+    std::mutex mu;
+    cudaStream_t st = nullptr;
+    uint8_t* h_buf = nullptr; uint8_t* d_buf = nullptr; size_t cap = 0;
+    unsigned long long* d_hist = nullptr; unsigned long long* h_hist = nullptr;
+    int sm_count = 0;
+};
+static HistCtx g_hist[64];
+
+extern "C" int fn3_byte_histogram(int32_t device, const uint8_t* bytes, int64_t n, int64_t hist[256]) {
+    if (!hist || n < 0 || (n > 0 && !bytes) || device < 0 || device >= 64) return FN3_EARG;
+    for (int b = 0; b < 256; ++b) hist[b] = 0;
+    if (n == 0) return FN3_OK;
+    HistCtx& c = g_hist[device];
+    std::lock_guard<std::mutex> g(c.mu);
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return FN3_ECUDA; }   // no device: no CPU path either
+    if (!c.st) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FN3_ECUDA;
+        c.sm_count = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) { c.st = nullptr; return FN3_ECUDA; }
+        if (cudaMalloc(&c.d_hist, 256 * sizeof(unsigned long long)) != cudaSuccess) return FN3_ENOMEM;
+        if (cudaHostAlloc(&c.h_hist, 256 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) return FN3_ENOMEM;
+    }
+    if ((size_t)n > c.cap) {
+        if (c.h_buf) cudaFreeHost(c.h_buf);
+        if (c.d_buf) cudaFree(c.d_buf);
+        c.h_buf = nullptr; c.d_buf = nullptr; c.cap = 0;
+        const size_t want = std::max<size_t>((size_t)n + (size_t)n / 4, 1u << 20);
+        if (cudaHostAlloc(&c.h_buf, want, cudaHostAllocDefault) != cudaSuccess) return FN3_ENOMEM;
+        if (cudaMalloc(&c.d_buf, want) != cudaSuccess) return FN3_ENOMEM;
+        c.cap = want;
+    }
+    memcpy(c.h_buf, bytes, (size_t)n);
+    if (cudaMemcpyAsync(c.d_buf, c.h_buf, (size_t)n, cudaMemcpyHostToDevice, c.st) != cudaSuccess) return FN3_ECUDA;
+    if (cudaMemsetAsync(c.d_hist, 0, 256 * sizeof(unsigned long long), c.st) != cudaSuccess) return FN3_ECUDA;
+    const long long chunks = (n + 16ll * FN3_HIST_THREADS - 1) / (16ll * FN3_HIST_THREADS);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(chunks, (long long)c.sm_count * 8));
+    k_byte_hist<<<grid, FN3_HIST_THREADS, 0, c.st>>>(c.d_buf, n, c.d_hist);
+    if (cudaGetLastError() != cudaSuccess) return FN3_ECUDA;
+    if (cudaMemcpyAsync(c.h_hist, c.d_hist, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return FN3_ECUDA;
+    if (cudaStreamSynchronize(c.st) != cudaSuccess) return FN3_ECUDA;
+    for (int b = 0; b < 256; ++b) hist[b] = (int64_t)c.h_hist[b];
     return FN3_OK;
 }
 

@@ -47,6 +47,17 @@ def _take(buf, n):
     return buf.view(np.uint8)[: n * isz].copy().view(buf.dtype)
 
 
+def byte_histogram(data, device=0):
+    """NucleicAcid.examine's character counts on the device (fn3_byte_histogram): bytes -> int64[256]."""
+    lib = N.load()
+    hist = np.zeros(256, dtype=np.int64)
+    buf = np.frombuffer(data, dtype=np.uint8)
+    rc = lib.fn3_byte_histogram(int(device), buf.ctypes.data if buf.size else None, buf.size, hist.ctypes.data)
+    if rc != N.FN3_OK:
+        raise EngineError("fn3_byte_histogram failed (%d): no usable CUDA device? There is no CPU path." % rc)
+    return hist
+
+
 class Engine:
     def __init__(self, genome_length, device=0):
         self._lib = N.load()
@@ -210,6 +221,36 @@ class Engine:
             self._n_rows = max(self._n_rows, row.value + 1)
         self._check(rc)
         return row.value, _take(buf, n_out.value)
+
+    def ingest_query(self, seq_bytes, max_ns, ceiling, want_hist=True):
+        """findNeighbour3.insert()'s data path in one ABI call (fn3_ingest_query): composition histogram + compress +
+        maxNs decision + persist + mcompare from one host->device copy of the sequence.
+        -> (row, invalid, pos int32[], off int32[7], m_chars bytes, survivors, hist int64[256] or None)."""
+        if len(seq_bytes) != self.genome_length:
+            raise ValueError("sequence length differs from the engine's genome length")
+        off = np.zeros(7, dtype=np.int32)
+        hist = np.zeros(256, dtype=np.int64) if want_hist else None
+        npos, row, n_out, invalid = C.c_int64(0), C.c_int64(-1), C.c_int64(0), C.c_int32(0)
+        buf = self._hit_buf(max(self._n_rows + 1, 1))
+        cap = int(max_ns) if max_ns < (1 << 62) else (1 << 62)
+        while True:
+            rc = self._lib.fn3_ingest_query(self._h, seq_bytes, cap, int(ceiling), _ptr(hist), _ptr(self._cpos), self._cpos.size,
+                                            _ptr(off), self._cm, len(self._cm), C.byref(npos), C.byref(invalid),
+                                            C.byref(row), self._hits_ptr, buf.size, C.byref(n_out))
+            if rc == N.FN3_ECAPACITY and row.value < 0:                 # the compress step ran out of room: nothing stored
+                n_m = int(off[6] - off[5])
+                if npos.value > self._cpos.size:
+                    self._cpos = np.empty(int(npos.value) * 2, dtype=np.int32)
+                if n_m > len(self._cm):
+                    self._cm = C.create_string_buffer(n_m * 2)
+                continue
+            break
+        if row.value >= 0:
+            self._n_rows = max(self._n_rows, row.value + 1)
+        self._check(rc)
+        n_m = int(off[6] - off[5])
+        return (row.value, bool(invalid.value), self._cpos[: npos.value].copy(), off, self._cm.raw[:n_m],
+                _take(buf, n_out.value), hist)
 
     def lists_vs_all(self, pos, off, invalid, ceiling, rows=None):
         rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)

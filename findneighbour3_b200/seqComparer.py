@@ -42,6 +42,14 @@ class _LazyPickle:
         self.invalid = invalid
 
 
+class _LazyLists:
+    """a sample inserted through insert_sequence(): still the packed lists the device returned; becomes a dict on first access"""
+    __slots__ = ("pos", "off", "m_chars", "invalid")
+
+    def __init__(self, pos, off, m_chars, invalid):
+        self.pos, self.off, self.m_chars, self.invalid = pos, off, m_chars, invalid
+
+
 class _Profile(MutableMapping):
     """`seqProfile`: guid -> sample dict.  Assignments and deletions keep the device store in step.
     Samples loaded by persist_pickles() stay pickled until somebody asks for their dict."""
@@ -54,6 +62,9 @@ class _Profile(MutableMapping):
         v = self._d[k]
         if type(v) is _LazyPickle:
             v = pickle.loads(v.blob)
+            self._d[k] = v
+        elif type(v) is _LazyLists:
+            v = self._owner._dict_from_lists(v.pos, v.off, v.m_chars, v.invalid)
             self._d[k] = v
         return v
 
@@ -253,7 +264,7 @@ class seqComparer():
     def _stored_kind(self, guid):
         """'invalid' | 'compressed' | 'patch' for a stored guid, without unpickling a lazily loaded sample"""
         v = self.seqProfile._d[guid]
-        if type(v) is _LazyPickle:
+        if type(v) is _LazyPickle or type(v) is _LazyLists:
             return 'invalid' if v.invalid else 'compressed'
         if 'invalid' in v and v['invalid'] == 1:
             return 'invalid'
@@ -335,14 +346,48 @@ class seqComparer():
         # one byte per character; anything outside latin-1 becomes '?', which (like every non-ACGTN-
         # character) is a mixed base; its real character is read back from `sequence` below (:296-298)
         pos, off, _ = eng.compress(sequence.encode('latin-1', 'replace'))
-        if int(off[6] - off[4]) > self.maxNs:                      # len(N) + len(M) > maxNs (:301)
+        invalid = int(off[6] - off[4]) > self.maxNs                # len(N) + len(M) > maxNs (:301)
+        return self._dict_from_lists(pos, off, [sequence[p] for p in pos[off[5]:off[6]].tolist()], invalid)
+
+    def _dict_from_lists(self, pos, off, m_chars, invalid):
+        """the device's six sorted lists -> the reference's compressed_sequence dict (:290-305)"""
+        if invalid:
             return {'invalid': 1}
         out = {'invalid': 0}
         for i, b in enumerate('ACGT'):
             out[b] = set(pos[off[i]:off[i + 1]].tolist())
         out['N'] = set(pos[off[4]:off[5]].tolist())
-        out['M'] = {p: sequence[p] for p in pos[off[5]:off[6]].tolist()}
+        out['M'] = dict(zip(pos[off[5]:off[6]].tolist(), m_chars))
         return out
+
+    def insert_sequence(self, guid, sequence, cutoff=None):
+        """findNeighbour3.insert()'s data path (findNeighbour3-server.py:511-538) in ONE device call: the character
+        counts NucleicAcid.examine needs, compress (:274-307), the maxNs decision (:301), persist (:119-124) and the
+        one-vs-all of mcompare (:149-172) from a single host->device copy of `sequence` (fn3_ingest_query).
+
+        -> ({guid2: (dist, n1, n2, nboth)} for the neighbours within `cutoff` (default snpCeiling) among the samples
+        stored before, 256 byte counts of the sequence for `NucleicAcid.examine(sequence, histogram=...)`).
+        `seqProfile[guid]` / `load(guid)` build the sample's dict of sets only when somebody asks for it."""
+        if not len(sequence) == len(self.reference):
+            raise TypeError("sequence must of the same length as reference; seq is {0} and ref is {1}".format(
+                len(sequence), len(self.reference)))
+        if len(self.reference) == 0:
+            raise TypeError("reference cannot be of zero length")
+        if cutoff is None:
+            cutoff = self.snpCeiling
+        eng = self._engine_with_reference()
+        with self._lock:
+            if guid in self._row_of:
+                self._drop_row(guid)
+            row, invalid, pos, off, _, hits, hist = eng.ingest_query(sequence.encode('latin-1', 'replace'), self.maxNs,
+                                                                     self._ceil(cutoff))
+            self._row_of[guid] = row
+            self._guid_of[row] = guid
+            self._key_of[guid] = None                        # computed if the guid is ever persisted again
+            self.seqProfile._d[guid] = _LazyLists(pos, off, [sequence[p] for p in pos[off[5]:off[6]].tolist()], invalid)
+            gof = self._guid_of
+            found = {gof[int(h['row'])]: (int(h['dist']), int(h['n1']), int(h['n2']), int(h['nboth'])) for h in hits}
+        return found, hist
 
     def uncompress(self, compressed_sequence):
         """compressed (or patched) sample -> sequence string with N at excluded positions (:250-272)."""

@@ -57,7 +57,10 @@ class seqComparer(_seqComparer):
         pos, off, _ = eng.compress(sequence.encode('latin-1', 'replace'))
         if off[6] > off[5]:
             raise KeyError(sequence[int(pos[off[5]])])
-        if int(off[5] - off[4]) > self.maxNs:
+        return self._dict_from_lists(pos, off, [], int(off[5] - off[4]) > self.maxNs)
+
+    def _dict_from_lists(self, pos, off, m_chars, invalid):
+        if invalid:
             return {'invalid': 1}
         out = {}
         for i, b in enumerate('ACGT'):
@@ -65,6 +68,15 @@ class seqComparer(_seqComparer):
         out['N'] = set(pos[off[4]:off[5]].tolist())
         out['invalid'] = 0
         return out
+
+    def insert_sequence(self, guid, sequence, cutoff=None):
+        """as in the current class; a character outside ACGTN- raises KeyError like compress() and stores nothing"""
+        found, hist = super().insert_sequence(guid, sequence, self.snpCeiling if cutoff is None else cutoff)
+        v = self.seqProfile._d[guid]
+        if v.off[6] > v.off[5]:
+            self.remove(guid)
+            raise KeyError(sequence[int(v.pos[v.off[5]])])
+        return found, hist
 
     def uncompress(self, compressed_sequence):
         """(:440-456)"""

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FN3_ABI_VERSION 3   /* 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align, fn3_unpickle_samples; 3: + fn3_msa_sites_rule */
+#define FN3_ABI_VERSION 3   /* 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align, fn3_unpickle_samples; 3: + fn3_msa_sites_rule, fn3_ingest_query, fn3_byte_histogram */
 
 /* status codes */
 #define FN3_OK          0
@@ -191,6 +191,26 @@ int fn3_set_reference(fn3_engine* e, const char* reference, const int32_t* exclu
  * taken here (the caller applies :301). */
 int fn3_compress(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_cap,
                  int32_t off[7], char* m_chars, int64_t m_cap, int64_t* n_pos);
+
+/* findNeighbour3.insert()'s data path in ONE call (src/findNeighbour3-server.py:511-530): the
+ * character counts of NucleicAcid.examine (src/NucleicAcid.py:50-58), compress (:274-307), the maxNs decision (:301),
+ * persist (:119-124) and mcompare (:149-172) from one host->device copy of `sequence` (len = genome_length, already
+ * upper-cased as examine leaves it, NucleicAcid.py:35).
+ *   hist     256 counts, one per byte value of the sequence, or NULL (the caller derives composition['A'] ... from it)
+ *   pos/off/m_chars/n_pos  the compressed sample as fn3_compress returns it (the server stores it in MongoDB, :547)
+ *   *invalid 1 if len(N)+len(M) > max_ns: the sample is stored as {'invalid':1} and has no neighbours
+ *   *out_row, out[0..*n_out)  as fn3_insert_query
+ * FN3_ECAPACITY from the compress step (pos / m_chars too small; *n_pos = required) stores NOTHING: call again with
+ * room.  FN3_ECAPACITY from the query step (out too small; *n_out = required) has stored the row: fetch the
+ * neighbours with fn3_one_vs_all(*out_row). */
+int fn3_ingest_query(fn3_engine* e, const char* sequence, int64_t max_ns, int32_t ceiling, int64_t* hist,
+                     int32_t* pos, int64_t pos_cap, int32_t off[7], char* m_chars, int64_t m_cap, int64_t* n_pos,
+                     int32_t* invalid, int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out);
+
+/* The character counts of NucleicAcid.examine (src/NucleicAcid.py:50-58: eighteen bytes.count() passes) as one device
+ * pass: hist[b] = number of bytes of value b in bytes[0..n).  No engine needed (the reference's NucleicAcid() takes no
+ * arguments); FN3_ECUDA without a usable device — there is no CPU path. */
+int fn3_byte_histogram(int32_t device, const uint8_t* bytes, int64_t n, int64_t hist[256]);
 
 /* ---- cluster statistics on the device ------------------- */
 

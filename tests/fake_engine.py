@@ -127,6 +127,13 @@ class OracleEngine:
         pos = np.array([p for lst in lists for p in lst], dtype=np.int32)
         return pos, off, "".join(d["M"][p] for p in lists[5]).encode("latin-1")
 
+    def ingest_query(self, seq_bytes, max_ns, ceiling, want_hist=True):
+        pos, off, m_chars = self.compress(seq_bytes)
+        invalid = int(off[6] - off[4]) > max_ns
+        row, hits = self.insert_query(pos, off, invalid, ceiling)
+        hist = np.bincount(np.frombuffer(seq_bytes, np.uint8), minlength=256).astype(np.int64) if want_hist else None
+        return row, invalid, pos, off, m_chars, hits, hist
+
     def _dict_of(self, row):
         p, o, bad = self.samples[row]
         if bad:

@@ -17,6 +17,8 @@ Files
   msa.json            multi_sequence_alignment outputs on the reference's own test families (tests 45a-47c)
   cluster.json        consensus votes, _msa sites / aligned strings / N-M tallies and estimate_expected_unk_sites on
                       the collection of collection.json (`--cluster` regenerates only this file)
+  nucleic.json        NucleicAcid.examine (src/NucleicAcid.py, unmodified): composition dicts / exception types
+                      (`--nucleic` regenerates only this file)
   mt.json             the older threaded class (src/seqComparer_mt.py, unmodified) on the same collection without its
                       M lists: compress, both mcompare conventions, consensus / patches / recompression, the
                       three-test MSA and estimate_expected_N[_sites] (`--mt` regenerates only this file)
@@ -520,7 +522,35 @@ def make_mt():
     dump("mt.json", out)
 
 
+def make_nucleic():
+    """NucleicAcid.examine of the unmodified reference: composition (key order kept, examinationDate dropped), isValid,
+    the cleaned string's length — or the exception type it raises."""
+    NA = ref_shim.load_reference_module("NucleicAcid")
+    rnd = random.Random(5)
+    cases = ["ACGT", "ACGTN-", "ACGTN-X", "", "AACCCGT", "AAAN", "acgtn-rykmsw", "RYSWKMryswkm", "ACGT" * 1000 + "NN--",
+             "A", "-", "nnnn", "ACGU", "AC GT", "ACGT\n", "ÀCGT", "ACGß", 35, None,
+             "".join(rnd.choice("ACGT") for _ in range(4099)) + "".join(rnd.choice("ACGTN-RYKMSWacgtn") for _ in range(333)),
+             "".join(rnd.choice("ACGTNX*") for _ in range(257))]
+    out = []
+    for c in cases:
+        na = NA.NucleicAcid()
+        rec = {"input": c}
+        try:
+            na.examine(c)
+        except Exception as ex:
+            rec["raises"] = type(ex).__name__
+        comp = dict(na.composition)
+        comp.pop("examinationDate")
+        rec.update({"composition": comp, "keys": list(na.composition.keys()), "isValid": na.isValid, "nchars": na.nchars,
+                    "cleaned": None if na.nucleicAcidString is None else na.nucleicAcidString.decode("utf-8")})
+        out.append(rec)
+    dump("nucleic.json", out)
+
+
 if __name__ == "__main__":
+    if "--nucleic" in sys.argv:
+        make_nucleic()
+        sys.exit(0)
     if "--mt" in sys.argv:
         make_mt()
         sys.exit(0)
@@ -535,3 +565,4 @@ if __name__ == "__main__":
     make_consensus()
     make_cluster()
     make_mt()
+    make_nucleic()

@@ -1330,6 +1330,8 @@ extern "C" int fn3_set_reference(fn3_engine* e, const char* reference, const int
     return FN3_OK;
 }
 
+#define FN3_STAGE_PIECE ((size_t)1 << 20)
+
 // compress() proper (ingest_mu held): sequence -> device lists -> caller's buffers; optionally the byte histogram of the
 // same device copy of the sequence (hist: 256 counts, or NULL)
 static int compress_locked(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_cap, int32_t off[7],
@@ -1337,8 +1339,12 @@ static int compress_locked(fn3_engine* e, const char* sequence, int32_t* pos, in
     if (!e->d_refmask) return set_err(e, FN3_EARG, "%s: call fn3_set_reference first", who);
     CU(e, cudaSetDevice(e->device));
     cudaStream_t st = e->in_stream;
-    memcpy(e->h_seq, sequence, (size_t)e->L);
-    CU(e, cudaMemcpyAsync(e->d_seq, e->h_seq, (size_t)e->L, cudaMemcpyHostToDevice, st));
+    // staged through pinned memory in 1 MB pieces: the DMA of one piece runs under the host copy of the next
+    for (size_t o = 0; o < (size_t)e->L; o += FN3_STAGE_PIECE) {
+        const size_t n = std::min<size_t>(FN3_STAGE_PIECE, (size_t)e->L - o);
+        memcpy(e->h_seq + o, sequence + o, n);
+        CU(e, cudaMemcpyAsync(e->d_seq + o, e->h_seq + o, n, cudaMemcpyHostToDevice, st));
+    }
     e->h2d_bytes += e->L;
     k_compress_count<<<e->cmp_ctas, FN3_CMP_THREADS, 0, st>>>(e->d_seq, e->d_refmask, e->d_ccounts);
     k_compress_scan<<<1, 32, 0, st>>>(e->d_ccounts, e->d_ctotals, e->cmp_ctas);
@@ -1449,8 +1455,11 @@ extern "C" int fn3_byte_histogram(int32_t device, const uint8_t* bytes, int64_t 
         if (cudaMalloc(&c.d_buf, want) != cudaSuccess) return FN3_ENOMEM;
         c.cap = want;
     }
-    memcpy(c.h_buf, bytes, (size_t)n);
-    if (cudaMemcpyAsync(c.d_buf, c.h_buf, (size_t)n, cudaMemcpyHostToDevice, c.st) != cudaSuccess) return FN3_ECUDA;
+    for (size_t o = 0; o < (size_t)n; o += FN3_STAGE_PIECE) {
+        const size_t m = std::min<size_t>(FN3_STAGE_PIECE, (size_t)n - o);
+        memcpy(c.h_buf + o, bytes + o, m);
+        if (cudaMemcpyAsync(c.d_buf + o, c.h_buf + o, m, cudaMemcpyHostToDevice, c.st) != cudaSuccess) return FN3_ECUDA;
+    }
     if (cudaMemsetAsync(c.d_hist, 0, 256 * sizeof(unsigned long long), c.st) != cudaSuccess) return FN3_ECUDA;
     const long long chunks = (n + 16ll * FN3_HIST_THREADS - 1) / (16ll * FN3_HIST_THREADS);
     const int grid = (int)std::max<long long>(1, std::min<long long>(chunks, (long long)c.sm_count * 8));

@@ -283,14 +283,8 @@ def run_allvsall(args, rank, world, local, barrier, max_over_ranks, sum_over_ran
     n_anc = max(world, args.samples // max_c)
     mine = list(range(rank, n_anc, world))
     t0 = time.time()
-    parts = [synth.make_collection(1, max_c, seed=300000 + a, excluded=_mask()) for a in mine]
-    pos = np.concatenate([c.pos for c in parts])
-    offs, total = [np.zeros(1, np.int64)], 0
-    for c in parts:
-        offs.append(total + c.off[1:])
-        total += int(c.off[-1])
-    off = np.concatenate(offs)
-    inv = np.concatenate([c.invalid for c in parts])
+    part = synth.make_families([300000 + a for a in mine], max_c, workers=max(1, (os.cpu_count() or 1) // world))
+    pos, off, inv = part.pos, part.off, part.invalid
     eng = Engine(synth.TB_LENGTH, local)
     if world == 1:
         eng.append_bulk(pos, off, inv)

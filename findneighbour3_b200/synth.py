@@ -210,6 +210,42 @@ def make_collection(n_anc, max_c, genome_length=TB_LENGTH, k1=500, s=3.0, n_bloc
     return Collection(genome_length, pos, off, invalid, family)
 
 
+def _families_task(task):
+    seeds, max_c, tb_mask = task
+    mask = synthetic_mask(TB_LENGTH, TB_EXCLUDED, TB_EXCLUDED_RUNS) if tb_mask else None
+    parts = [make_collection(1, max_c, seed=int(sd), excluded=mask) for sd in seeds]
+    return (np.concatenate([c.pos for c in parts]), np.concatenate([np.diff(c.off) for c in parts]),
+            np.concatenate([c.invalid for c in parts]))
+
+
+def make_families(seeds, max_c, workers=None, tb_mask=True):
+    """One TB-shaped family per seed — make_collection(1, max_c, seed=seed), the collection BASELINE configs[2] is built
+    from — concatenated in seed order, generated by a pool of processes (the generator is single-threaded numpy:
+    200 000 samples take minutes on one core).  -> Collection; family f holds the samples of seeds[f]."""
+    import multiprocessing
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    seeds = [int(x) for x in seeds]
+    workers = max(1, min(workers or (os.cpu_count() or 1), len(seeds)))
+    per = max(1, min(25, (len(seeds) + workers - 1) // workers))
+    tasks = [(seeds[i:i + per], max_c, tb_mask) for i in range(0, len(seeds), per)]
+    if workers == 1:
+        results = [_families_task(t) for t in tasks]
+    else:                                # spawn: the parent may hold a CUDA context, which must not be forked
+        try:
+            with ProcessPoolExecutor(max_workers=workers, mp_context=multiprocessing.get_context("spawn")) as pool:
+                results = list(pool.map(_families_task, tasks))
+        except Exception:                # e.g. a __main__ that cannot be re-imported (stdin, REPL): same result, one core
+            results = [_families_task(t) for t in tasks]
+    pos = np.concatenate([r[0] for r in results]) if results else np.empty(0, dtype=np.int32)
+    lens = np.concatenate([r[1] for r in results]) if results else np.empty(0, dtype=np.int64)
+    off = np.zeros(lens.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    invalid = np.concatenate([r[2] for r in results]) if results else np.empty(0, dtype=np.uint8)
+    family = np.repeat(np.arange(len(seeds), dtype=np.int32), max_c)
+    return Collection(TB_LENGTH, pos, off, invalid, family)
+
+
 def new_sample_like(coll, i, extra_snps, seed, rule="lss", ref_seed=962):
     """a 'newly sequenced' relative of sample i: its lists + `extra_snps` fresh substitutions (same N/M)."""
     rng = np.random.default_rng(seed)

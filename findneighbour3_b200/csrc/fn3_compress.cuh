@@ -62,14 +62,7 @@ __global__ void __launch_bounds__(FN3_CMP_THREADS) k_compress_count(const uint8_
     }
 }
 
-// exclusive scan over CTAs, per class; totals[6] receives the list lengths
-__global__ void k_compress_scan(uint32_t* __restrict__ counts, uint32_t* __restrict__ totals, int ncta) {
-    const int c = threadIdx.x;
-    if (c >= 6) return;
-    uint32_t acc = 0;
-    for (int i = 0; i < ncta; ++i) { const uint32_t v = counts[(long long)i * 6 + c]; counts[(long long)i * 6 + c] = acc; acc += v; }
-    totals[c] = acc;
-}
+// (the exclusive scan of the per-CTA counts, per class, is k_sel_scan of fn3_cluster.cuh: same counts[cta * NL + l] layout)
 
 __global__ void __launch_bounds__(FN3_CMP_THREADS) k_compress_write(const uint8_t* __restrict__ seq,
                                                                      const uint8_t* __restrict__ refmask,

@@ -6,6 +6,7 @@ exactly one C entry point; errors become the exception classes the reference's A
 (SURVEY.md §8(b)): FN3_EARG -> ValueError, FN3_ENOTFOUND -> KeyError, the rest -> RuntimeError.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -69,7 +70,14 @@ class Engine:
         self.device = int(device)
         self._hits = np.empty(4096, dtype=HIT_DTYPE)
         self._edges = np.empty(1 << 16, dtype=EDGE_DTYPE)
+        self._cpos = np.empty(1 << 16, dtype=np.int32)
+        self._cm = C.create_string_buffer(1 << 12)
         self._n_rows = 0          # rows appended through this object (sizes the hit buffer without an ABI call)
+        # the result buffers below are reused from call to call: calls that fill them are serialised per Engine object
+        # (the library serialises queries on its own mutex anyway, so no concurrency is lost).  Appends and removals
+        # take no Python lock and run concurrently with queries, as the server needs (SURVEY.md §8(b) "Threading").
+        self._q_lock = threading.Lock()       # _hits, _edges
+        self._c_lock = threading.Lock()       # _cpos, _cm (compress outputs); taken before _q_lock
 
     # -- plumbing -------------------------------------------------------------------------
     def close(self):
@@ -162,28 +170,27 @@ class Engine:
         if excluded is not None and len(excluded) > 0:
             ex = np.sort(np.fromiter(excluded, dtype=np.int64, count=len(excluded))).astype(np.int32)
         self._check(self._lib.fn3_set_reference(self._h, ref, _ptr(ex, _i32p), 0 if ex is None else ex.size))
-        self._cpos = np.empty(1 << 16, dtype=np.int32)
-        self._cm = C.create_string_buffer(1 << 12)
 
     def compress(self, seq_bytes):
         """device compress of one sequence (bytes, len = genome length) -> (pos int32[], off int32[7], m_chars bytes)."""
-        if len(seq_bytes) != self.genome_length:
-            raise ValueError("sequence length differs from the engine's genome length")
-        off = np.zeros(7, dtype=np.int32)
-        npos = C.c_int64(0)
-        while True:
-            rc = self._lib.fn3_compress(self._h, seq_bytes, _ptr(self._cpos, _i32p), self._cpos.size,
-                                        _ptr(off, _i32p), self._cm, len(self._cm), C.byref(npos))
-            if rc == N.FN3_ECAPACITY:
+        with self._c_lock:
+            if len(seq_bytes) != self.genome_length:
+                raise ValueError("sequence length differs from the engine's genome length")
+            off = np.zeros(7, dtype=np.int32)
+            npos = C.c_int64(0)
+            while True:
+                rc = self._lib.fn3_compress(self._h, seq_bytes, _ptr(self._cpos, _i32p), self._cpos.size,
+                                            _ptr(off, _i32p), self._cm, len(self._cm), C.byref(npos))
+                if rc == N.FN3_ECAPACITY:
+                    n_m = int(off[6] - off[5])
+                    if npos.value > self._cpos.size:
+                        self._cpos = np.empty(int(npos.value) * 2, dtype=np.int32)
+                    if n_m > len(self._cm):
+                        self._cm = C.create_string_buffer(n_m * 2)
+                    continue
+                self._check(rc)
                 n_m = int(off[6] - off[5])
-                if npos.value > self._cpos.size:
-                    self._cpos = np.empty(int(npos.value) * 2, dtype=np.int32)
-                if n_m > len(self._cm):
-                    self._cm = C.create_string_buffer(n_m * 2)
-                continue
-            self._check(rc)
-            n_m = int(off[6] - off[5])
-            return self._cpos[: npos.value].copy(), off, self._cm.raw[:n_m]
+                return self._cpos[: npos.value].copy(), off, self._cm.raw[:n_m]
 
     # -- hot path -------------------------------------------------------------------------
     def _hit_buf(self, n):
@@ -196,31 +203,33 @@ class Engine:
 
     def one_vs_all(self, query_row, ceiling, rows=None):
         """mcompare: stored row vs all (or `rows`); -> structured array of survivors (copy)."""
-        rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
-        n_cand = self._n_rows if rows_a is None else rows_a.size
-        buf = self._hit_buf(max(int(n_cand), 1))
-        n_out = C.c_int64(0)
-        rc = self._lib.fn3_one_vs_all(self._h, int(query_row), int(ceiling), _ptr(rows_a, _i64p),
-                                      0 if rows_a is None else rows_a.size,
-                                      self._hits_ptr, buf.size, C.byref(n_out))
-        self._check(rc)
-        return _take(buf, n_out.value)
+        with self._q_lock:
+            rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+            n_cand = self._n_rows if rows_a is None else rows_a.size
+            buf = self._hit_buf(max(int(n_cand), 1))
+            n_out = C.c_int64(0)
+            rc = self._lib.fn3_one_vs_all(self._h, int(query_row), int(ceiling), _ptr(rows_a, _i64p),
+                                          0 if rows_a is None else rows_a.size,
+                                          self._hits_ptr, buf.size, C.byref(n_out))
+            self._check(rc)
+            return _take(buf, n_out.value)
 
     def insert_query(self, pos, off, invalid, ceiling):
         """persist + mcompare in one ABI call -> (row, structured array of survivors among the earlier rows)."""
-        buf = self._hit_buf(max(self._n_rows + 1, 1))
-        row = C.c_int64(-1)
-        n_out = C.c_int64(0)
-        if invalid:
-            pos_a, off_a = None, None
-        else:
-            pos_a, off_a = _as_i32(pos), _as_i32(off)
-        rc = self._lib.fn3_insert_query(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
-                                        int(ceiling), C.byref(row), self._hits_ptr, buf.size, C.byref(n_out))
-        if row.value >= 0:
-            self._n_rows = max(self._n_rows, row.value + 1)
-        self._check(rc)
-        return row.value, _take(buf, n_out.value)
+        with self._q_lock:
+            buf = self._hit_buf(max(self._n_rows + 1, 1))
+            row = C.c_int64(-1)
+            n_out = C.c_int64(0)
+            if invalid:
+                pos_a, off_a = None, None
+            else:
+                pos_a, off_a = _as_i32(pos), _as_i32(off)
+            rc = self._lib.fn3_insert_query(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
+                                            int(ceiling), C.byref(row), self._hits_ptr, buf.size, C.byref(n_out))
+            if row.value >= 0:
+                self._n_rows = max(self._n_rows, row.value + 1)
+            self._check(rc)
+            return row.value, _take(buf, n_out.value)
 
     def ingest_query(self, seq_bytes, max_ns, ceiling, want_hist=True):
         """findNeighbour3.insert()'s data path in one ABI call (fn3_ingest_query): composition histogram + compress +
@@ -228,59 +237,62 @@ class Engine:
         -> (row, invalid, pos int32[], off int32[7], m_chars bytes, survivors, hist int64[256] or None)."""
         if len(seq_bytes) != self.genome_length:
             raise ValueError("sequence length differs from the engine's genome length")
-        off = np.zeros(7, dtype=np.int32)
-        hist = np.zeros(256, dtype=np.int64) if want_hist else None
-        npos, row, n_out, invalid = C.c_int64(0), C.c_int64(-1), C.c_int64(0), C.c_int32(0)
-        buf = self._hit_buf(max(self._n_rows + 1, 1))
-        cap = int(max_ns) if max_ns < (1 << 62) else (1 << 62)
-        while True:
-            rc = self._lib.fn3_ingest_query(self._h, seq_bytes, cap, int(ceiling), _ptr(hist), _ptr(self._cpos), self._cpos.size,
-                                            _ptr(off), self._cm, len(self._cm), C.byref(npos), C.byref(invalid),
-                                            C.byref(row), self._hits_ptr, buf.size, C.byref(n_out))
-            if rc == N.FN3_ECAPACITY and row.value < 0:                 # the compress step ran out of room: nothing stored
-                n_m = int(off[6] - off[5])
-                if npos.value > self._cpos.size:
-                    self._cpos = np.empty(int(npos.value) * 2, dtype=np.int32)
-                if n_m > len(self._cm):
-                    self._cm = C.create_string_buffer(n_m * 2)
-                continue
-            break
-        if row.value >= 0:
-            self._n_rows = max(self._n_rows, row.value + 1)
-        self._check(rc)
-        n_m = int(off[6] - off[5])
-        return (row.value, bool(invalid.value), self._cpos[: npos.value].copy(), off, self._cm.raw[:n_m],
-                _take(buf, n_out.value), hist)
+        with self._c_lock, self._q_lock:
+            off = np.zeros(7, dtype=np.int32)
+            hist = np.zeros(256, dtype=np.int64) if want_hist else None
+            npos, row, n_out, invalid = C.c_int64(0), C.c_int64(-1), C.c_int64(0), C.c_int32(0)
+            buf = self._hit_buf(max(self._n_rows + 1, 1))
+            cap = int(max_ns) if max_ns < (1 << 62) else (1 << 62)
+            while True:
+                rc = self._lib.fn3_ingest_query(self._h, seq_bytes, cap, int(ceiling), _ptr(hist), _ptr(self._cpos), self._cpos.size,
+                                                _ptr(off), self._cm, len(self._cm), C.byref(npos), C.byref(invalid),
+                                                C.byref(row), self._hits_ptr, buf.size, C.byref(n_out))
+                if rc == N.FN3_ECAPACITY and row.value < 0:                 # the compress step ran out of room: nothing stored
+                    n_m = int(off[6] - off[5])
+                    if npos.value > self._cpos.size:
+                        self._cpos = np.empty(int(npos.value) * 2, dtype=np.int32)
+                    if n_m > len(self._cm):
+                        self._cm = C.create_string_buffer(n_m * 2)
+                    continue
+                break
+            if row.value >= 0:
+                self._n_rows = max(self._n_rows, row.value + 1)
+            self._check(rc)
+            n_m = int(off[6] - off[5])
+            return (row.value, bool(invalid.value), self._cpos[: npos.value].copy(), off, self._cm.raw[:n_m],
+                    _take(buf, n_out.value), hist)
 
     def lists_vs_all(self, pos, off, invalid, ceiling, rows=None):
-        rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
-        n_cand = self._n_rows if rows_a is None else rows_a.size
-        buf = self._hit_buf(max(int(n_cand), 1))
-        n_out = C.c_int64(0)
-        if invalid:
-            pos_a, off_a = None, None
-        else:
-            pos_a, off_a = _as_i32(pos), _as_i32(off)
-        rc = self._lib.fn3_lists_vs_all(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
-                                        int(ceiling), _ptr(rows_a, _i64p), 0 if rows_a is None else rows_a.size,
-                                        self._hits_ptr, buf.size, C.byref(n_out))
-        self._check(rc)
-        return _take(buf, n_out.value)
+        with self._q_lock:
+            rows_a = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+            n_cand = self._n_rows if rows_a is None else rows_a.size
+            buf = self._hit_buf(max(int(n_cand), 1))
+            n_out = C.c_int64(0)
+            if invalid:
+                pos_a, off_a = None, None
+            else:
+                pos_a, off_a = _as_i32(pos), _as_i32(off)
+            rc = self._lib.fn3_lists_vs_all(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
+                                            int(ceiling), _ptr(rows_a, _i64p), 0 if rows_a is None else rows_a.size,
+                                            self._hits_ptr, buf.size, C.byref(n_out))
+            self._check(rc)
+            return _take(buf, n_out.value)
 
     def all_vs_all(self, ceiling, upper_only=True, row_begin=0, row_end=None, stride=1, phase=0):
         """distmat over the block rows this caller owns -> structured array of edges (copy)."""
-        if row_end is None:
-            row_end = self.stats()["n_rows"]
-        n_out = C.c_int64(0)
-        buf = self._edges
-        rc = self._lib.fn3_all_vs_all(self._h, int(ceiling), 1 if upper_only else 0, int(row_begin), int(row_end),
-                                      int(stride), int(phase), buf.ctypes.data_as(C.POINTER(N.Edge)), buf.size,
-                                      C.byref(n_out))
-        if rc == N.FN3_ECAPACITY:                 # the edges are still on the device: fetch, do not recompute
-            buf = self._edges = np.empty(int(n_out.value), dtype=EDGE_DTYPE)
-            rc = self._lib.fn3_all_vs_all_fetch(self._h, buf.ctypes.data_as(C.POINTER(N.Edge)), buf.size, C.byref(n_out))
-        self._check(rc)
-        return buf[: n_out.value].copy()
+        with self._q_lock:
+            if row_end is None:
+                row_end = self.stats()["n_rows"]
+            n_out = C.c_int64(0)
+            buf = self._edges
+            rc = self._lib.fn3_all_vs_all(self._h, int(ceiling), 1 if upper_only else 0, int(row_begin), int(row_end),
+                                          int(stride), int(phase), buf.ctypes.data_as(C.POINTER(N.Edge)), buf.size,
+                                          C.byref(n_out))
+            if rc == N.FN3_ECAPACITY:                 # the edges are still on the device: fetch, do not recompute
+                buf = self._edges = np.empty(int(n_out.value), dtype=EDGE_DTYPE)
+                rc = self._lib.fn3_all_vs_all_fetch(self._h, buf.ctypes.data_as(C.POINTER(N.Edge)), buf.size, C.byref(n_out))
+            self._check(rc)
+            return buf[: n_out.value].copy()
 
     def pair(self, row1, row2, ceiling):
         """countDifferences_byKey on stored rows -> (dist,n1,n2,nboth) or None."""

@@ -168,6 +168,58 @@ def test_byte_histogram_on_the_device():
         assert byte_histogram(ch * 100003)[ch[0]] == 100003
 
 
+def _check_concurrent_compress():
+    """compress() and insert_sequence() from several request threads at once (the server compresses outside its write
+    semaphore, findNeighbour3-server.py:513): every thread gets its own sample back, not another thread's buffer"""
+    import threading
+    from findneighbour3_b200.seqComparer import seqComparer
+    rng = np.random.default_rng(21)
+    L = 20000
+    ref = "".join(rng.choice(list("ACGT"), size=L))
+    sc = seqComparer(reference=ref, maxNs=L, snpCeiling=20)
+    seqs = []
+    for t in range(6):
+        s = np.frombuffer(ref.encode(), dtype=np.uint8).copy()
+        at = rng.choice(L, size=50 + 400 * t, replace=False)
+        s[at] = rng.choice(np.frombuffer(b"ACGTNR", np.uint8), size=at.size)
+        seqs.append(s.tobytes().decode())
+    want = [sc.compress(s) for s in seqs]
+    errors = []
+
+    def work(t):
+        try:
+            for rep in range(8):
+                assert sc.compress(seqs[t]) == want[t]
+                sc.insert_sequence("t%d_%d" % (t, rep), seqs[t])
+                assert sc.seqProfile["t%d_%d" % (t, rep)] == want[t]
+        except Exception as ex:          # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]
+    assert len(sc.guidscachedinram()) == 48
+    for t in range(6):                                       # the eight copies of a sample find each other at distance 0
+        got = sc.neighbours("t%d_0" % t)
+        assert sum(1 for g, v in got.items() if g.startswith("t%d_" % t) and v[0] == 0) == 7
+    sc.engine.close()
+
+
+def test_concurrent_compress_host_layer(monkeypatch):
+    import findneighbour3_b200.seqComparer as base
+    from fake_engine import OracleEngine
+    monkeypatch.setattr(base, "Engine", lambda genome_length, device=0: OracleEngine(genome_length))
+    _check_concurrent_compress()
+
+
+@pytest.mark.gpu
+def test_concurrent_compress_on_the_device():
+    _check_concurrent_compress()
+
+
 @pytest.mark.gpu
 def test_nucleic_acid_golden_on_the_device():
     _check_nucleic_golden()

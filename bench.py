@@ -259,8 +259,12 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_used / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "configs[1]: one-vs-all over a synthetic TB collection, snpCeiling %d" % args.ceiling,
-                       "candidates_per_step": m, "genome_length": coll.genome_length},
+            "config": {"workload": "configs[1]: 50,000 synthetic TB sequences per GPU, one new-sample one-vs-all query "
+                                   "per step, snpCeiling %d" % args.ceiling,
+                       "samples_per_gpu": int(args.samples), "genome_length": int(coll.genome_length),
+                       "candidates_per_step": m,
+                       "sample": "each step compares the query with a bounded sample of %d of the shard's candidates "
+                                 "(the reference's cost is linear in the candidates)" % m},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "host_cpus": os.cpu_count()}

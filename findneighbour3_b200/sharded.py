@@ -23,6 +23,8 @@ import torch
 import torch.distributed as dist
 
 HIT_FIELDS = 5          # row, dist, n1, n2, nboth
+HDR = 16                # header words of the sample message: n, off[0..6], invalid, ctl[0..2] (op, ceiling, argument), spare
+OP_INSERT, OP_QUERY, OP_REMOVE, OP_STOP = 1, 2, 3, 4     # ctl[0] of a served round (ShardedSeqComparer); 0 = caller knows
 
 
 class ShardedStore:
@@ -35,13 +37,13 @@ class ShardedStore:
         self.dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         self.max_hits = int(max_hits)
         self.bcast_cap = 1 << 13                 # positions carried by the single fixed-size broadcast (32 KB)
-        self._bbuf = torch.zeros(9 + self.bcast_cap, dtype=torch.int32)
+        self._bbuf = torch.zeros(HDR + self.bcast_cap, dtype=torch.int32)
         self._hblk = torch.zeros(1 + HIT_FIELDS * self.max_hits, dtype=torch.int32)
         self._dbuf = self._dhblk = self._dhall = self._hhall = None
         if self.dev.type == "cuda":
             self._bbuf = self._bbuf.pin_memory()
             self._hblk = self._hblk.pin_memory()
-            self._dbuf = torch.zeros(9 + self.bcast_cap, dtype=torch.int32, device=self.dev)
+            self._dbuf = torch.zeros(HDR + self.bcast_cap, dtype=torch.int32, device=self.dev)
             self._dhblk = torch.zeros(1 + HIT_FIELDS * self.max_hits, dtype=torch.int32, device=self.dev)
             self._dhall = torch.zeros(self.world * (1 + HIT_FIELDS * self.max_hits), dtype=torch.int32, device=self.dev)
             self._hhall = torch.zeros(self.world * (1 + HIT_FIELDS * self.max_hits), dtype=torch.int32).pin_memory()
@@ -94,20 +96,22 @@ class ShardedStore:
                 pass
             self._shm = None
 
-    def _shm_exchange(self, sample, src, compute):
-        """one insert/query round over shared memory: `src` publishes the sample, every rank runs `compute(pos, off,
-        invalid) -> hits` and publishes its records, every rank collects all slots."""
+    def _shm_exchange(self, sample, src, compute, ctl=(0, 0, 0)):
+        """one insert/query round over shared memory: `src` publishes the sample (+ three control words), every rank runs
+        `compute(pos, off, invalid, ctl) -> hits` and publishes its records, every rank collects all slots.
+        -> ({global id: (dist, n1, n2, nboth)}, ctl)"""
         self._seq += 1
         seq = self._seq
         s64, s32 = self._s64, self._s32
         if self.rank == src:
-            pos, off, invalid = sample
+            pos, off, invalid = sample if sample is not None else (None, None, True)
             n = 0 if invalid else len(pos)
             if n > self.bcast_cap:
                 raise ValueError("sample with %d positions exceeds the shared-memory exchange buffer (%d)" % (n, self.bcast_cap))
             s64[1] = n
             s64[2:9] = 0 if invalid else off
             s64[9] = 1 if invalid else 0
+            s64[10:13] = ctl
             if n:
                 s32[:n] = pos
             s64[0] = seq                          # publish (x86 TSO: earlier stores are visible first)
@@ -118,7 +122,8 @@ class ShardedStore:
         pos = s32[:n].copy()
         off = s64[2:9].astype(np.int32)
         invalid = bool(s64[9])
-        hits = compute(pos, off, invalid)
+        ctl = (int(s64[10]), int(s64[11]), int(s64[12]))
+        hits = compute(pos, off, invalid, ctl)
         m = len(hits)
         if m > self.max_hits:
             raise ValueError("%d neighbours exceed the shared-memory result slot (%d)" % (m, self.max_hits))
@@ -139,7 +144,7 @@ class ShardedStore:
                 rec = self._r32[r][: HIT_FIELDS * c].reshape(c, HIT_FIELDS)
                 gids = (rec[:, 0].astype(np.int64) * self.world + r).tolist()
                 out.update(zip(gids, map(tuple, rec[:, 1:].tolist())))
-        return out
+        return out, ctl
 
     # -- id mapping -------------------------------------------------------------------------
     def owner(self, gid):
@@ -165,22 +170,25 @@ class ShardedStore:
         return first
 
     # -- collectives ------------------------------------------------------------------------
-    def _bcast_sample(self, sample, src=0):
-        """`src`'s (pos, off, invalid) -> every rank, in ONE broadcast of a fixed-size buffer
-        [n, off[0..6], invalid | positions ...] (a second one only for samples beyond `self.bcast_cap`)."""
+    def _bcast_sample(self, sample, src=0, ctl=(0, 0, 0)):
+        """`src`'s (pos, off, invalid) and three control words -> every rank, in ONE broadcast of a fixed-size buffer
+        [n, off[0..6], invalid, ctl[0..2], spare | positions ...] (a second one only for samples beyond `self.bcast_cap`).
+        -> (pos, off, invalid, ctl)"""
         if self.world == 1:
-            return sample
+            pos, off, invalid = sample if sample is not None else (np.empty(0, np.int32), np.zeros(7, np.int32), True)
+            return pos, off, invalid, tuple(int(x) for x in ctl)
         cap = self.bcast_cap
         buf = self._bbuf_np                       # numpy view of the (pinned) staging tensor
         if self.rank == src:
-            pos, off, invalid = sample
+            pos, off, invalid = sample if sample is not None else (None, None, True)
             n = 0 if invalid else len(pos)
             buf[0] = n
             buf[1:8] = 0 if invalid else off
             buf[8] = 1 if invalid else 0
+            buf[9:12] = ctl
             m = min(n, cap)
             if m:
-                buf[9:9 + m] = pos[:m]
+                buf[HDR:HDR + m] = pos[:m]
         if self.dev.type == "cuda":
             self._dbuf.copy_(self._bbuf, non_blocking=True)
             dist.broadcast(self._dbuf, src=src, group=self.group)
@@ -191,7 +199,8 @@ class ShardedStore:
         n = int(buf[0])
         off = buf[1:8].astype(np.int32)
         invalid = bool(buf[8])
-        pos = buf[9:9 + min(n, cap)].copy()
+        ctl = (int(buf[9]), int(buf[10]), int(buf[11]))
+        pos = buf[HDR:HDR + min(n, cap)].copy()
         if n > cap:                               # rare: a sample larger than the fixed buffer
             rest = torch.zeros(n - cap, dtype=torch.int32)
             if self.rank == src:
@@ -199,7 +208,15 @@ class ShardedStore:
             rest = rest.to(self.dev)
             dist.broadcast(rest, src=src, group=self.group)
             pos = np.concatenate([pos, rest.cpu().numpy()])
-        return pos, off, invalid
+        return pos, off, invalid, ctl
+
+    def _exchange(self, sample, src, compute, ctl=(0, 0, 0)):
+        """one round on the configured transport: the sample and `ctl` go from `src` to every rank, every rank runs
+        `compute(pos, off, invalid, ctl) -> hits`, everybody receives all hits -> (dict, ctl)"""
+        if self.exchange == "shm":
+            return self._shm_exchange(sample, src, compute, ctl)
+        pos, off, invalid, ctl = self._bcast_sample(sample, src, ctl)
+        return self._gather_hits(compute(pos, off, invalid, ctl)), ctl
 
     def _all_gather_i64(self, t):
         if self.world == 1:
@@ -269,7 +286,7 @@ class ShardedStore:
         gid = self.n_global
         own = self.owner(gid) == self.rank
 
-        def compute(pos, off, invalid):
+        def compute(pos, off, invalid, ctl):
             if own:
                 row, hits = self.engine.insert_query(pos, off, invalid, ceiling)
                 assert row == self.local_row(gid) == self._local_rows, (row, gid, self._local_rows)
@@ -277,11 +294,7 @@ class ShardedStore:
                 return hits
             return self.engine.lists_vs_all(pos, off, invalid, ceiling)
 
-        if self.exchange == "shm":
-            out = self._shm_exchange(sample, 0, compute)
-        else:
-            pos, off, invalid = self._bcast_sample(sample)
-            out = self._gather_hits(compute(pos, off, invalid))
+        out, _ = self._exchange(sample, 0, compute)
         self.n_global += 1
         return gid, out
 
@@ -293,15 +306,12 @@ class ShardedStore:
         src = self.owner(gid)
         sample = self.engine.row_get(self.local_row(gid)) if own else None
 
-        def compute(pos, off, invalid):
+        def compute(pos, off, invalid, ctl):
             if own:
                 return self.engine.one_vs_all(self.local_row(gid), ceiling)
             return self.engine.lists_vs_all(pos, off, invalid, ceiling)
 
-        if self.exchange == "shm":
-            return self._shm_exchange(sample, src, compute)
-        pos, off, invalid = self._bcast_sample(sample, src=src)
-        return self._gather_hits(compute(pos, off, invalid))
+        return self._exchange(sample, src, compute)[0]
 
     # -- all-vs-all: replicated store, block rows by rank (no exchange until the final gather) ---
     @staticmethod
@@ -309,3 +319,125 @@ class ShardedStore:
         """row ownership for the upper triangle: row r belongs to rank r % world (rows are interleaved, so long
         and short rows — row r has n-r-1 pairs — are spread evenly)."""
         return dict(row_begin=0, row_end=n_rows, stride=world, phase=rank)
+
+
+class ShardedSeqComparer:
+    """Guid-level face of a ShardedStore for BASELINE configs[4] (a collection resident across the GPUs of one box,
+    streaming inserts each queried one-vs-all): the server process is rank 0 and calls insert / neighbours / mcompare /
+    remove with guids and the reference's sample dicts; every other rank runs serve().
+
+    Every call is ONE round of the store's exchange: rank 0 ships (operation, cut-off, sample lists) — it keeps the host
+    dict of every sample, as the reference's seqProfile does, so a query on a stored sample needs no hop through its
+    owner rank — every rank compares against its own shard, the thresholded neighbour records come back.
+    Samples are plain compressed_sequence dicts ({'invalid': 1} included); the double-delta form stays a host-RAM matter
+    of the single-GPU class."""
+
+    def __init__(self, store, snpCeiling):
+        self.store = store
+        self.snpCeiling = snpCeiling
+        self.seqProfile = {}                 # guid -> sample dict (rank 0)
+        self._gid_of = {}                    # guid -> global id (rank 0)
+        self._guid_of = {}                   # global id -> guid (rank 0)
+
+    # -- one round, all ranks ---------------------------------------------------------------
+    def _round(self, ctl=(0, 0, 0), sample=None):
+        st = self.store
+        gid_new = st.n_global
+
+        def compute(pos, off, invalid, c):
+            op, ceiling, arg = c
+            if op == OP_INSERT:
+                if st.owner(gid_new) == st.rank:
+                    row, hits = st.engine.insert_query(pos, off, invalid, ceiling)
+                    assert row == st.local_row(gid_new) == st._local_rows, (row, gid_new, st._local_rows)
+                    st._local_rows += 1
+                    return hits
+                return st.engine.lists_vs_all(pos, off, invalid, ceiling)
+            if op == OP_QUERY:
+                return st.engine.lists_vs_all(pos, off, invalid, ceiling)
+            if op == OP_REMOVE and st.owner(arg) == st.rank:
+                st.engine.remove(st.local_row(arg))
+            return np.zeros(0, dtype=[("row", "<i8"), ("dist", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("nboth", "<i4")])
+
+        hits, c = st._exchange(sample, 0, compute, ctl)
+        if c[0] == OP_INSERT:
+            st.n_global += 1
+        return hits, c
+
+    def serve(self):
+        """ranks >= 1: take part in every round until rank 0 calls shutdown()"""
+        while True:
+            _, c = self._round()
+            if c[0] == OP_STOP:
+                return
+
+    # -- rank 0 -----------------------------------------------------------------------------
+    @staticmethod
+    def _ceil(cutoff):
+        return max(-1, min(int(np.floor(cutoff)), 2 ** 31 - 1))
+
+    def _named(self, hits, skip=None):
+        return {self._guid_of[g]: v for g, v in hits.items() if g != skip and g in self._guid_of}
+
+    def insert(self, guid, obj, cutoff=None):
+        """persist + the one-vs-all of mcompare (findNeighbour3-server.py:516, :530) across all shards
+        -> {guid2: (dist, n1, n2, nboth)} for the samples stored before."""
+        from . import packing
+        if guid in self._gid_of:
+            self.remove(guid)
+        sample = packing.pack_compressed(obj)
+        gid = self.store.n_global
+        hits, _ = self._round((OP_INSERT, self._ceil(self.snpCeiling if cutoff is None else cutoff), 0), sample)
+        self._gid_of[guid] = gid
+        self._guid_of[gid] = guid
+        self.seqProfile[guid] = obj
+        return self._named(hits, skip=gid)
+
+    def neighbours(self, guid, cutoff=None):
+        """one stored sample against all shards -> {guid2: (dist, n1, n2, nboth)}"""
+        from . import packing
+        if guid not in self._gid_of:
+            raise KeyError("Asked to compare {0}  but guid requested has not been stored.".format(guid))
+        gid = self._gid_of[guid]
+        sample = packing.pack_compressed(self.seqProfile[guid])
+        hits, _ = self._round((OP_QUERY, self._ceil(self.snpCeiling if cutoff is None else cutoff), gid), sample)
+        return self._named(hits, skip=gid)                   # its own stored copy answers with distance 0: dropped
+
+    def mcompare(self, guid, guids=None):
+        """the reference's return shape (seqComparer.py:149-172): one 9-element list per other guid"""
+        found = self.neighbours(guid)
+        s1 = self.seqProfile[guid]
+        out = []
+        for key2 in (set(self.seqProfile.keys()) if guids is None else set(guids)):
+            if key2 == guid:
+                continue
+            if key2 not in self.seqProfile:
+                raise KeyError("Key1={0} does not exist in the in-memory store.".format(guid))
+            hit = found.get(key2)
+            if hit is None:
+                out.append([guid, key2, None, None, None, None, None, None, None])
+            else:
+                s2 = self.seqProfile[key2]
+                u1 = s1['N'] | set(s1['M'].keys())
+                u2 = s2['N'] | set(s1['M'].keys())           # sic (seqComparer.py:417)
+                out.append([guid, key2, hit[0], hit[1], hit[2], hit[3], u1, u2, u2 | u1])
+        return out
+
+    def remove(self, guid):
+        """silent if absent (seqComparer.py:131-134); the owner rank tombstones the row"""
+        gid = self._gid_of.pop(guid, None)
+        if gid is None:
+            return
+        self._guid_of.pop(gid, None)
+        self.seqProfile.pop(guid, None)
+        self._round((OP_REMOVE, 0, gid), None)
+
+    def iscachedinram(self, guid):
+        return guid in self._gid_of
+
+    def guidscachedinram(self):
+        return set(self._gid_of.keys())
+
+    def shutdown(self):
+        """rank 0: release the serving ranks"""
+        self._round((OP_STOP, 0, 0), None)

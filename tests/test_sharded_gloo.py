@@ -91,3 +91,97 @@ def test_sharded_store_single_rank():
         sub = coll.subset(np.arange(i + 1))
         assert gid == i and hits == c_oracle.one_vs_all(sub.pos, sub.off, sub.invalid, i, 20)
     assert ShardedStore.block_rows(10, 1, 4) == dict(row_begin=0, row_end=10, stride=4, phase=1)
+
+
+def _class_worker(rank, world, port, q, exchange):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_engine import OracleEngine
+        from findneighbour3_b200 import synth
+        from findneighbour3_b200.sharded import ShardedSeqComparer, ShardedStore
+        from oracle import seqcomparer_port as port_oracle
+
+        L = 60000
+        store = ShardedStore(OracleEngine(L), max_hits=256, exchange=exchange)
+        sc = ShardedSeqComparer(store, snpCeiling=20)
+        if rank != 0:
+            sc.serve()                                   # until rank 0 shuts the service down
+            q.put((rank, True, store.n_global))
+            store.close()
+            return
+        coll = synth.make_collection(4, 10, genome_length=L, seed=18, k1=80, s=2.0, n_blocks=4, n_mean=300, m_mean=3,
+                                     rule="any", p_invalid=0.05)
+        flat = {}                                        # what one reference seqComparer would hold
+        ok = True
+        for i in range(coll.n):
+            obj = coll.as_dict(i)
+            got = sc.insert("g%d" % i, obj)
+            flat["g%d" % i] = obj
+            ok &= got == port_oracle.neighbours(flat, {}, "g%d" % i, 20)
+        for g in ("g0", "g1", "g7", "g38"):              # stored samples owned by either rank
+            ok &= sc.neighbours(g) == port_oracle.neighbours(flat, {}, g, 20)
+            ok &= sc.neighbours(g, cutoff=3) == port_oracle.neighbours(flat, {}, g, 3)
+        # the reference's mcompare shape, position sets included
+        want = {r[1]: r[2:] for r in port_oracle.mcompare(flat, {}, "g5", 20)}
+        got = {r[1]: r[2:] for r in sc.mcompare("g5")}
+        ok &= got == want and len(got) == coll.n - 1
+        # removal on both ranks; re-insert under the same guid
+        for g in ("g2", "g3"):
+            sc.remove(g)
+            del flat[g]
+        sc.remove("never-there")
+        ok &= sc.neighbours("g4") == port_oracle.neighbours(flat, {}, "g4", 20)
+        ok &= not sc.iscachedinram("g2") and sc.guidscachedinram() == set(flat)
+        obj = coll.as_dict(2)
+        got = sc.insert("g2", obj)
+        flat["g2"] = obj
+        ok &= got == port_oracle.neighbours(flat, {}, "g2", 20)
+        try:
+            sc.neighbours("nobody")
+            ok = False
+        except KeyError:
+            pass
+        sc.shutdown()
+        q.put((rank, bool(ok), store.n_global))
+        store.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "shm"])
+def test_sharded_class_world2_gloo(exchange):
+    """ShardedSeqComparer: rank 0 drives inserts / queries / removals by guid, rank 1 serves."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + (11 if exchange == "shm" else 0)
+    procs = [ctx.Process(target=_class_worker, args=(r, 2, port, q, exchange)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in out), out
+    assert out[0][2] == out[1][2] == 41                  # 40 inserts + one re-insert, counted alike on both ranks
+
+
+def test_sharded_class_single_rank():
+    sys.path.insert(0, HERE)
+    from fake_engine import OracleEngine
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.sharded import ShardedSeqComparer, ShardedStore
+    from oracle import seqcomparer_port as port_oracle
+    coll = synth.make_collection(3, 6, genome_length=30000, seed=4, k1=50, s=2.0, n_blocks=3, n_mean=200, m_mean=2, rule="any")
+    sc = ShardedSeqComparer(ShardedStore(OracleEngine(30000)), snpCeiling=12)
+    flat = {}
+    for i in range(coll.n):
+        flat[i] = coll.as_dict(i)
+        assert sc.insert(i, flat[i]) == port_oracle.neighbours(flat, {}, i, 12)
+    sc.remove(3)
+    del flat[3]
+    assert sc.neighbours(4) == port_oracle.neighbours(flat, {}, 4, 12)
+    sc.shutdown()

@@ -47,18 +47,16 @@ class NucleicAcid():
             histogram = byte_histogram(self.nucleicAcidString, self._device)
         elif int(sum(histogram)) != self.nchars:
             raise ValueError("histogram does not belong to this string")
-        totalValid = 0
-        nMixed = 0
-        for thisChar in _VALID:
-            self.composition[thisChar] = int(histogram[ord(thisChar)])
-            totalValid = totalValid + self.composition[thisChar]
-            if thisChar in _IUPAC:
-                nMixed = nMixed + self.composition[thisChar]
-        self.composition['invalid'] = self.nchars - totalValid
-        self.composition['length'] = self.nchars
-        self.composition['ACTG'] = self.composition['A'] + self.composition['C'] + self.composition['G'] + self.composition['T']
-        self.composition['mixed'] = nMixed
-        self.composition['propACTG'] = float(self.composition['ACTG']) / float(self.composition['length'])
+        # the 18 permitted characters in the reference's order (upper-case codes first within each pair, :46-48); after the
+        # upper-casing above the lower-case keys are always 0, as in the reference
+        counts = {ch: int(histogram[ord(ch)]) for ch in _VALID}
+        comp = self.composition
+        comp.update(counts)
+        comp['invalid'] = self.nchars - sum(counts.values())
+        comp['length'] = self.nchars
+        comp['ACTG'] = counts['A'] + counts['C'] + counts['G'] + counts['T']
+        comp['mixed'] = sum(counts[ch] for ch in _IUPAC)
+        comp['propACTG'] = float(comp['ACTG']) / float(comp['length'])
         if self.composition['invalid'] == 0:
             self.isValid = True
         else:

@@ -60,3 +60,18 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), "%s reaches into oracle/" % f
+
+
+def test_dropin_directory_shadows_the_reference_module_names():
+    """PYTHONPATH=<repo>/findneighbour3_b200/dropin:<repo> makes the server's own import lines
+    (findNeighbour3-server.py:72, :74) pick up the B200 classes without touching the server."""
+    import subprocess
+    import sys
+    code = ("from seqComparer import seqComparer as a; from seqComparer_mt import seqComparer as b; "
+            "from NucleicAcid import NucleicAcid as c; "
+            "print(a.__module__, b.__module__, c.__module__)")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "findneighbour3_b200", "dropin"), ROOT]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/")
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["findneighbour3_b200.seqComparer", "findneighbour3_b200.seqComparer_mt",
+                                  "findneighbour3_b200.NucleicAcid"]

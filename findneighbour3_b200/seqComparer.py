@@ -261,6 +261,36 @@ class seqComparer():
                 self._key_of[g] = None                   # computed if the guid is ever persisted again
                 self.seqProfile._d[g] = objs[i] if objs[i] is not None else _LazyPickle(blobs[i], bool(invalid[i]))
 
+    def compact_store(self):
+        """Rebuild the device store without the rows remove() and re-persist have tombstoned (they keep their words in
+        HBM: rows are never reused, include/fn3.h).  Maintenance call for a long-running server: every live row is read
+        back (fn3_row_get), bulk-appended to a fresh engine in the old row order, and the guid<->row maps are switched
+        over under the lock.  Returns (rows before, rows after)."""
+        with self._lock:
+            old = self.engine
+            live = sorted(self._guid_of.keys())
+            before = int(old.stats()["n_rows"])
+            if len(live) == before:
+                return before, before
+            packed = [old.row_get(r) for r in live]
+            n = len(packed)
+            off = np.zeros(6 * n + 1, dtype=np.int64)
+            inv = np.zeros(n, dtype=np.uint8)
+            total = 0
+            for i, (p, f, bad) in enumerate(packed):
+                inv[i] = 1 if bad else 0
+                off[6 * i: 6 * i + 7] = total + (0 if bad else f.astype(np.int64))
+                total += 0 if bad else int(f[6])
+            pos = np.concatenate([p for p, _, bad in packed if not bad]) if total else np.empty(0, dtype=np.int32)
+            fresh = Engine(len(self.reference), self._device)
+            first = fresh.append_bulk(pos, off, inv) if n else 0
+            self._engine = fresh
+            self._ref_uploaded = False                       # uploaded again by the next compress / MSA call
+            self._row_of = {self._guid_of[r]: first + i for i, r in enumerate(live)}
+            self._guid_of = {row: guid for guid, row in self._row_of.items()}
+            old.close()
+            return before, n
+
     def _stored_kind(self, guid):
         """'invalid' | 'compressed' | 'patch' for a stored guid, without unpickling a lazily loaded sample"""
         v = self.seqProfile._d[guid]

@@ -57,13 +57,17 @@ class ShardedStore:
             self._shm_open()
 
     # -- shared-memory transport (one box) ----------------------------------------------------
-    # layout (int64 words): [sample: seq | n, off[0..6], invalid | positions (int32 pairs packed as int64 view)]
-    #                       [per rank: seq | count | records (max_hits x 5 int32)]
+    # layout (int64 words): [sample: seq | n, off[0..6], invalid, ctl | positions (int32 pairs packed as int64 view)]
+    #                       [per rank, TWO slots: seq | count | records (max_hits x 5 int32)]
+    # Round `seq` uses slot seq & 1.  A rank writes its slot of round seq+1 as soon as the next sample is out, which may be
+    # before a slow rank has collected round seq — with one slot per rank that reader would wait for a sequence number
+    # that is gone (a deadlock, reproduced with three ranks and one delayed reader).  Round seq+2 cannot start before
+    # every rank has written round seq+1, i.e. has finished collecting round seq: two slots suffice.
     def _shm_open(self):
         cap = self.bcast_cap
         self._s_words = 16 + (cap + 1) // 2                         # sample area, int64 words
         self._r_words = 2 + (HIT_FIELDS * self.max_hits + 1) // 2     # one result slot, int64 words
-        total = 8 * (self._s_words + self.world * self._r_words)
+        total = 8 * (self._s_words + 2 * self.world * self._r_words)
         name = [None]
         if self.rank == 0:
             self._shm = shared_memory.SharedMemory(create=True, size=total)
@@ -80,8 +84,9 @@ class ShardedStore:
         w = np.frombuffer(self._shm.buf, dtype=np.int64)
         self._s64 = w[: self._s_words]
         self._s32 = self._s64[16:].view(np.int32)
-        self._r64 = [w[self._s_words + r * self._r_words: self._s_words + (r + 1) * self._r_words] for r in range(self.world)]
-        self._r32 = [x[2:].view(np.int32) for x in self._r64]
+        self._r64 = [[w[self._s_words + (2 * r + b) * self._r_words: self._s_words + (2 * r + b + 1) * self._r_words]
+                      for b in range(2)] for r in range(self.world)]
+        self._r32 = [[x[2:].view(np.int32) for x in pair] for pair in self._r64]
         self._seq = 0
         dist.barrier(group=self.group)
 
@@ -125,23 +130,32 @@ class ShardedStore:
         ctl = (int(s64[10]), int(s64[11]), int(s64[12]))
         hits = compute(pos, off, invalid, ctl)
         m = len(hits)
-        if m > self.max_hits:
-            raise ValueError("%d neighbours exceed the shared-memory result slot (%d)" % (m, self.max_hits))
-        r64, r32 = self._r64[self.rank], self._r32[self.rank]
-        if m:
+        b = seq & 1
+        r64, r32 = self._r64[self.rank][b], self._r32[self.rank][b]
+        if 0 < m <= self.max_hits:
             rec = r32[: HIT_FIELDS * m].reshape(m, HIT_FIELDS)
             rec[:, 0] = hits["row"]; rec[:, 1] = hits["dist"]; rec[:, 2] = hits["n1"]
             rec[:, 3] = hits["n2"]; rec[:, 4] = hits["nboth"]
         r64[1] = m
         r64[0] = seq
         out = {}
+        counts = []
+        if getattr(self, "_debug_read_delay", 0):          # tests only: a reader that is slow to collect the slots
+            import time
+            time.sleep(self._debug_read_delay)
         for r in range(self.world):
-            q64 = self._r64[r]
+            q64 = self._r64[r][b]
             while q64[0] != seq:
                 pass
-            c = int(q64[1])
+            counts.append(int(q64[1]))
+        if max(counts) > self.max_hits:
+            # some rank found more neighbours than a result slot holds (its slot carries the count only): every rank sees
+            # the same counts, so all of them repeat the collection through the collective path, which grows its blocks
+            return self._gather_hits(hits), ctl
+        for r in range(self.world):
+            c = counts[r]
             if c:
-                rec = self._r32[r][: HIT_FIELDS * c].reshape(c, HIT_FIELDS)
+                rec = self._r32[r][b][: HIT_FIELDS * c].reshape(c, HIT_FIELDS)
                 gids = (rec[:, 0].astype(np.int64) * self.world + r).tolist()
                 out.update(zip(gids, map(tuple, rec[:, 1:].tolist())))
         return out, ctl

@@ -185,3 +185,52 @@ def test_sharded_class_single_rank():
     del flat[3]
     assert sc.neighbours(4) == port_oracle.neighbours(flat, {}, 4, 12)
     sc.shutdown()
+
+
+def _slow_reader_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_engine import OracleEngine
+        from findneighbour3_b200 import synth
+        from findneighbour3_b200.sharded import ShardedStore
+        from oracle import c_oracle
+        L = 20000
+        coll = synth.make_collection(2, 12, genome_length=L, seed=8, k1=40, s=2.0, n_blocks=2, n_mean=100, rule="any")
+        # max_hits=3: families of 12 overflow the result slots, so the collective fallback is exercised as well
+        store = ShardedStore(OracleEngine(L), max_hits=3, exchange="shm")
+        if rank == 2:
+            store._debug_read_delay = 0.01               # collects the slots long after the others have moved on
+        ok = True
+        for i in range(coll.n):
+            gid, hits = store.insert_query(coll.lists(i) if rank == 0 else None, 20)
+            sub = coll.subset(np.arange(i + 1))
+            ok &= gid == i and hits == c_oracle.one_vs_all(sub.pos, sub.off, sub.invalid, i, 20)
+        for g in (0, 1, 2, 13):                          # queries whose sample comes from each of the three ranks
+            ok &= store.one_vs_all(g, 20) == c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, g, 20)
+        q.put((rank, bool(ok)))
+        store.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shm_exchange_three_ranks_one_slow_reader():
+    """One result slot per rank deadlocked here (a rank may write round n+1 before a slow rank has collected round n);
+    the slots are double-buffered now.  Also: more neighbours than a slot holds fall back to the collective gather."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_slow_reader_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    try:
+        out = [q.get(timeout=120) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    assert sorted(out) == [(0, True), (1, True), (2, True)]

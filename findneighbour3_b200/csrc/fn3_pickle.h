@@ -42,7 +42,7 @@ struct Machine {
     bool pop(Val& v) { if (stack.empty()) { ok = false; return false; } v = stack.back(); stack.pop_back(); return true; }
     void put(uint32_t id) {
         if (stack.empty()) { ok = false; return; }
-        if (id >= memo.size()) { if (id > (1u << 24)) { ok = false; return; } memo.resize(id + 1); }
+        if (id >= memo.size()) { if (id > (1u << 24) || (int64_t)id > size) { ok = false; return; } memo.resize(id + 1); }   // a memo id costs >= 2 bytes of pickle
         memo[id] = stack.back();
     }
     void get(uint32_t id) { if (id >= memo.size()) { ok = false; return; } push(memo[id]); }

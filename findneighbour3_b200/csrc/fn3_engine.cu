@@ -435,6 +435,49 @@ static void pack_row(const fn3_engine* e, const int32_t* pos, const long long of
     }
 }
 
+// true iff the six lists of a packed row are mutually disjoint (include/fn3.h: a position carries ONE call; the reference's
+// compress() cannot produce anything else, seqComparer.py:292-298, but a hand-made sample could, and the kernel's per-position
+// code map would then answer differently from the reference's set algebra).  One merge over six sorted streams — the V lists
+// word by word, the N and M lists run by run — every item an interval [start, start + len): ~6 compares per row word.
+static bool packed_disjoint(const fn3_engine* e, const uint32_t* w, const uint32_t ends[6]) {
+    uint32_t at[6], end[6];
+    for (int b = 0; b < 6; ++b) { at[b] = b ? ends[b - 1] : 0u; end[b] = ends[b]; }
+    const uint32_t pmask = (e->pos_bits >= 32) ? 0xffffffffu : ((1u << e->pos_bits) - 1u);
+    unsigned long long last_end = 0;
+    for (;;) {
+        int best = -1; uint32_t bs = 0;
+        for (int b = 0; b < 6; ++b)
+            if (at[b] < end[b]) {
+                const uint32_t st = b < 4 ? w[at[b]] : (w[at[b]] & pmask);
+                if (best < 0 || st < bs) { best = b; bs = st; }
+            }
+        if (best < 0) return true;
+        const uint32_t x = w[at[best]++];
+        const unsigned long long len = (best < 4 || e->pos_bits >= 32) ? 1ull : (unsigned long long)(x >> e->pos_bits) + 1ull;
+        if ((unsigned long long)bs < last_end) return false;
+        last_end = (unsigned long long)bs + len;
+    }
+}
+
+// the same test on the caller's raw lists (bulk path, pass 1: everything is validated before anything is stored); the N and M
+// lists are walked run by run (maximal stretches of consecutive positions)
+static bool raw_disjoint(const int32_t* pos, const long long off[7]) {
+    long long at[6];
+    for (int b = 0; b < 6; ++b) at[b] = off[b];
+    long long last_end = 0;
+    for (;;) {
+        int best = -1; int32_t bs = 0;
+        for (int b = 0; b < 6; ++b)
+            if (at[b] < off[b + 1] && (best < 0 || pos[at[b]] < bs)) { best = b; bs = pos[at[b]]; }
+        if (best < 0) return true;
+        long long j = at[best] + 1;
+        if (best >= 4) while (j < off[best + 1] && pos[j] == pos[j - 1] + 1) ++j;
+        if ((long long)bs < last_end) return false;
+        last_end = (long long)bs + (j - at[best]);
+        at[best] = j;
+    }
+}
+
 // single pass for the insert hot path: validates the six lists AND writes the row words (dst must hold one word per
 // position, the worst case).  Returns the number of words, or -1 with the error set; *nblk = touched-block bound.
 static long long pack_checked(fn3_engine* e, const int32_t* pos, const long long off[7], uint32_t* dst, uint32_t ends[6],
@@ -483,6 +526,7 @@ static long long pack_checked(fn3_engine* e, const int32_t* pos, const long long
         }
         ends[b] = w;
     }
+    if (!packed_disjoint(e, dst, ends)) { set_err(e, FN3_EARG, "the six lists of a sample must be mutually disjoint"); return -1; }
     *nblk = (uint32_t)std::min<long long>(blocks, 0x7fffffff);
     return (long long)w;
 }
@@ -592,6 +636,10 @@ static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const lon
             long long o[7];
             for (int b = 0; b < 7; ++b) o[b] = off6[6 * i + b];
             long long w = row_words_needed(e, pos, o, invalid ? invalid[i] : 0, &nblks[(size_t)i]);
+            if (w >= 0 && !(invalid && invalid[i]) && !raw_disjoint(pos, o)) {
+                set_err(e, FN3_EARG, "the six lists of a sample must be mutually disjoint");
+                w = -1;
+            }
             if (w < 0) { bad.store(1); return; }
             words[(size_t)i] = w;
         }

@@ -197,7 +197,21 @@ def test_bad_input_is_rejected():
         eng.append(np.array([5, 5], np.int32), off)          # not strictly increasing
     with pytest.raises(ValueError):
         eng.append(np.array([5, 100], np.int32), off)        # out of range
+    # a position in two lists (A and N; C and an N run; N and M): every entry point that takes lists refuses it
+    for pos_, off_ in (([5, 9, 9], [0, 2, 2, 2, 2, 3, 3]), ([7, 20, 4, 5, 6, 7, 8], [0, 0, 2, 2, 2, 7, 7]),
+                       ([1, 2, 3, 3], [0, 0, 0, 0, 0, 3, 4])):
+        p_, o_ = np.array(pos_, np.int32), np.array(off_, np.int32)
+        with pytest.raises(ValueError):
+            eng.append(p_, o_)
+        with pytest.raises(ValueError):
+            eng.insert_query(p_, o_, False, 20)
+        with pytest.raises(ValueError):
+            eng.lists_vs_all(p_, o_, False, 20)
+        with pytest.raises(ValueError):
+            eng.append_bulk(p_, np.array(off_, np.int64))
     assert eng.stats()["n_rows"] == 0
+    eng.append(np.array([5, 9, 10], np.int32), np.array([0, 2, 2, 2, 2, 3, 3], np.int32))    # disjoint: accepted
+    assert eng.stats()["n_rows"] == 1
     eng.close()
 
 

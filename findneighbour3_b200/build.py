@@ -5,6 +5,7 @@
 The shared objects are built IN-TREE (findneighbour3_b200/libfn3.so) so that they
 travel with a snapshot of the repository; nothing is JIT-compiled at import time.
 """
+import glob
 import os
 import shutil
 import subprocess
@@ -14,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libfn3.so")
 SRC = [os.path.join(HERE, "csrc", "fn3_engine.cu")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("fn3_types.h", "fn3_kernels.cuh", "fn3_compress.cuh", "fn3_cluster.cuh")]
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.h")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh")))
 HDR = [os.path.join(ROOT, "include", "fn3.h")]
 
 NVCC_FLAGS = [

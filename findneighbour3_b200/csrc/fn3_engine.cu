@@ -35,6 +35,7 @@ static_assert(sizeof(QEntry) == 32, "QEntry must be one 32-byte sector");
 static_assert(sizeof(EdgeRec) == sizeof(fn3_edge), "EdgeRec/fn3_edge mismatch");
 
 #include "fn3_kernels.cuh"
+#include "fn3_scan.cuh"
 #include "fn3_compress.cuh"
 #include "fn3_cluster.cuh"
 #include "fn3_pickle.h"
@@ -76,7 +77,8 @@ struct fn3_engine {
     long long store_words = 0, store_bytes = 0, positions = 0;
 
     // staging
-    uint32_t* stage = nullptr; size_t stage_words = 0;     // pinned
+    uint32_t* stage = nullptr; size_t stage_words = 0;     // pinned (append path, store_mu)
+    uint32_t* istage = nullptr; size_t istage_words = 0;   // pinned (fn3_insert_query, query_mu)
     RowHead* stage_hdr = nullptr; size_t stage_hdr_n = 0;  // pinned, row order
     RowHead* d_heads = nullptr; size_t d_heads_n = 0;      // device staging for k_scatter_heads
 
@@ -136,6 +138,7 @@ struct fn3_engine {
     uint8_t* d_codes = nullptr; size_t codes_cap = 0;
     int32_t* d_acounts = nullptr; size_t acounts_cap = 0;
     int32_t* d_lpos = nullptr; size_t lpos_cap = 0;
+    unsigned char* d_vtiles = nullptr; size_t vtiles_cap = 0;   // head tiles of a virtual row set (engine groups)
     long long* d_loff = nullptr; size_t loff_cap = 0;
 
     std::atomic<long long> launches{0};
@@ -306,10 +309,12 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         e->max_smem = (int)prop.sharedMemPerBlockOptin;
         e->stage_limit = env_ll("FN3_FORCE_GLOBAL_QUERY", 0) ? 0 : e->max_smem;   // tests: exercise the global-memory variants
         // opt in to the full shared memory for the variants that build the query in shared memory
-        const void* staged[4] = {(const void*)k_query<false, 1, false>, (const void*)k_query<false, 1, true>,
-                                 (const void*)k_query<true, 1, false>, (const void*)k_query<true, 1, true>};
+        // (k_scan always needs dynamic shared memory: its row rings)
+        const void* staged[6] = {(const void*)k_query<false, 1>, (const void*)k_query<true, 1>,
+                                 (const void*)k_scan<false, 1>, (const void*)k_scan<true, 1>,
+                                 (const void*)k_scan<false, 0>, (const void*)k_scan<true, 0>};
         e->q_static_smem = 0;
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 6; ++i) {
             cudaFuncAttributes fa;
             if ((s = cudaFuncGetAttributes(&fa, staged[i])) != cudaSuccess) return fail("cudaFuncGetAttributes", s);
             e->q_static_smem = std::max(e->q_static_smem, (int)fa.sharedSizeBytes);
@@ -359,13 +364,14 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     cudaFree(e->d_hist);
     if (e->h_hist) cudaFreeHost(e->h_hist);
     cudaFree(e->d_refcode); cudaFree(e->d_votes); cudaFree(e->d_sel_counts); cudaFree(e->d_sel_totals); cudaFree(e->d_sel_out);
-    cudaFree(e->d_sites); cudaFree(e->d_codes); cudaFree(e->d_acounts); cudaFree(e->d_lpos); cudaFree(e->d_loff);
+    cudaFree(e->d_sites); cudaFree(e->d_codes); cudaFree(e->d_acounts); cudaFree(e->d_lpos); cudaFree(e->d_loff); cudaFree(e->d_vtiles);
     if (e->h_sel_totals) cudaFreeHost(e->h_sel_totals);
     if (e->in_stream) cudaStreamDestroy(e->in_stream);
     if (e->h_slots) cudaFreeHost(e->h_slots);
     if (e->h_outbuf) cudaFreeHost(e->h_outbuf);
     if (e->h_rows) cudaFreeHost(e->h_rows);
     if (e->stage) cudaFreeHost(e->stage);
+    if (e->istage) cudaFreeHost(e->istage);
     if (e->qstage) cudaFreeHost(e->qstage);
     if (e->stage_hdr) cudaFreeHost(e->stage_hdr);
     if (e->q_stream) cudaStreamDestroy(e->q_stream);
@@ -847,8 +853,8 @@ static bool use_filter_for(int ceiling) { return ceiling <= FN3_HEAD_FP - 8; }
 
 template <bool COUNT, int QMODE>
 static void launch_query(bool filter, dim3 g, size_t smem, cudaStream_t st, const CompareParams& p) {
-    if (filter) k_query<COUNT, QMODE, true><<<g, FN3_Q_THREADS, smem, st>>>(p);
-    else k_query<COUNT, QMODE, false><<<g, FN3_Q_THREADS, smem, st>>>(p);
+    if (filter) k_query<COUNT, QMODE><<<g, FN3_Q_THREADS, smem, st>>>(p);
+    else k_scan<COUNT, QMODE><<<g, FN3_Q_THREADS, smem, st>>>(p);
 }
 
 struct QueryJob {                    // what enqueue_query needs beyond the engine state
@@ -881,8 +887,12 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     uint32_t blocks = job.blocks;
     if (ns == 1 && blocks == 0) blocks = e->slot_blocks[0];
     blocks = std::min<uint32_t>(blocks, (uint32_t)e->n_blk);
-    const size_t smem = (size_t)e->nw * sizeof(uint2) + (size_t)e->ncw * 4 + ((size_t)blocks + 1) * sizeof(QEntry);
-    const bool in_smem = smem + (size_t)e->q_static_smem + 256 <= (size_t)e->stage_limit;
+    const bool filter = use_filter_for(job.ceiling);
+    // dynamic shared memory: the query structure (when it fits) and, for k_scan, the row rings behind it
+    const size_t q_smem = ((size_t)e->nw * sizeof(uint2) + (size_t)e->ncw * 4 + ((size_t)blocks + 1) * sizeof(QEntry) + 127) & ~(size_t)127;
+    const size_t ring = filter ? 0 : FN3_SCAN_RING_BYTES;
+    const bool in_smem = q_smem + ring + (size_t)e->q_static_smem + 256 <= (size_t)e->stage_limit;
+    const size_t smem = (in_smem ? q_smem : 0) + ring;
     if (!in_smem) {
         int rcq = ensure_qstate(e, ns);
         if (rcq) return rcq;
@@ -902,32 +912,42 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     p.commit_row = job.commit_row;
     if (job.commit_head) p.commit_head = *job.commit_head;
     p.out = e->d_out; p.out_count = e->d_count; p.touched = e->d_count + 1; p.out_cap = e->out_cap;
-    p.ceiling = job.ceiling; p.pos_bits = e->pos_bits; p.use_filter = use_filter_for(job.ceiling) ? 1 : 0;
+    p.ceiling = job.ceiling; p.pos_bits = e->pos_bits; p.use_filter = filter ? 1 : 0;
     p.fshift = e->fshift; p.nw = e->nw; p.ncw = e->ncw; p.debug_stop = e->debug_stop;
     if (job.zero_copy) {
         p.host_out = reinterpret_cast<EdgeRec*>(e->zc_buf + 64);
         p.host_flag = reinterpret_cast<volatile unsigned long long*>(e->zc_buf);
         p.done_ctas = e->d_done; p.host_cap = FN3_ZC_CAP; p.seq = e->zc_seq;
     }
-    const bool filter = p.use_filter != 0;
     const long long warps_per_cta = FN3_Q_THREADS / 32;
     const long long sb = 1ll << e->sb_shift;
     const long long slots_scanned = ((job.n_rows + sb - 1) / sb) * sb;          // whole superblocks of head tiles
     const long long cand = job.d_rows ? job.n_list : slots_scanned;
-    const long long units = filter ? (cand + 31) / 32 : cand;                   // warp-sized work units
-    long long ctas = std::max<long long>(1, (units + warps_per_cta - 1) / warps_per_cta);
-    long long per_sm = FN3_Q_MINB;                                  // __launch_bounds__(512, FN3_Q_MINB)
+    const long long units = (cand + 31) / 32;                                   // warp-sized work units (32 candidates)
+    long long per_sm = filter ? FN3_Q_MINB : 1;                     // __launch_bounds__(512, FN3_Q_MINB) / k_scan: (512, 1)
     if (in_smem && per_sm * (long long)(smem + (size_t)e->q_static_smem + 1024) > (long long)228 * 1024) per_sm = 1;
     // every CTA builds its query first: with several slots per launch give each slot its share of the resident
     // CTAs and let every CTA scan more candidates, rather than several waves that each rebuild the query
-    ctas = std::min<long long>(ctas, std::max<long long>(1, (long long)e->sm_count * per_sm / ns));
+    const long long cta_cap = std::max<long long>(1, (long long)e->sm_count * per_sm / ns);
+    long long ctas;
+    if (filter) {
+        ctas = std::min<long long>(std::max<long long>(1, (units + warps_per_cta - 1) / warps_per_cta), cta_cap);
+    } else {
+        // k_scan: a warp streams its rows one after the other, so the unit of balance is small — split the 32-row tiles
+        // until every warp of the launch can draw about three sub-units (50 000 rows = 1 792 tiles for 2 368 warps)
+        int ss = 0;
+        while (ss < 3 && (units << ss) < 3 * cta_cap * warps_per_cta) ++ss;
+        p.split_shift = ss;
+        p.ring_off = (unsigned int)(in_smem ? q_smem : 0);
+        ctas = std::min<long long>(std::max<long long>(1, ((units << ss) + warps_per_cta - 1) / warps_per_cta), cta_cap);
+    }
     dim3 g((unsigned)ctas, (unsigned)ns);
     if (in_smem) {
         if (job.count_bytes) launch_query<true, 1>(filter, g, smem, st, p);
         else launch_query<false, 1>(filter, g, smem, st, p);
     } else {
-        if (job.count_bytes) launch_query<true, 0>(filter, g, 0, st, p);
-        else launch_query<false, 0>(filter, g, 0, st, p);
+        if (job.count_bytes) launch_query<true, 0>(filter, g, smem, st, p);
+        else launch_query<false, 0>(filter, g, smem, st, p);
     }
     e->launches += 1;
     CU(e, cudaGetLastError());
@@ -1099,17 +1119,14 @@ extern "C" int fn3_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling,
     return run_one_vs_all(e, job, rows, n_rows, out, cap, n_out);
 }
 
-// insert() of the reference's server (findNeighbour3-server.py:516 persist + :530 mcompare) as ONE call on ONE
-// stream with ONE host synchronisation: the row data goes host->device, k_query places the row's head (passed by
-// value) in its tile and compares the new sample with every earlier row, the neighbour records come back.
-extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
-                                int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out) {
-    if (!e || !n_out || !out_row || (cap > 0 && !out) || (!invalid && !off))
-        return set_err(e, FN3_EARG, "fn3_insert_query: bad arguments");
-    std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
-    std::lock_guard<std::mutex> g(e->store_mu);      // held to the end: the pinned staging row must not be repacked
-    RowHdr h; memset(&h, 0, sizeof h);               // by a concurrent append before the stream has consumed it
+// Body of fn3_insert_query (query_mu held, device set).  The sample is packed into the insert path's OWN pinned staging
+// buffer (istage, guarded by query_mu), so store_mu is held only while the row is reserved and, after the kernel has
+// answered, while it is published: fn3_append / fn3_remove / fn3_stats_get do not wait behind the query.  The row is
+// reserved as "pending" (its host flags say removed) and becomes live only once k_query has placed its head — a call
+// that fails before the launch leaves a tombstone, never a live row without a head.
+static int insert_query_locked(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
+                               int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out) {
+    RowHdr h; memset(&h, 0, sizeof h);
     const auto t_begin = std::chrono::steady_clock::now();
     uint32_t nblk = 0;
     long long o[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -1117,9 +1134,17 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     // one pass: validate + pack into pinned staging (one word per position is the worst case)
     const size_t npos_in = invalid ? 0 : (size_t)(o[6] - o[0]);
     const size_t nv_in = invalid ? 0 : (size_t)(o[4] - o[0]);
-    int rc = ensure_stage(e, row_alloc_words(npos_in, nv_in) + 8, 1);
-    if (rc) return rc;
-    uint32_t* const stage = e->stage;
+    const size_t worst = row_alloc_words(npos_in, nv_in) + 8;
+    int rc;
+    if (worst > e->istage_words) {
+        const size_t want = std::max(worst, std::max<size_t>(e->istage_words * 2, 1u << 16));
+        CU(e, cudaStreamSynchronize(e->q_stream));       // a copy out of the old buffer may still be in flight
+        if (e->istage) cudaFreeHost(e->istage);
+        e->istage = nullptr; e->istage_words = 0;
+        CU(e, cudaHostAlloc(&e->istage, want * 4, cudaHostAllocDefault));
+        e->istage_words = want;
+    }
+    uint32_t* const stage = e->istage;
     long long w = 0;
     if (!invalid) {
         w = pack_checked(e, pos, o, stage, h.end, &nblk);
@@ -1129,13 +1154,25 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     if (invalid) memset(stage, 0, need * 4);
     else finish_row(e, stage, (size_t)w, nv_in);
     uint32_t* dbase = nullptr;
-    if ((rc = arena_alloc(e, need, &dbase))) return rc;
-    const long long row = e->n_rows;
-    const size_t chunks_before = e->hdr_chunks.size();
-    if ((rc = ensure_hdr_chunk(e, row))) return rc;
-    if (e->hdr_chunks.size() != chunks_before)       // a new chunk is zeroed on copy_stream: order q_stream behind it
-        CU(e, cudaStreamSynchronize(e->copy_stream));
-    if (!invalid) h.data = (unsigned long long)(uintptr_t)dbase;
+    long long row;
+    QueryJob job; job.ceiling = ceiling;
+    const uint32_t np = invalid ? 0u : (uint32_t)(o[6] - o[0]);
+    {
+        std::lock_guard<std::mutex> g(e->store_mu);
+        if ((rc = arena_alloc(e, need, &dbase))) return rc;
+        row = e->n_rows;
+        const size_t chunks_before = e->hdr_chunks.size();
+        if ((rc = ensure_hdr_chunk(e, row))) return rc;
+        if (e->hdr_chunks.size() != chunks_before)       // a new chunk is zeroed on copy_stream: order q_stream behind it
+            CU(e, cudaStreamSynchronize(e->copy_stream));
+        if (!invalid) h.data = (unsigned long long)(uintptr_t)dbase;
+        e->h_hdr.push_back(h);
+        e->h_flags.push_back((uint8_t)((invalid ? 1 : 0) | 2));      // pending: not live until the kernel has run
+        e->h_npos.push_back(np);
+        e->h_nblk.push_back(nblk);
+        e->n_rows = row + 1;
+        fill_hdr_table(e, job.ht);
+    }
     RowHead head;
     fill_head(e, head, h, stage);
     e->t_pack_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
@@ -1144,22 +1181,33 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     //  wait -1.0 us, enqueue +0.7 us — the DMA overlaps the launch latency anyway)
     CU(e, cudaMemcpyAsync(dbase, stage, need * 4, cudaMemcpyHostToDevice, e->q_stream));
     e->h2d_bytes += (long long)need * 4;
-    e->h_hdr.push_back(h);
-    e->h_flags.push_back(invalid ? 1 : 0);
-    const uint32_t np = invalid ? 0u : (uint32_t)(o[6] - o[0]);
-    e->h_npos.push_back(np);
-    e->h_nblk.push_back(nblk);
-    e->positions += np;
-    e->n_live++; if (invalid) e->n_invalid++;
-    e->n_rows = row + 1;
     *out_row = row;
-    QueryJob job; job.ceiling = ceiling;
-    fill_hdr_table(e, job.ht);
     job.n_rows = row;                                // candidates: every earlier row
     job.commit_head = &head; job.commit_row = row;   // an invalid row's head too: zero header, fingerprints that always mismatch
     set_slot0(e, h, row, row);
     e->slot_blocks[0] = nblk;
-    return run_one_vs_all(e, job, nullptr, 0, out, cap, n_out);
+    rc = run_one_vs_all(e, job, nullptr, 0, out, cap, n_out);
+    if (rc == FN3_OK || (rc == FN3_ECAPACITY && *n_out > cap)) {   // the kernel ran: the row is in the store
+        std::lock_guard<std::mutex> g(e->store_mu);
+        e->h_flags[(size_t)row] = invalid ? 1 : 0;
+        e->positions += np;
+        e->n_live++; if (invalid) e->n_invalid++;
+    } else {
+        *out_row = -1;                               // the reserved row stays a tombstone
+    }
+    return rc;
+}
+
+// insert() of the reference's server (findNeighbour3-server.py:516 persist + :530 mcompare) as ONE call on ONE
+// stream with ONE host synchronisation: the row data goes host->device, k_query places the row's head (passed by
+// value) in its tile and compares the new sample with every earlier row, the neighbour records come back.
+extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
+                                int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out) {
+    if (!e || !n_out || !out_row || (cap > 0 && !out) || (!invalid && !off))
+        return set_err(e, FN3_EARG, "fn3_insert_query: bad arguments");
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    return insert_query_locked(e, pos, off, invalid, ceiling, out_row, out, cap, n_out);
 }
 
 extern "C" int fn3_lists_vs_all(fn3_engine* e, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
@@ -1208,23 +1256,11 @@ extern "C" int fn3_pair_lists(fn3_engine* e, const int32_t* pos1, const int32_t 
     memset(&job.ht, 0, sizeof job.ht);
     job.ht.chunk[0] = e->d_scratch_tile; job.ht.shift = 5; job.ht.sb_shift = 5;
     job.n_rows = 1;
-    {
-        // head by value through a 1-element device staging copy
-        if (e->d_heads_n < 1) {
-            CU(e, cudaMalloc(&e->d_heads, 1024 * sizeof(RowHead)));
-            e->d_heads_n = 1024;
-        }
-        std::lock_guard<std::mutex> g(e->store_mu);          // d_heads / stage_hdr are shared with append
-        CU(e, cudaStreamSynchronize(e->copy_stream));
-        int rc2 = ensure_stage(e, 4, 1);
-        if (rc2) return rc2;
-        e->stage_hdr[0] = chead;
-        CU(e, cudaMemcpyAsync(e->d_heads, e->stage_hdr, sizeof(RowHead), cudaMemcpyHostToDevice, e->q_stream));
-        k_scatter_heads<<<1, 32, 0, e->q_stream>>>(e->d_heads, 0, 1, job.ht);
-        e->launches += 1;
-        CU(e, cudaGetLastError());
-        CU(e, cudaStreamSynchronize(e->q_stream));
-    }
+    // the candidate's head travels by value in the kernel parameters (k_put_head on the query stream): nothing is shared
+    // with the append path, which owns d_heads / stage_hdr under store_mu
+    k_put_head<<<1, 1, 0, e->q_stream>>>(chead, 0, job.ht);
+    e->launches += 1;
+    CU(e, cudaGetLastError());
     set_slot0(e, qh, -1, -1);
     int64_t n = 0;
     rc = run_one_vs_all(e, job, nullptr, 0, out, 1, &n);
@@ -1247,52 +1283,36 @@ static int grow_out_keep(fn3_engine* e, long long cap, long long keep) {
     return FN3_OK;
 }
 
-extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only, int64_t row_begin, int64_t row_end,
-                              int64_t stride, int64_t phase, fn3_edge* out, int64_t cap, int64_t* n_out) {
-    if (!e || !n_out || (cap > 0 && !out) || stride < 1 || phase < 0 || phase >= stride)
-        return set_err(e, FN3_EARG, "fn3_all_vs_all: bad arguments");
-    std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
-    QueryJob job; job.ceiling = ceiling;
-    snapshot_store(e, job);
-    const long long n_store = job.n_rows;
-    if (row_begin < 0) row_begin = 0;
-    if (row_end > n_store) row_end = n_store;
-    *n_out = 0;
+// One query of an all-vs-all pass: the row's header (its data may live on a peer device of an engine group), the row id the
+// edges carry as row1, and which local candidates it is compared with.
+struct AvaQuery { RowHdr hdr; long long tag; long long skip_le; long long exclude; uint32_t nblk; };
+
+// Core of fn3_all_vs_all (query_mu held, device set, job.ht / job.n_rows snapshotted): every query of `qs` against the local
+// store.  Tiles of T queries are queued FN3_SLOT_RING at a time with no host synchronisation in between; edges accumulate
+// behind one device counter.  After each batch the counter is read back; if the batch overflowed the buffer (the kernels
+// never write past it) the buffer grows and the batch is repeated.  The edges stay in d_out (e->edges_ready).
+static int all_vs_all_core(fn3_engine* e, QueryJob& job, const std::vector<AvaQuery>& qs, long long* n_total) {
     int rc;
     const int T = e->n_slots;
-    std::vector<long long> qrows;
-    std::vector<RowHdr> qhdr;
-    std::vector<uint32_t> qblk;
-    {
-        std::lock_guard<std::mutex> g(e->store_mu);
-        for (long long r = row_begin; r < row_end; ++r)
-            if ((r % stride) == phase && e->h_flags[(size_t)r] == 0) {
-                qrows.push_back(r); qhdr.push_back(e->h_hdr[(size_t)r]); qblk.push_back(e->h_nblk[(size_t)r]);
-            }
-    }
-    // Tiles of T queries are queued FN3_SLOT_RING at a time with no host synchronisation in between; edges
-    // accumulate behind one device counter.  After each batch the counter is read back; if the batch overflowed
-    // the buffer (the kernels never write past it) the buffer grows and the batch is repeated.
-    if ((rc = ensure_out(e, std::max<long long>(1 << 20, 4 * (long long)qrows.size())))) return rc;
+    if ((rc = ensure_out(e, std::max<long long>(1 << 20, 4 * (long long)qs.size())))) return rc;
     CU(e, cudaMemsetAsync(e->d_count, 0, FN3_OUT_HDR, e->q_stream));
     e->count_dirty = true;
     long long total = 0;
-    const size_t n_tiles = (qrows.size() + (size_t)T - 1) / (size_t)T;
+    const size_t n_tiles = (qs.size() + (size_t)T - 1) / (size_t)T;
     for (size_t b0 = 0; b0 < n_tiles; b0 += FN3_SLOT_RING) {
         const size_t b1 = std::min(n_tiles, b0 + (size_t)FN3_SLOT_RING);
         for (;;) {
             for (size_t t = b0; t < b1; ++t) {
                 const size_t q0 = t * (size_t)T;
-                const int ns = (int)std::min<size_t>((size_t)T, qrows.size() - q0);
+                const int ns = (int)std::min<size_t>((size_t)T, qs.size() - q0);
                 job.ns = ns;
                 job.slot_base = (int)(t - b0) * FN3_MAX_SLOTS;
                 job.blocks = 1;
                 for (int s = 0; s < ns; ++s) {
-                    const long long r = qrows[q0 + s];
-                    QuerySlot& qs = e->h_slots[job.slot_base + s];
-                    qs.hdr = qhdr[q0 + s]; qs.row = r; qs.exclude = r; qs.skip_le = upper_only ? r : -1; qs.pad = 0;
-                    job.blocks = std::max(job.blocks, qblk[q0 + s]);
+                    const AvaQuery& q = qs[q0 + s];
+                    QuerySlot& sl = e->h_slots[job.slot_base + s];
+                    sl.hdr = q.hdr; sl.row = q.tag; sl.exclude = q.exclude; sl.skip_le = q.skip_le; sl.pad = 0;
+                    job.blocks = std::max(job.blocks, q.nblk);
                 }
                 if ((rc = enqueue_query(e, job))) return rc;
             }
@@ -1308,13 +1328,65 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
             CU(e, cudaStreamSynchronize(e->q_stream));
         }
     }
-    *n_out = total;
+    *n_total = total;
     e->edges_ready = total;                           // fetchable until the next query on this engine
-    if (total > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld edges, %lld needed", (long long)cap, total);
-    if (total > 0) {
-        CU(e, cudaMemcpy(out, e->d_out, (size_t)total * sizeof(EdgeRec), cudaMemcpyDeviceToHost));
-        e->d2h_bytes += total * (long long)sizeof(EdgeRec);
+    return FN3_OK;
+}
+
+// copy the pending edges to the caller (through pinned staging in pieces: a pageable cudaMemcpy of a large edge list
+// runs at a fraction of the link rate)
+static int fetch_edges(fn3_engine* e, fn3_edge* out, long long total) {
+    const long long piece = 1 << 18;                  // 8 MB of records
+    int rc;
+    if ((rc = ensure_hout(e, std::min<long long>(total, 2 * piece)))) return rc;
+    const long long half = e->h_out_cap / 2 >= piece ? piece : std::max<long long>(1, e->h_out_cap / 2);
+    cudaStream_t st = e->q_stream;
+    long long done = 0; int buf = 0;
+    long long prev_n = 0, prev_at = 0; int prev_buf = -1;
+    while (done < total || prev_buf >= 0) {
+        long long n = 0; int this_buf = -1;
+        if (done < total) {
+            n = std::min(half, total - done);
+            this_buf = buf;
+            CU(e, cudaMemcpyAsync(e->h_out + (size_t)this_buf * half, e->d_out + done, (size_t)n * sizeof(EdgeRec), cudaMemcpyDeviceToHost, st));
+        }
+        if (prev_buf >= 0) memcpy(out + prev_at, e->h_out + (size_t)prev_buf * half, (size_t)prev_n * sizeof(EdgeRec));
+        if (this_buf >= 0) CU(e, cudaStreamSynchronize(st));
+        prev_buf = this_buf; prev_n = n; prev_at = done;
+        done += n; buf ^= 1;
     }
+    e->d2h_bytes += total * (long long)sizeof(EdgeRec);
+    return FN3_OK;
+}
+
+extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only, int64_t row_begin, int64_t row_end,
+                              int64_t stride, int64_t phase, fn3_edge* out, int64_t cap, int64_t* n_out) {
+    if (!e || !n_out || (cap > 0 && !out) || stride < 1 || phase < 0 || phase >= stride)
+        return set_err(e, FN3_EARG, "fn3_all_vs_all: bad arguments");
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    QueryJob job; job.ceiling = ceiling;
+    snapshot_store(e, job);
+    const long long n_store = job.n_rows;
+    if (row_begin < 0) row_begin = 0;
+    if (row_end > n_store) row_end = n_store;
+    *n_out = 0;
+    std::vector<AvaQuery> qs;
+    {
+        std::lock_guard<std::mutex> g(e->store_mu);
+        for (long long r = row_begin; r < row_end; ++r)
+            if ((r % stride) == phase && e->h_flags[(size_t)r] == 0) {
+                AvaQuery q; q.hdr = e->h_hdr[(size_t)r]; q.tag = r; q.exclude = r; q.skip_le = upper_only ? r : -1;
+                q.nblk = e->h_nblk[(size_t)r];
+                qs.push_back(q);
+            }
+    }
+    long long total = 0;
+    int rc = all_vs_all_core(e, job, qs, &total);
+    if (rc) return rc;
+    *n_out = total;
+    if (total > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld edges, %lld needed", (long long)cap, total);
+    if (total > 0) return fetch_edges(e, out, total);
     return FN3_OK;
 }
 
@@ -1325,10 +1397,7 @@ extern "C" int fn3_all_vs_all_fetch(fn3_engine* e, fn3_edge* out, int64_t cap, i
     if (e->edges_ready < 0) return set_err(e, FN3_ENOTFOUND, "fn3_all_vs_all_fetch: no all-vs-all result is pending");
     *n_out = e->edges_ready;
     if (e->edges_ready > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld edges, %lld needed", (long long)cap, e->edges_ready);
-    if (e->edges_ready > 0) {
-        CU(e, cudaMemcpy(out, e->d_out, (size_t)e->edges_ready * sizeof(EdgeRec), cudaMemcpyDeviceToHost));
-        e->d2h_bytes += e->edges_ready * (long long)sizeof(EdgeRec);
-    }
+    if (e->edges_ready > 0) return fetch_edges(e, out, e->edges_ready);
     return FN3_OK;
 }
 
@@ -1621,16 +1690,32 @@ static int consensus_tail(fn3_engine* e, int64_t min_votes, int32_t* pos, int64_
     return fetch_selected(e, total, pos, pos_cap, who);
 }
 
-extern "C" int fn3_consensus(fn3_engine* e, const int64_t* rows, int64_t n_rows, int64_t min_votes, int32_t* pos,
-                             int64_t pos_cap, int32_t off[6], int64_t* n_pos) {
-    if (!e || !off || !n_pos || n_rows < 0 || (n_rows > 0 && !rows) || min_votes < 1)
-        return set_err(e, FN3_EARG, "fn3_consensus: bad arguments (min_votes must be >= 1)");
-    std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+// Rows of a "virtual store" for the cluster kernels: headers given by value — their row data may live on PEER devices of
+// an engine group, read over NVLink — uploaded as head tiles of 32, with the identity row list in d_rows.  query_mu held.
+static int virtual_rows(fn3_engine* e, const RowHdr* hdrs, int64_t n, HdrTable* ht) {
+    int rc;
+    if ((rc = ensure_rows(e, std::max<long long>(n, 1)))) return rc;
+    const size_t n_tiles = (size_t)((n + 31) / 32);
+    if ((rc = ensure_dev(e, &e->d_vtiles, &e->vtiles_cap, std::max<size_t>(n_tiles, 1) * FN3_TILE_BYTES))) return rc;
+    std::vector<unsigned char> tiles(std::max<size_t>(n_tiles, 1) * FN3_TILE_BYTES, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        memcpy(tiles.data() + (size_t)(i >> 5) * FN3_TILE_BYTES + (size_t)(i & 31) * 32, &hdrs[i], sizeof(RowHdr));
+        e->h_rows[i] = i;
+    }
+    CU(e, cudaMemcpyAsync(e->d_vtiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice, e->q_stream));
+    if (n > 0) CU(e, cudaMemcpyAsync(e->d_rows, e->h_rows, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, e->q_stream));
+    CU(e, cudaStreamSynchronize(e->q_stream));             // `tiles` is pageable and leaves scope
+    e->h2d_bytes += (long long)tiles.size() + n * (long long)sizeof(long long);
+    memset(ht, 0, sizeof *ht);
+    ht->chunk[0] = e->d_vtiles; ht->shift = 26; ht->sb_shift = 5;
+    return FN3_OK;
+}
+
+// consensus over the rows in d_rows[0..n_rows) of the store described by ht (query_mu held, device set)
+static int consensus_core(fn3_engine* e, const HdrTable& ht, int64_t n_rows, int64_t min_votes, int32_t* pos,
+                          int64_t pos_cap, int32_t off[6], int64_t* n_pos, const char* who) {
     int rc;
     if ((rc = ensure_votes(e))) return rc;
-    HdrTable ht;
-    if ((rc = cluster_rows(e, rows, n_rows, false, "fn3_consensus", &ht))) return rc;
     cudaStream_t st = e->q_stream;
     CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * 5 * sizeof(uint32_t), st));
     if (n_rows > 0) {
@@ -1638,7 +1723,19 @@ extern "C" int fn3_consensus(fn3_engine* e, const int64_t* rows, int64_t n_rows,
         e->launches += 1;
         CU(e, cudaGetLastError());
     }
-    return consensus_tail(e, min_votes, pos, pos_cap, off, n_pos, "fn3_consensus");
+    return consensus_tail(e, min_votes, pos, pos_cap, off, n_pos, who);
+}
+
+extern "C" int fn3_consensus(fn3_engine* e, const int64_t* rows, int64_t n_rows, int64_t min_votes, int32_t* pos,
+                             int64_t pos_cap, int32_t off[6], int64_t* n_pos) {
+    if (!e || !off || !n_pos || n_rows < 0 || (n_rows > 0 && !rows) || min_votes < 1)
+        return set_err(e, FN3_EARG, "fn3_consensus: bad arguments (min_votes must be >= 1)");
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    int rc;
+    HdrTable ht;
+    if ((rc = cluster_rows(e, rows, n_rows, false, "fn3_consensus", &ht))) return rc;
+    return consensus_core(e, ht, n_rows, min_votes, pos, pos_cap, off, n_pos, "fn3_consensus");
 }
 
 extern "C" int fn3_consensus_lists(fn3_engine* e, int64_t n, const int32_t* pos_in, const int64_t* off_in, int64_t min_votes,
@@ -1677,19 +1774,11 @@ extern "C" int fn3_consensus_lists(fn3_engine* e, int64_t n, const int32_t* pos_
     return consensus_tail(e, min_votes, pos, pos_cap, off, n_pos, "fn3_consensus_lists");
 }
 
-extern "C" int fn3_msa_sites_rule(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t rule, int32_t* sites,
-                                  int64_t sites_cap, int64_t* n_sites) {
-    if (!e || !n_sites || n_rows < 0 || (n_rows > 0 && !rows) || (rule != FN3_SITES_CALLS && rule != FN3_SITES_CALLS_OR_N))
-        return set_err(e, FN3_EARG, "fn3_msa_sites: bad arguments");
-    *n_sites = 0;
-    if (n_rows == 0) return FN3_OK;
-    std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+static int msa_sites_core(fn3_engine* e, const HdrTable& ht, int64_t n_rows, int32_t rule, int32_t* sites, int64_t sites_cap,
+                          int64_t* n_sites) {
     if (!e->d_refcode) return set_err(e, FN3_EARG, "fn3_msa_sites: call fn3_set_reference first (the variant-site rule needs the reference bases)");
     int rc;
     if ((rc = ensure_votes(e))) return rc;
-    HdrTable ht;
-    if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_sites", &ht))) return rc;
     cudaStream_t st = e->q_stream;
     const int planes = rule == FN3_SITES_CALLS_OR_N ? 5 : 4;          // the N plane only where the rule reads it
     CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * planes * sizeof(uint32_t), st));
@@ -1703,25 +1792,36 @@ extern "C" int fn3_msa_sites_rule(fn3_engine* e, const int64_t* rows, int64_t n_
     return fetch_selected(e, total, sites, sites_cap, "fn3_msa_sites");
 }
 
-extern "C" int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t* sites, int64_t sites_cap,
-                             int64_t* n_sites) {
-    return fn3_msa_sites_rule(e, rows, n_rows, FN3_SITES_CALLS, sites, sites_cap, n_sites);
-}
-
-extern "C" int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows, const int32_t* sites, int64_t n_sites,
-                             uint8_t* codes, int32_t* counts) {
-    if (!e || n_rows < 0 || n_sites < 0 || (n_rows > 0 && (!rows || !counts)) || (n_sites > 0 && !sites))
-        return set_err(e, FN3_EARG, "fn3_msa_align: bad arguments");
-    for (int64_t k = 0; k < n_sites; ++k) {
-        if (sites[k] < 0 || (long long)sites[k] >= e->L) return set_err(e, FN3_EARG, "fn3_msa_align: site out of range");
-        if (k && sites[k] <= sites[k - 1]) return set_err(e, FN3_EARG, "fn3_msa_align: sites must be strictly increasing");
-    }
+extern "C" int fn3_msa_sites_rule(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t rule, int32_t* sites,
+                                  int64_t sites_cap, int64_t* n_sites) {
+    if (!e || !n_sites || n_rows < 0 || (n_rows > 0 && !rows) || (rule != FN3_SITES_CALLS && rule != FN3_SITES_CALLS_OR_N))
+        return set_err(e, FN3_EARG, "fn3_msa_sites: bad arguments");
+    *n_sites = 0;
     if (n_rows == 0) return FN3_OK;
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
     int rc;
     HdrTable ht;
-    if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_align", &ht))) return rc;
+    if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_sites", &ht))) return rc;
+    return msa_sites_core(e, ht, n_rows, rule, sites, sites_cap, n_sites);
+}
+
+extern "C" int fn3_msa_sites(fn3_engine* e, const int64_t* rows, int64_t n_rows, int32_t* sites, int64_t sites_cap,
+                             int64_t* n_sites) {
+    return fn3_msa_sites_rule(e, rows, n_rows, FN3_SITES_CALLS, sites, sites_cap, n_sites);
+}
+
+static int msa_align_check_sites(fn3_engine* e, const int32_t* sites, int64_t n_sites) {
+    for (int64_t k = 0; k < n_sites; ++k) {
+        if (sites[k] < 0 || (long long)sites[k] >= e->L) return set_err(e, FN3_EARG, "fn3_msa_align: site out of range");
+        if (k && sites[k] <= sites[k - 1]) return set_err(e, FN3_EARG, "fn3_msa_align: sites must be strictly increasing");
+    }
+    return FN3_OK;
+}
+
+static int msa_align_core(fn3_engine* e, const HdrTable& ht, int64_t n_rows, const int32_t* sites, int64_t n_sites,
+                          uint8_t* codes, int32_t* counts) {
+    int rc;
     cudaStream_t st = e->q_stream;
     if ((rc = ensure_dev(e, &e->d_sites, &e->sites_cap, (size_t)std::max<int64_t>(n_sites, 1)))) return rc;
     if ((rc = ensure_dev(e, &e->d_acounts, &e->acounts_cap, (size_t)n_rows * 4))) return rc;
@@ -1744,6 +1844,20 @@ extern "C" int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows,
     CU(e, cudaStreamSynchronize(st));
     e->d2h_bytes += n_rows * 16 + (want_codes ? (long long)ncodes : 0);
     return FN3_OK;
+}
+
+extern "C" int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows, const int32_t* sites, int64_t n_sites,
+                             uint8_t* codes, int32_t* counts) {
+    if (!e || n_rows < 0 || n_sites < 0 || (n_rows > 0 && (!rows || !counts)) || (n_sites > 0 && !sites))
+        return set_err(e, FN3_EARG, "fn3_msa_align: bad arguments");
+    int rc;
+    if ((rc = msa_align_check_sites(e, sites, n_sites))) return rc;
+    if (n_rows == 0) return FN3_OK;
+    std::lock_guard<std::mutex> q(e->query_mu);
+    CU(e, cudaSetDevice(e->device));
+    HdrTable ht;
+    if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_align", &ht))) return rc;
+    return msa_align_core(e, ht, n_rows, sites, n_sites, codes, counts);
 }
 
 // ---- wire format: the reference's GridFS pickles -> packed lists (fn3_pickle.h) --------------------------

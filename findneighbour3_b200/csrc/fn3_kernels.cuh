@@ -244,9 +244,10 @@ __global__ void __launch_bounds__(FN3_Q_THREADS) k_build_query(const QuerySlot* 
 //     fall in coarse blocks the query does not touch at all: each such position is a certain mismatch, so a
 //     count above the ceiling proves "not a neighbour" (this is ~every unrelated pair).  Survivors are then
 //     streamed one WARP per candidate.
-//   STREAM variant (larger ceilings): one WARP per candidate from the start, next header prefetched.
-// Row streaming: coalesced 128-bit loads, 256 words per warp step with the next 256 in flight,
-// __reduce_add_sync tallies, survivors compacted into the neighbour buffer with one atomic each.
+//     (coalesced 128-bit loads, 256 words per warp step with the next 256 in flight, __reduce_add_sync tallies).
+//   STREAM variant (larger ceilings): k_scan in fn3_scan.cuh — whole rows by bulk asynchronous copy into per-warp
+//     shared-memory rings.
+// Survivors are compacted into the neighbour buffer with one atomic each.
 
 struct QView {                  // where the query structure lives (shared or global)
     const uint32_t* bm;         // bit per 32-position block: touched by the query
@@ -296,7 +297,6 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
     return r;
 }
 
-#ifndef FN3_STREAM_V1
 // One warp streams one candidate row against the query (all 32 lanes must call).
 // The V words (A,C,G,T positions) and the run words (N, M) are handled by separate loops: V words 256 per warp step
 // with two 128-bit loads per lane and the next step in flight; run words one per lane, the first 32 of them requested
@@ -320,24 +320,6 @@ __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __r
         const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
         int mism = 0;
         if (base + 256u <= e3) {                                // warp-uniform: a full step
-#ifdef FN3_STREAM_V3
-            // all 8 bitmap tests first (independent LDS, no branches); the rare words whose block the query touches
-            // are then looked up one by one in a loop that most warps skip
-            uint32_t tm = 0u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tm |= touched_bit(qv, w[j]) << j;
-            mism = 8 - __popc(tm);
-            while (tm) {
-                const int j = __ffs(tm) - 1;
-                tm &= tm - 1u;
-                const uint32_t lo4 = (j & 2) ? ((j & 1) ? c0.w : c0.z) : ((j & 1) ? c0.y : c0.x);
-                const uint32_t hi4 = (j & 2) ? ((j & 1) ? c1.w : c1.z) : ((j & 1) ? c1.y : c1.x);
-                const uint32_t wj = (j & 4) ? hi4 : lo4;
-                const uint32_t r = look_touched(qv, wj, idx + (j & 3) + ((j >> 2) << 7), e0, e1, e2);
-                mism += r & 1u;
-                t.qdefV += r >> 1;
-            }
-#else
             // (a branch-free variant — all 8 bitmap tests first, touched words afterwards — measured slower on
             //  B200: more registers, spills at 64 regs/thread, 57 vs 42 us at ceiling 250; profiles/README.md)
 #pragma unroll
@@ -348,7 +330,6 @@ __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __r
                     t.qdefV += r >> 1;
                 } else mism += 1;
             }
-#endif
         } else {                                                // the last, partial step
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -384,99 +365,6 @@ __device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __r
     }
     return t;
 }
-#else
-// One warp streams one candidate row against the query (all 32 lanes must call).
-template <bool COUNT>
-__device__ __forceinline__ Tally stream_row(const QView& qv, const uint32_t* __restrict__ d, uint32_t e0, uint32_t e1,
-                                            uint32_t e2, uint32_t e3, uint32_t e4, uint32_t e5, int k, int pos_bits,
-                                            uint32_t pmask, int lane, unsigned long long& touched) {
-    Tally t; t.S1 = 0; t.qdefV = 0; t.qdefU = 0; t.nNc = 0; t.nNU = 0; t.nNM = 0; t.dead = false;
-    // 256 words per warp step (two 128-bit loads per lane), the next 256 already in flight
-    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-    if ((uint32_t)lane * 4u < e5) { c0 = ld_stream_v4(d + lane * 4); if (COUNT) touched += 16; }
-    if ((uint32_t)lane * 4u + 128u < e5) { c1 = ld_stream_v4(d + lane * 4 + 128); if (COUNT) touched += 16; }
-    for (uint32_t base = 0; base < e5; base += 256) {
-        const uint32_t idx = base + lane * 4;
-        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-        if (idx + 256u < e5) { n0 = ld_stream_v4(d + idx + 256); if (COUNT) touched += 16; }
-        if (idx + 384u < e5) { n1 = ld_stream_v4(d + idx + 384); if (COUNT) touched += 16; }
-        const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        int mism = 0;
-        if (base + 256u <= e3) {                                // warp-uniform: the whole step is V words
-            // (a branch-free variant — all 8 bitmap tests first, touched words afterwards — measured slower on
-            //  B200: more registers, spills at 64 regs/thread, 57 vs 42 us at ceiling 250; profiles/README.md)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (touched_bit(qv, w[j])) {
-                    const uint32_t r = look_touched(qv, w[j], idx + (j & 3) + ((j >> 2) << 7), e0, e1, e2);
-                    mism += r & 1u;
-                    t.qdefV += r >> 1;
-                } else mism += 1;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t ii = idx + (j & 3) + ((j >> 2) << 7);
-                if (ii < e3) {
-                    if (touched_bit(qv, w[j])) {
-                        const uint32_t r = look_touched(qv, w[j], ii, e0, e1, e2);
-                        mism += r & 1u;
-                        t.qdefV += r >> 1;
-                    } else mism += 1;
-                } else if (ii < e5) {
-                    const uint32_t s = w[j] & pmask;
-                    const uint32_t len = (pos_bits >= 32) ? 1u : ((w[j] >> pos_bits) + 1u);
-                    const bool isN = ii < e4;
-                    uint32_t aD, aU, aM, bD, bU, bM;
-                    rank3(qv, s, aD, aU, aM, isN);
-                    rank3(qv, s + len, bD, bU, bM, isN);
-                    t.qdefU += (int)(bD - aD);
-                    if (isN) { t.nNc += (int)len; t.nNU += (int)(bU - aU); t.nNM += (int)(bM - aM); }
-                }
-            }
-        }
-        if (base < e3) {                                        // warp-uniform: this step touched V words
-            t.S1 += __reduce_add_sync(0xffffffffu, mism);
-            if (t.S1 > k) { t.dead = true; break; }
-        }
-        c0 = n0; c1 = n1;
-    }
-    return t;
-}
-
-#endif
-
-// STREAM variant pre-pass on the row's 16-bit fingerprints (stored behind its list words): a V position whose coarse
-// block the query does not touch at all is a certain mismatch, so once their count exceeds the ceiling the pair is
-// proven "not a neighbour" from 2 bytes and ~4 instructions per word instead of 4 bytes and ~30.
-template <bool COUNT>
-__device__ __forceinline__ bool prepass_dead(const QView& qv, const uint32_t* __restrict__ d, uint32_t e3, uint32_t e5,
-                                             int k, int lane, unsigned long long& touched) {
-    const uint32_t* fp = d + ((e5 + 3u) & ~3u);
-    const uint32_t n8 = (e3 + 7u) >> 3;                        // 8 fingerprints per 128-bit load
-    int S = 0;
-    for (uint32_t b = 0; b < n8; b += 64) {                    // two loads per lane in flight: 512 fingerprints per step
-        uint4 f0 = make_uint4(0, 0, 0, 0), f1 = f0;
-        const bool h0 = b + lane < n8, h1 = b + 32u + lane < n8;
-        if (h0) { f0 = ld_stream_v4(fp + 4u * (b + lane)); if (COUNT) touched += 16; }
-        if (h1) { f1 = ld_stream_v4(fp + 4u * (b + 32u + lane)); if (COUNT) touched += 16; }
-        int s = 0;
-        if (h0) {
-            const uint32_t w[4] = {f0.x, f0.y, f0.z, f0.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s += 2 - (int)qv.cmap[w[i] & 0xffffu] - (int)qv.cmap[w[i] >> 16];
-        }
-        if (h1) {
-            const uint32_t w[4] = {f1.x, f1.y, f1.z, f1.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s += 2 - (int)qv.cmap[w[i] & 0xffffu] - (int)qv.cmap[w[i] >> 16];
-        }
-        S += __reduce_add_sync(0xffffffffu, s);
-        if (S > k) return true;
-    }
-    return false;
-}
-
 __device__ __forceinline__ void emit_if_close(const CompareParams& p, const Tally& t0, int k, uint32_t nVq, uint32_t nUq,
                                               uint32_t nMq, long long qrow, long long crow, int lane) {
     if (t0.dead) return;
@@ -522,7 +410,7 @@ __device__ __forceinline__ void signal_done(const CompareParams& p) {
 #ifndef FN3_Q_MINB
 #define FN3_Q_MINB 2
 #endif
-template <bool COUNT, int QMODE, bool FILTER>
+template <bool COUNT, int QMODE>
 __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const CompareParams p) {
     extern __shared__ __align__(128) uint4 qsm[];
     __shared__ uint32_t ws[99];
@@ -542,7 +430,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     // FILTER: work unit = 32 candidates.  Consecutive units (tiles hold consecutively inserted rows, i.e. relatives)
     // go to different CTAs, so that the few surviving candidates of a family are streamed on different SMs.
     // (Requesting the first unit's heads before the query build was measured: no gain, +58 registers.)
-    const uint32_t units = !FILTER ? 0u : p.rows ? (uint32_t)((p.n_list + 31) >> 5)
+    const uint32_t units = p.rows ? (uint32_t)((p.n_list + 31) >> 5)
                            : (uint32_t)(((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5));
     const uint32_t u0 = (uint32_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     uint32_t nVq, nUq, nMq;
@@ -567,11 +455,9 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     const int k = p.ceiling;
     const int pos_bits = p.pos_bits;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
-    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     unsigned long long touched = 0;
 
-    if (FILTER) {
+    {
         // upper triangle: superblocks that hold only rows <= skip_le cannot contain a candidate
         const int exclude = (int)qs.exclude, skip_le = (int)qs.skip_le;
         const uint32_t ufirst = (p.rows || skip_le < 0) ? 0u
@@ -687,46 +573,6 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
                 }
                 survivors(pass, row, false, -1, true, h0, h1);
             }
-        }
-    } else {
-        // one warp per candidate; the next candidate's header is requested before the current row is streamed
-        const long long n = p.rows ? p.n_list
-                                   : ((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << p.hdr.sb_shift;   // slots
-        auto fetch = [&](long long ci, long long& r, uint4& a, uint4& b) {
-            a = make_uint4(0, 0, 0, 0); b = a; r = -1;
-            if (ci < n) {
-                const unsigned char* tile; int tl;
-                if (p.rows) { r = p.rows[ci]; tile = tile_of(p.hdr, r, tl); }
-                else {
-                    const long long t = ci >> 5, chunk = t >> tshift, lt = t & ((1ll << tshift) - 1);
-                    tl = (int)(ci & 31);
-                    r = (chunk << p.hdr.shift) + fn3_row_of(lt, tl, p.hdr.sb_shift);
-                    tile = p.hdr.chunk[chunk] + lt * FN3_TILE_BYTES;
-                    if (r >= p.n_rows) r = -1;
-                }
-                if (r >= 0 && r != qs.exclude && r > qs.skip_le) {
-                    const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
-                    a = __ldg(hp); b = __ldg(hp + 1);
-                    if (COUNT && lane == 0) touched += 32;
-                }
-            }
-        };
-        long long i = warp0, row;
-        uint4 h0, h1;
-        fetch(i, row, h0, h1);
-        while (i < n) {
-            long long nrow; uint4 n0, n1;
-            fetch(i + nwarps, nrow, n0, n1);
-            if ((h0.x | h0.y) != 0u) {
-                const uint32_t* d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
-                // rows with more V words than the ceiling can be rejected by the fingerprint pre-pass
-                const bool dead = (long long)h1.y > (long long)k && prepass_dead<COUNT>(qv, d, h1.y, h1.w, k, lane, touched);
-                if (!dead) {
-                    const Tally t = stream_row<COUNT>(qv, d, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, k, pos_bits, pmask, lane, touched);
-                    emit_if_close(p, t, k, nVq, nUq, nMq, qs.row, row, lane);
-                }
-            }
-            i += nwarps; row = nrow; h0 = n0; h1 = n1;
         }
     }
     if (COUNT) {

@@ -116,4 +116,6 @@ struct CompareParams {
     int nw;                        // bmpref words (multiple of 4)
     int ncw;                       // coarse byte map size in 32-bit words (multiple of 8)
     int debug_stop;                // profiling aid: 1 stop after build, 2 after phase A, 3 at entry, 4 after slot load
+    unsigned int ring_off;         // k_scan: byte offset of the row rings in dynamic shared memory (multiple of 128)
+    int split_shift;               // k_scan: a 32-row work unit is drawn as 1 << split_shift sub-units
 };

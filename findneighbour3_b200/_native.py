@@ -73,6 +73,31 @@ SIGNATURES = {
     "fn3_unpickle_samples": (C.c_int, [C.c_int64, _u8p, _i64p, _i32p, C.c_int64, _i64p, _u8p, _i64p]),
     "fn3_profile_queries": (C.c_int, [_vp, _i64p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i64p, _i64p]),
     "fn3_launch_count": (C.c_int64, [_vp]),
+    # engine groups (one process, several GPUs): same argument lists as the single-engine calls of the same name
+    "fn3_group_create": (_vp, [C.c_int64, C.c_int32, _i32p]),
+    "fn3_group_destroy": (C.c_int, [_vp]),
+    "fn3_group_last_error": (C.c_char_p, [_vp]),
+    "fn3_group_n_devices": (C.c_int32, [_vp]),
+    "fn3_group_peer_access": (C.c_int32, [_vp]),
+    "fn3_group_engine": (_vp, [_vp, C.c_int32]),
+    "fn3_group_launch_count": (C.c_int64, [_vp]),
+    "fn3_group_append": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, _i64p]),
+    "fn3_group_append_bulk": (C.c_int, [_vp, C.c_int64, _i32p, _i64p, _u8p, _i64p]),
+    "fn3_group_remove": (C.c_int, [_vp, C.c_int64]),
+    "fn3_group_row_get": (C.c_int, [_vp, C.c_int64, _i32p, C.c_int64, _i32p, _i32p, _i64p]),
+    "fn3_group_stats_get": (C.c_int, [_vp, _vp]),
+    "fn3_group_set_reference": (C.c_int, [_vp, C.c_char_p, _i32p, C.c_int64]),
+    "fn3_group_insert_query": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, _vp, C.c_int64, _i64p]),
+    "fn3_group_ingest_query": (C.c_int, [_vp, C.c_char_p, C.c_int64, C.c_int32, _i64p, _i32p, C.c_int64, _i32p, C.c_char_p,
+                                         C.c_int64, _i64p, _i32p, _i64p, _vp, C.c_int64, _i64p]),
+    "fn3_group_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, _i64p, C.c_int64, _vp, C.c_int64, _i64p]),
+    "fn3_group_lists_vs_all": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, C.c_int64, _vp, C.c_int64, _i64p]),
+    "fn3_group_pair": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, _vp, _i32p]),
+    "fn3_group_all_vs_all": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int64, _i64p]),
+    "fn3_group_consensus": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),
+    "fn3_group_consensus_lists": (C.c_int, [_vp, C.c_int64, _i32p, _i64p, C.c_int64, _i32p, C.c_int64, _i32p, _i64p]),
+    "fn3_group_msa_sites_rule": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int32, _i32p, C.c_int64, _i64p]),
+    "fn3_group_msa_align": (C.c_int, [_vp, _i64p, C.c_int64, _i32p, C.c_int64, _u8p, _i32p]),
 }
 
 _lib = None

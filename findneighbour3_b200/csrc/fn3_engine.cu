@@ -854,7 +854,7 @@ static bool use_filter_for(int ceiling) { return ceiling <= FN3_HEAD_FP - 8; }
 template <bool COUNT, int QMODE>
 static void launch_query(bool filter, dim3 g, size_t smem, cudaStream_t st, const CompareParams& p) {
     if (filter) k_query<COUNT, QMODE><<<g, FN3_Q_THREADS, smem, st>>>(p);
-    else k_scan<COUNT, QMODE><<<g, FN3_Q_THREADS, smem, st>>>(p);
+    else k_scan<COUNT, QMODE><<<g, FN3_SCAN_THREADS, smem, st>>>(p);
 }
 
 struct QueryJob {                    // what enqueue_query needs beyond the engine state
@@ -919,7 +919,7 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
         p.host_flag = reinterpret_cast<volatile unsigned long long*>(e->zc_buf);
         p.done_ctas = e->d_done; p.host_cap = FN3_ZC_CAP; p.seq = e->zc_seq;
     }
-    const long long warps_per_cta = FN3_Q_THREADS / 32;
+    const long long warps_per_cta = (filter ? FN3_Q_THREADS : FN3_SCAN_THREADS) / 32;
     const long long sb = 1ll << e->sb_shift;
     const long long slots_scanned = ((job.n_rows + sb - 1) / sb) * sb;          // whole superblocks of head tiles
     const long long cand = job.d_rows ? job.n_list : slots_scanned;
@@ -1968,3 +1968,5 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     if (sync != cudaSuccess) return set_err(e, FN3_ECUDA, "fn3_profile_queries: %s", cudaGetErrorString(sync));
     return FN3_OK;
 }
+
+#include "fn3_group.inl"

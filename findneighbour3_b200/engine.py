@@ -59,6 +59,14 @@ def byte_histogram(data, device=0):
     return hist
 
 
+# calls that exist both for one engine (fn3_<name>) and for an engine group (fn3_group_<name>)
+_SHARED_CALLS = ("append", "append_bulk", "remove", "stats_get", "row_get", "set_reference", "one_vs_all", "insert_query",
+                 "ingest_query", "lists_vs_all", "pair", "consensus", "consensus_lists", "msa_sites_rule", "msa_align",
+                 "launch_count", "last_error", "destroy")
+# calls that always run on ONE engine (a group uses its first member)
+_LOCAL_CALLS = ("compress", "pair_lists", "profile_queries")
+
+
 class Engine:
     def __init__(self, genome_length, device=0):
         self._lib = N.load()
@@ -66,8 +74,20 @@ class Engine:
         if not self._h:
             msg = self._lib.fn3_last_error(None)
             raise EngineError("fn3_create failed: %s" % (msg.decode() if msg else "unknown"))
+        self._hl = self._h
+        self._bind("fn3_")
         self.genome_length = int(genome_length)
         self.device = int(device)
+        self.n_devices = 1
+        self._init_buffers()
+
+    def _bind(self, prefix):
+        for name in _SHARED_CALLS:
+            setattr(self, "_f_" + name, getattr(self._lib, prefix + name))
+        for name in _LOCAL_CALLS:
+            setattr(self, "_f_" + name, getattr(self._lib, "fn3_" + name))
+
+    def _init_buffers(self):
         self._hits = np.empty(4096, dtype=HIT_DTYPE)
         self._edges = np.empty(1 << 16, dtype=EDGE_DTYPE)
         self._cpos = np.empty(1 << 16, dtype=np.int32)
@@ -82,8 +102,9 @@ class Engine:
     # -- plumbing -------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.fn3_destroy(self._h)
+            self._f_destroy(self._h)
             self._h = None
+            self._hl = None
 
     def __del__(self):
         try:
@@ -94,7 +115,7 @@ class Engine:
     def _check(self, rc):
         if rc == N.FN3_OK:
             return
-        msg = self._lib.fn3_last_error(self._h)
+        msg = self._f_last_error(self._h)
         msg = msg.decode() if msg else "fn3 error %d" % rc
         if rc == N.FN3_EARG:
             raise ValueError(msg)
@@ -109,13 +130,13 @@ class Engine:
         """persist one sample (six sorted lists A,C,G,T,N,M as pos + 7 offsets) -> row index."""
         row = C.c_int64(-1)
         if invalid:
-            rc = self._lib.fn3_append(self._h, None, None, 1, C.byref(row))
+            rc = self._f_append(self._h, None, None, 1, C.byref(row))
         else:
             pos = _as_i32(pos)
             off = _as_i32(off)
             if off.shape != (7,):
                 raise ValueError("off must have 7 entries")
-            rc = self._lib.fn3_append(self._h, _ptr(pos, _i32p), _ptr(off, _i32p), 0, C.byref(row))
+            rc = self._f_append(self._h, _ptr(pos, _i32p), _ptr(off, _i32p), 0, C.byref(row))
         self._check(rc)
         self._n_rows = max(self._n_rows, row.value + 1)
         return row.value
@@ -131,17 +152,17 @@ class Engine:
         if inv is not None and inv.size != n:
             raise ValueError("invalid must have n entries")
         first = C.c_int64(-1)
-        rc = self._lib.fn3_append_bulk(self._h, n, _ptr(pos, _i32p), _ptr(off, _i64p), _ptr(inv, _u8p), C.byref(first))
+        rc = self._f_append_bulk(self._h, n, _ptr(pos, _i32p), _ptr(off, _i64p), _ptr(inv, _u8p), C.byref(first))
         self._check(rc)
         self._n_rows = max(self._n_rows, first.value + n)
         return first.value
 
     def remove(self, row):
-        self._check(self._lib.fn3_remove(self._h, int(row)))
+        self._check(self._f_remove(self._h, int(row)))
 
     def stats(self):
         st = N.Stats()
-        self._check(self._lib.fn3_stats_get(self._h, C.byref(st)))
+        self._check(self._f_stats_get(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in N.Stats._fields_}
 
     def row_get(self, row):
@@ -152,7 +173,7 @@ class Engine:
         cap = 1024
         while True:
             pos = np.empty(cap, dtype=np.int32)
-            rc = self._lib.fn3_row_get(self._h, int(row), _ptr(pos, _i32p), cap, _ptr(off, _i32p),
+            rc = self._f_row_get(self._h, int(row), _ptr(pos, _i32p), cap, _ptr(off, _i32p),
                                        C.byref(inv), C.byref(npos))
             if rc == N.FN3_ECAPACITY:
                 cap = int(npos.value)
@@ -169,7 +190,7 @@ class Engine:
         ex = None
         if excluded is not None and len(excluded) > 0:
             ex = np.sort(np.fromiter(excluded, dtype=np.int64, count=len(excluded))).astype(np.int32)
-        self._check(self._lib.fn3_set_reference(self._h, ref, _ptr(ex, _i32p), 0 if ex is None else ex.size))
+        self._check(self._f_set_reference(self._h, ref, _ptr(ex, _i32p), 0 if ex is None else ex.size))
 
     def compress(self, seq_bytes):
         """device compress of one sequence (bytes, len = genome length) -> (pos int32[], off int32[7], m_chars bytes)."""
@@ -179,7 +200,7 @@ class Engine:
             off = np.zeros(7, dtype=np.int32)
             npos = C.c_int64(0)
             while True:
-                rc = self._lib.fn3_compress(self._h, seq_bytes, _ptr(self._cpos, _i32p), self._cpos.size,
+                rc = self._f_compress(self._hl, seq_bytes, _ptr(self._cpos, _i32p), self._cpos.size,
                                             _ptr(off, _i32p), self._cm, len(self._cm), C.byref(npos))
                 if rc == N.FN3_ECAPACITY:
                     n_m = int(off[6] - off[5])
@@ -208,7 +229,7 @@ class Engine:
             n_cand = self._n_rows if rows_a is None else rows_a.size
             buf = self._hit_buf(max(int(n_cand), 1))
             n_out = C.c_int64(0)
-            rc = self._lib.fn3_one_vs_all(self._h, int(query_row), int(ceiling), _ptr(rows_a, _i64p),
+            rc = self._f_one_vs_all(self._h, int(query_row), int(ceiling), _ptr(rows_a, _i64p),
                                           0 if rows_a is None else rows_a.size,
                                           self._hits_ptr, buf.size, C.byref(n_out))
             self._check(rc)
@@ -224,10 +245,14 @@ class Engine:
                 pos_a, off_a = None, None
             else:
                 pos_a, off_a = _as_i32(pos), _as_i32(off)
-            rc = self._lib.fn3_insert_query(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
+            rc = self._f_insert_query(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
                                             int(ceiling), C.byref(row), self._hits_ptr, buf.size, C.byref(n_out))
             if row.value >= 0:
                 self._n_rows = max(self._n_rows, row.value + 1)
+            if rc == N.FN3_ECAPACITY and row.value >= 0:
+                # the row IS stored (include/fn3.h); only the neighbour buffer was too small: ask again with room
+                buf = self._hit_buf(int(n_out.value))
+                rc = self._f_one_vs_all(self._h, row.value, int(ceiling), None, 0, self._hits_ptr, buf.size, C.byref(n_out))
             self._check(rc)
             return row.value, _take(buf, n_out.value)
 
@@ -244,7 +269,7 @@ class Engine:
             buf = self._hit_buf(max(self._n_rows + 1, 1))
             cap = int(max_ns) if max_ns < (1 << 62) else (1 << 62)
             while True:
-                rc = self._lib.fn3_ingest_query(self._h, seq_bytes, cap, int(ceiling), _ptr(hist), _ptr(self._cpos), self._cpos.size,
+                rc = self._f_ingest_query(self._h, seq_bytes, cap, int(ceiling), _ptr(hist), _ptr(self._cpos), self._cpos.size,
                                                 _ptr(off), self._cm, len(self._cm), C.byref(npos), C.byref(invalid),
                                                 C.byref(row), self._hits_ptr, buf.size, C.byref(n_out))
                 if rc == N.FN3_ECAPACITY and row.value < 0:                 # the compress step ran out of room: nothing stored
@@ -257,6 +282,9 @@ class Engine:
                 break
             if row.value >= 0:
                 self._n_rows = max(self._n_rows, row.value + 1)
+            if rc == N.FN3_ECAPACITY and row.value >= 0:           # stored; the neighbour buffer was too small
+                buf = self._hit_buf(int(n_out.value))
+                rc = self._f_one_vs_all(self._h, row.value, int(ceiling), None, 0, self._hits_ptr, buf.size, C.byref(n_out))
             self._check(rc)
             n_m = int(off[6] - off[5])
             return (row.value, bool(invalid.value), self._cpos[: npos.value].copy(), off, self._cm.raw[:n_m],
@@ -272,7 +300,7 @@ class Engine:
                 pos_a, off_a = None, None
             else:
                 pos_a, off_a = _as_i32(pos), _as_i32(off)
-            rc = self._lib.fn3_lists_vs_all(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
+            rc = self._f_lists_vs_all(self._h, _ptr(pos_a, _i32p), _ptr(off_a, _i32p), 1 if invalid else 0,
                                             int(ceiling), _ptr(rows_a, _i64p), 0 if rows_a is None else rows_a.size,
                                             self._hits_ptr, buf.size, C.byref(n_out))
             self._check(rc)
@@ -298,7 +326,7 @@ class Engine:
         """countDifferences_byKey on stored rows -> (dist,n1,n2,nboth) or None."""
         hit = N.Hit()
         has = C.c_int32(0)
-        self._check(self._lib.fn3_pair(self._h, int(row1), int(row2), int(ceiling), C.byref(hit), C.byref(has)))
+        self._check(self._f_pair(self._h, int(row1), int(row2), int(ceiling), C.byref(hit), C.byref(has)))
         if not has.value:
             return None
         return (hit.dist, hit.n1, hit.n2, hit.nboth)
@@ -311,7 +339,7 @@ class Engine:
         o1 = None if invalid1 else _as_i32(off1)
         p2 = None if invalid2 else _as_i32(pos2)
         o2 = None if invalid2 else _as_i32(off2)
-        rc = self._lib.fn3_pair_lists(self._h, _ptr(p1, _i32p), _ptr(o1, _i32p), 1 if invalid1 else 0,
+        rc = self._f_pair_lists(self._hl, _ptr(p1, _i32p), _ptr(o1, _i32p), 1 if invalid1 else 0,
                                       _ptr(p2, _i32p), _ptr(o2, _i32p), 1 if invalid2 else 0, int(ceiling),
                                       C.byref(hit), C.byref(has))
         self._check(rc)
@@ -337,7 +365,7 @@ class Engine:
     def consensus(self, rows, min_votes):
         """per-list positions carried by >= min_votes of the stored rows -> (pos, off[6]) in list order A,C,G,T,N."""
         r = np.ascontiguousarray(rows, dtype=np.int64)
-        return self._consensus_call(lambda p, cap, off, npos: self._lib.fn3_consensus(
+        return self._consensus_call(lambda p, cap, off, npos: self._f_consensus(
             self._h, _ptr(r, _i64p), r.size, int(min_votes), p, cap, off, npos))
 
     def consensus_lists(self, pos_in, off_in, min_votes):
@@ -347,7 +375,7 @@ class Engine:
         n = (off_in.size - 1) // 6
         if off_in.size != 6 * n + 1:
             raise ValueError("off must have 6*n+1 entries")
-        return self._consensus_call(lambda p, cap, off, npos: self._lib.fn3_consensus_lists(
+        return self._consensus_call(lambda p, cap, off, npos: self._f_consensus_lists(
             self._h, n, _ptr(pos_in, _i32p), _ptr(off_in, _i64p), int(min_votes), p, cap, off, npos))
 
     def msa_sites(self, rows, n_is_call=False):
@@ -358,7 +386,7 @@ class Engine:
         cap = 1 << 14
         while True:
             sites = np.empty(cap, dtype=np.int32)
-            rc = self._lib.fn3_msa_sites_rule(self._h, _ptr(r, _i64p), r.size, 1 if n_is_call else 0, _ptr(sites, _i32p), cap,
+            rc = self._f_msa_sites_rule(self._h, _ptr(r, _i64p), r.size, 1 if n_is_call else 0, _ptr(sites, _i32p), cap,
                                               C.byref(n_sites))
             if rc == N.FN3_ECAPACITY:
                 cap = int(n_sites.value)
@@ -372,7 +400,7 @@ class Engine:
         s = _as_i32(sites)
         counts = np.zeros((r.size, 4), dtype=np.int32)
         codes = np.zeros((r.size, s.size), dtype=np.uint8) if want_codes else None
-        rc = self._lib.fn3_msa_align(self._h, _ptr(r, _i64p), r.size, _ptr(s, _i32p), s.size,
+        rc = self._f_msa_align(self._h, _ptr(r, _i64p), r.size, _ptr(s, _i32p), s.size,
                                      _ptr(codes, _u8p) if codes is not None and codes.size else None,
                                      _ptr(counts, _i32p))
         self._check(rc)
@@ -387,11 +415,63 @@ class Engine:
         ms_cmp = np.zeros(n, dtype=np.float32)
         n_hits = np.zeros(n, dtype=np.int64)
         touched = np.zeros(n, dtype=np.int64) if count_bytes else None
-        rc = self._lib.fn3_profile_queries(self._h, _ptr(q, _i64p), n, int(ceiling), 1 if flush_l2 else 0,
+        rc = self._f_profile_queries(self._hl, _ptr(q, _i64p), n, int(ceiling), 1 if flush_l2 else 0,
                                            _ptr(ms_build, _f32p), _ptr(ms_cmp, _f32p), _ptr(n_hits, _i64p),
                                            _ptr(touched, _i64p))
         self._check(rc)
         return {"ms_build": ms_build, "ms_compare": ms_cmp, "n_hits": n_hits, "bytes_touched": touched}
 
     def launch_count(self):
-        return int(self._lib.fn3_launch_count(self._h))
+        return int(self._f_launch_count(self._h))
+
+
+class GroupEngine(Engine):
+    """An engine GROUP (include/fn3.h, fn3_group_*): the store sharded over several GPUs of one box, driven from THIS
+    process — global row g lives on devices[g % G].  Same methods, same row numbering (global rows) and same results as
+    `Engine`; every query fans out to one host thread per device inside libfn3 and the neighbour records are merged there.
+    compress / pair_lists / profile_queries run on the first member engine."""
+
+    def __init__(self, genome_length, devices):
+        self._lib = N.load()
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        if devs.size < 1:
+            raise ValueError("an engine group needs at least one device")
+        self._h = self._lib.fn3_group_create(int(genome_length), int(devs.size), _ptr(devs))
+        if not self._h:
+            msg = self._lib.fn3_last_error(None)
+            raise EngineError("fn3_group_create failed: %s" % (msg.decode() if msg else "unknown"))
+        self._hl = self._lib.fn3_group_engine(self._h, 0)
+        self._bind("fn3_group_")
+        self.genome_length = int(genome_length)
+        self.devices = [int(d) for d in devs]
+        self.device = self.devices[0]
+        self.n_devices = len(self.devices)
+        self.peer_access = bool(self._lib.fn3_group_peer_access(self._h))
+        self._init_buffers()
+
+    def member(self, i):
+        """handle of the i-th member engine (bench.py: per-device profiling)"""
+        return self._lib.fn3_group_engine(self._h, int(i))
+
+    def all_vs_all(self, ceiling, upper_only=True, row_begin=0, row_end=None, stride=1, phase=0):
+        """distmat over the sharded store: every device takes every live row as a query against its own shard (rows of
+        other shards are read over NVLink).  Block-row arguments do not apply to a group (it already uses every device)."""
+        if row_begin != 0 or row_end is not None or stride != 1 or phase != 0:
+            raise ValueError("an engine group computes the whole matrix: no block-row arguments")
+        with self._q_lock:
+            n_out = C.c_int64(0)
+            buf = self._edges
+            rc = self._lib.fn3_group_all_vs_all(self._h, int(ceiling), 1 if upper_only else 0, _ptr(buf), buf.size, C.byref(n_out))
+            if rc == N.FN3_ECAPACITY:
+                buf = self._edges = np.empty(int(n_out.value), dtype=EDGE_DTYPE)
+                rc = self._lib.fn3_group_all_vs_all(self._h, int(ceiling), 1 if upper_only else 0, _ptr(buf), buf.size,
+                                                    C.byref(n_out))
+            self._check(rc)
+            return buf[: n_out.value].copy()
+
+
+def make_engine(genome_length, device=0):
+    """`device`: one CUDA ordinal -> Engine; a list / tuple of ordinals -> GroupEngine over those GPUs."""
+    if isinstance(device, (list, tuple)):
+        return GroupEngine(genome_length, device)
+    return Engine(genome_length, device)

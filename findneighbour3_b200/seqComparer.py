@@ -19,6 +19,7 @@ persist() time instead of at the first comparison.
 import hashlib
 import json
 import math
+import os
 import pickle
 import threading
 import uuid
@@ -28,7 +29,7 @@ from collections.abc import MutableMapping
 import numpy as np
 
 from . import packing
-from .engine import Engine
+from .engine import Engine, make_engine
 
 _BASES5 = ("A", "C", "T", "G", "N")
 
@@ -94,8 +95,11 @@ class _Profile(MutableMapping):
 
 class seqComparer():
     def __init__(self, reference, maxNs, snpCeiling, debugMode=False, excludePositions=set(),
-                 snpCompressionCeiling=250, cpuCount=1, device=0):
-        """Same arguments as the reference (src/seqComparer.py:32-40); `device` (CUDA ordinal) is new.
+                 snpCompressionCeiling=250, cpuCount=1, device=None):
+        """Same arguments as the reference (src/seqComparer.py:32-40); `device` is new: one CUDA ordinal, or a list of
+        ordinals — the store is then sharded over those GPUs and this ONE object (the server constructs one,
+        findNeighbour3-server.py:340-345) drives all of them (engine.GroupEngine).  Left out, it is read from the
+        environment variable FN3_DEVICES ("0" by default; "0,1,2,3,4,5,6,7" hands the unmodified server eight GPUs).
         cpuCount is accepted and ignored, as in the reference (:65, :112)."""
         self.compressed_sequence_keys = set(['invalid', 'A', 'C', 'G', 'T', 'N', 'M'])
         self.patch_and_consensus_keys = set(['consensus_md5', 'patch'])
@@ -121,6 +125,9 @@ class seqComparer():
 
         # device store: created on first use, so that the host-only methods (compress, hashes, patches) work
         # anywhere; anything that needs a distance needs the CUDA engine and fails loudly without it.
+        if device is None:
+            ids = [int(x) for x in os.environ.get("FN3_DEVICES", "0").split(",") if x.strip() != ""]
+            device = ids[0] if len(ids) == 1 else ids
         self._device = device
         self._engine = None
         # persist() may run on another request thread while a query is in flight (server.py:513-516 is outside the
@@ -146,7 +153,7 @@ class seqComparer():
         if self._engine is None:
             if len(self.reference) == 0:
                 raise TypeError("reference cannot be of zero length")
-            self._engine = Engine(len(self.reference), self._device)     # raises if libfn3.so / a GPU is missing
+            self._engine = make_engine(len(self.reference), self._device)     # raises if libfn3.so / a GPU is missing
         return self._engine
 
     def _engine_with_reference(self):
@@ -203,9 +210,6 @@ class seqComparer():
         """Bulk persist (server start-up reload, findNeighbour3-server.py:358-362): one device copy for all."""
         objects, guids = list(objects), list(guids)
         fresh = [(o, g) for o, g in zip(objects, guids)]
-        for _, g in fresh:
-            if g in self._row_of:
-                self._drop_row(g)
         packed = [self._lists_of(o) for o, _ in fresh]
         n = len(packed)
         off = np.zeros(6 * n + 1, dtype=np.int64)
@@ -216,12 +220,16 @@ class seqComparer():
             off[6 * i: 6 * i + 7] = total + f.astype(np.int64)
             total += int(f[6])
         pos = np.concatenate([p for p, _, _ in packed]) if total else np.empty(0, dtype=np.int32)
-        first = self.engine.append_bulk(pos, off, inv)
-        for i, ((o, g), (p, f, bad)) in enumerate(zip(fresh, packed)):
-            self._row_of[g] = first + i
-            self._guid_of[first + i] = g
-            self._key_of[g] = packing.content_key(p, f, bad)
-            self.seqProfile._d[g] = o
+        with self._lock:                                 # the maps and the device store change together
+            for _, g in fresh:
+                if g in self._row_of:
+                    self._drop_row(g)
+            first = self.engine.append_bulk(pos, off, inv)
+            for i, ((o, g), (p, f, bad)) in enumerate(zip(fresh, packed)):
+                self._row_of[g] = first + i
+                self._guid_of[first + i] = g
+                self._key_of[g] = packing.content_key(p, f, bad)
+                self.seqProfile._d[g] = o
 
     def persist_pickles(self, blobs, guids):
         """Start-up reload straight from the stored form (findNeighbour3-server.py:358-362 reads GridFS pickles written by
@@ -282,7 +290,7 @@ class seqComparer():
                 off[6 * i: 6 * i + 7] = total + (0 if bad else f.astype(np.int64))
                 total += 0 if bad else int(f[6])
             pos = np.concatenate([p for p, _, bad in packed if not bad]) if total else np.empty(0, dtype=np.int32)
-            fresh = Engine(len(self.reference), self._device)
+            fresh = make_engine(len(self.reference), self._device)
             first = fresh.append_bulk(pos, off, inv) if n else 0
             self._engine = fresh
             self._ref_uploaded = False                       # uploaded again by the next compress / MSA call

@@ -27,7 +27,7 @@ _BASES5 = ("A", "C", "T", "G", "N")
 
 class seqComparer(_seqComparer):
     def __init__(self, reference, maxNs, snpCeiling, debugMode=False, excludePositions=set(),
-                 snpCompressionCeiling=250, cpuCount=None, device=0):
+                 snpCompressionCeiling=250, cpuCount=None, device=None):
         """Same arguments as src/seqComparer_mt.py:212-220; `device` (CUDA ordinal) is new.  cpuCount only selects
         which of the reference's two mcompare conventions is returned (:294-300 clamp it to 1..cpu_count)."""
         super().__init__(reference, maxNs, snpCeiling, debugMode, excludePositions, snpCompressionCeiling, 1, device)

@@ -8,16 +8,14 @@ Both go through torch.distributed on the group's backend: NCCL over NVLink with 
 gloo with host tensors in the CPU tests.  Sample i (global insertion order) lives on rank i % G as local row
 i // G, which keeps the shards balanced under streaming inserts.
 
-Both messages are KB-sized and host-originated / host-terminated (the server process holds the new sample; the
-neighbour list goes to MongoDB), so on ONE box there is a second transport, `exchange="shm"`: a POSIX shared-memory
-segment with sequence-number flags that every rank process maps — no device hop, no collective launch; the per-insert
-exchange cost drops from ~250 us (two torch.distributed collectives with their host synchronisations) to a few us.
-`exchange="nccl"` (torch.distributed on the group's backend) remains the default and the multi-node path.
+On ONE box the product path is the engine GROUP (include/fn3.h fn3_group_*, engine.GroupEngine): one process, one host
+thread per device inside libfn3, no collective at all.  This module is the multi-PROCESS form — one rank per GPU, as
+`torchrun` launches them, and the form that extends over several boxes.  (A second, shared-memory transport that lived
+here in round 1 was removed: the group does the same job without leaving the process.)
 
 The per-rank engine is duck-typed (append / insert_query / lists_vs_all / one_vs_all / row_get): the product
 passes findneighbour3_b200.engine.Engine; the CPU-only gloo tests pass a stand-in built on the oracle.
 """
-from multiprocessing import shared_memory
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -28,7 +26,7 @@ OP_INSERT, OP_QUERY, OP_REMOVE, OP_STOP = 1, 2, 3, 4     # ctl[0] of a served ro
 
 
 class ShardedStore:
-    def __init__(self, engine, group=None, max_hits=512, local_rows=0, exchange="nccl"):
+    def __init__(self, engine, group=None, max_hits=512, local_rows=0):
         self.engine = engine
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -51,114 +49,9 @@ class ShardedStore:
         # `local_rows`: rows the engine already holds (every rank the same number, placed as by load_shard)
         self._local_rows = int(local_rows)
         self.n_global = self._local_rows * self.world       # samples inserted so far (same value on every rank)
-        self.exchange = exchange if self.world > 1 else "nccl"
-        self._shm = None
-        if self.exchange == "shm":
-            self._shm_open()
-
-    # -- shared-memory transport (one box) ----------------------------------------------------
-    # layout (int64 words): [sample: seq | n, off[0..6], invalid, ctl | positions (int32 pairs packed as int64 view)]
-    #                       [per rank, TWO slots: seq | count | records (max_hits x 5 int32)]
-    # Round `seq` uses slot seq & 1.  A rank writes its slot of round seq+1 as soon as the next sample is out, which may be
-    # before a slow rank has collected round seq — with one slot per rank that reader would wait for a sequence number
-    # that is gone (a deadlock, reproduced with three ranks and one delayed reader).  Round seq+2 cannot start before
-    # every rank has written round seq+1, i.e. has finished collecting round seq: two slots suffice.
-    def _shm_open(self):
-        cap = self.bcast_cap
-        self._s_words = 16 + (cap + 1) // 2                         # sample area, int64 words
-        self._r_words = 2 + (HIT_FIELDS * self.max_hits + 1) // 2     # one result slot, int64 words
-        total = 8 * (self._s_words + 2 * self.world * self._r_words)
-        name = [None]
-        if self.rank == 0:
-            self._shm = shared_memory.SharedMemory(create=True, size=total)
-            np.frombuffer(self._shm.buf, dtype=np.int64)[:] = 0
-            name[0] = self._shm.name
-        dist.broadcast_object_list(name, src=0, group=self.group)
-        if self.rank != 0:
-            self._shm = shared_memory.SharedMemory(name=name[0])
-            try:                                  # the creator (rank 0) owns the segment: keep Python's resource
-                from multiprocessing import resource_tracker      # tracker of the other ranks from unlinking it
-                resource_tracker.unregister(self._shm._name, "shared_memory")
-            except Exception:
-                pass
-        w = np.frombuffer(self._shm.buf, dtype=np.int64)
-        self._s64 = w[: self._s_words]
-        self._s32 = self._s64[16:].view(np.int32)
-        self._r64 = [[w[self._s_words + (2 * r + b) * self._r_words: self._s_words + (2 * r + b + 1) * self._r_words]
-                      for b in range(2)] for r in range(self.world)]
-        self._r32 = [[x[2:].view(np.int32) for x in pair] for pair in self._r64]
-        self._seq = 0
-        dist.barrier(group=self.group)
 
     def close(self):
-        if self._shm is not None:
-            self._s64 = self._s32 = self._r64 = self._r32 = None
-            try:
-                self._shm.close()
-                if self.rank == 0:
-                    self._shm.unlink()
-            except Exception:
-                pass
-            self._shm = None
-
-    def _shm_exchange(self, sample, src, compute, ctl=(0, 0, 0)):
-        """one insert/query round over shared memory: `src` publishes the sample (+ three control words), every rank runs
-        `compute(pos, off, invalid, ctl) -> hits` and publishes its records, every rank collects all slots.
-        -> ({global id: (dist, n1, n2, nboth)}, ctl)"""
-        self._seq += 1
-        seq = self._seq
-        s64, s32 = self._s64, self._s32
-        if self.rank == src:
-            pos, off, invalid = sample if sample is not None else (None, None, True)
-            n = 0 if invalid else len(pos)
-            if n > self.bcast_cap:
-                raise ValueError("sample with %d positions exceeds the shared-memory exchange buffer (%d)" % (n, self.bcast_cap))
-            s64[1] = n
-            s64[2:9] = 0 if invalid else off
-            s64[9] = 1 if invalid else 0
-            s64[10:13] = ctl
-            if n:
-                s32[:n] = pos
-            s64[0] = seq                          # publish (x86 TSO: earlier stores are visible first)
-        else:
-            while s64[0] != seq:
-                pass
-        n = int(s64[1])
-        pos = s32[:n].copy()
-        off = s64[2:9].astype(np.int32)
-        invalid = bool(s64[9])
-        ctl = (int(s64[10]), int(s64[11]), int(s64[12]))
-        hits = compute(pos, off, invalid, ctl)
-        m = len(hits)
-        b = seq & 1
-        r64, r32 = self._r64[self.rank][b], self._r32[self.rank][b]
-        if 0 < m <= self.max_hits:
-            rec = r32[: HIT_FIELDS * m].reshape(m, HIT_FIELDS)
-            rec[:, 0] = hits["row"]; rec[:, 1] = hits["dist"]; rec[:, 2] = hits["n1"]
-            rec[:, 3] = hits["n2"]; rec[:, 4] = hits["nboth"]
-        r64[1] = m
-        r64[0] = seq
-        out = {}
-        counts = []
-        if getattr(self, "_debug_read_delay", 0):          # tests only: a reader that is slow to collect the slots
-            import time
-            time.sleep(self._debug_read_delay)
-        for r in range(self.world):
-            q64 = self._r64[r][b]
-            while q64[0] != seq:
-                pass
-            counts.append(int(q64[1]))
-        if max(counts) > self.max_hits:
-            # some rank found more neighbours than a result slot holds (its slot carries the count only): every rank sees
-            # the same counts, so all of them repeat the collection through the collective path, which grows its blocks
-            return self._gather_hits(hits), ctl
-        for r in range(self.world):
-            c = counts[r]
-            if c:
-                rec = self._r32[r][b][: HIT_FIELDS * c].reshape(c, HIT_FIELDS)
-                gids = (rec[:, 0].astype(np.int64) * self.world + r).tolist()
-                out.update(zip(gids, map(tuple, rec[:, 1:].tolist())))
-        return out, ctl
+        pass
 
     # -- id mapping -------------------------------------------------------------------------
     def owner(self, gid):
@@ -225,12 +118,21 @@ class ShardedStore:
         return pos, off, invalid, ctl
 
     def _exchange(self, sample, src, compute, ctl=(0, 0, 0)):
-        """one round on the configured transport: the sample and `ctl` go from `src` to every rank, every rank runs
-        `compute(pos, off, invalid, ctl) -> hits`, everybody receives all hits -> (dict, ctl)"""
-        if self.exchange == "shm":
-            return self._shm_exchange(sample, src, compute, ctl)
+        """one round: the sample and `ctl` go from `src` to every rank, every rank runs
+        `compute(pos, off, invalid, ctl) -> hits`, everybody receives all hits -> (dict, ctl).
+        A rank whose compute() raises still takes part in the gather (with an error marker), so that every rank raises
+        together instead of leaving the others waiting in the collective."""
         pos, off, invalid, ctl = self._bcast_sample(sample, src, ctl)
-        return self._gather_hits(compute(pos, off, invalid, ctl)), ctl
+        err = None
+        try:
+            hits = compute(pos, off, invalid, ctl)
+        except Exception as ex:                      # noqa: BLE001 - re-raised on every rank below
+            err = ex
+            hits = np.zeros(0, dtype=[("row", "<i8"), ("dist", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("nboth", "<i4")])
+        out = self._gather_hits(hits, failed=err is not None)
+        if err is not None:
+            raise err
+        return out, ctl
 
     def _all_gather_i64(self, t):
         if self.world == 1:
@@ -240,12 +142,13 @@ class ShardedStore:
         dist.all_gather_into_tensor(out, t, group=self.group)
         return out.cpu().reshape(self.world, -1)
 
-    def _gather_hits(self, hits):
+    def _gather_hits(self, hits, failed=False):
         """each rank's structured hits (local rows) -> dict {global id: (dist, n1, n2, nboth)} on every rank.
         One all-gather of fixed-size int32 blocks [count | row, dist, n1, n2, nboth ...] through pre-allocated
-        (pinned / device) buffers; a second, larger one only if some rank overflowed its block."""
+        (pinned / device) buffers; a second, larger one only if some rank overflowed its block.  A count of -1 marks
+        a rank whose engine call failed: every rank then raises."""
         cap = self.max_hits
-        n = len(hits)
+        n = -1 if failed else len(hits)
         while True:
             if cap == self.max_hits:
                 blk, dblk, dall, hall = self._hblk, self._dhblk, self._dhall, self._hhall
@@ -254,7 +157,7 @@ class ShardedStore:
                 dblk = dall = hall = None
             b = blk.numpy()
             b[0] = n
-            m = min(n, cap)
+            m = min(max(n, 0), cap)
             if m:
                 rec = b[1:1 + HIT_FIELDS * m].reshape(m, HIT_FIELDS)
                 rec[:, 0] = hits["row"][:m]
@@ -279,6 +182,10 @@ class ShardedStore:
                 dist.all_gather_into_tensor(hall, blk, group=self.group)
                 allb = hall.numpy().reshape(self.world, -1)
             counts = allb[:, 0]
+            if int(counts.min()) < 0:
+                if failed:
+                    return {}
+                raise RuntimeError("the engine call of this round failed on rank(s) %s" % np.flatnonzero(counts < 0).tolist())
             if int(counts.max()) <= cap:
                 break
             cap = int(counts.max())             # a rank overflowed its block: every rank repeats with room for all

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FN3_ABI_VERSION 3   /* 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align, fn3_unpickle_samples; 3: + fn3_msa_sites_rule, fn3_ingest_query, fn3_byte_histogram */
+#define FN3_ABI_VERSION 4   /* 4: + fn3_group_* (engine groups: one process, several GPUs); 2: + fn3_consensus, fn3_consensus_lists, fn3_msa_sites, fn3_msa_align, fn3_unpickle_samples; 3: + fn3_msa_sites_rule, fn3_ingest_query, fn3_byte_histogram */
 
 /* status codes */
 #define FN3_OK          0
@@ -263,6 +263,61 @@ int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows, const int3
  * pos_cap in elements (sum of blob sizes / 2 always suffices); FN3_ECAPACITY with *n_pos = required if too small. */
 int fn3_unpickle_samples(int64_t n, const uint8_t* blobs, const int64_t* blob_off, int32_t* pos, int64_t pos_cap,
                          int64_t* off, uint8_t* status, int64_t* n_pos);
+
+/* ---- engine groups: one process, every GPU of the box ------------------------------ */
+
+/* The reference's server constructs ONE seqComparer (findNeighbour3-server.py:340-345) and calls sc.mcompare from that
+ * one process (:530).  A group is that object's store spread over n_devices GPUs: global row g lives on device
+ * device_ids[g % n_devices] as local row g / n_devices (candidates sharded by insertion order), and every
+ * call below fans out to one host thread per device inside the library — each enqueues on its own device's stream and
+ * waits for its own completion flag — and merges the thresholded neighbour records.  All row arguments and results are
+ * GLOBAL rows; semantics, status codes and capacity protocol are those of the single-engine call of the same name.
+ * Where a call needs a row that lives on another device (a stored query against the other shards, all-vs-all of the
+ * sharded store, consensus / MSA over rows of several shards) the kernels read it where it lives, over NVLink, through
+ * peer access; fn3_group_peer_access() tells whether that is available (without it only the query calls work, through a
+ * staging copy; the all-vs-all and cluster calls return FN3_ECUDA).  The same device may be listed more than once
+ * (several shards on one GPU: how the group logic is tested on a one-GPU box).  NULL on failure (fn3_last_error(NULL)). */
+typedef struct fn3_group fn3_group;
+fn3_group*  fn3_group_create(int64_t genome_length, int32_t n_devices, const int32_t* device_ids);
+int         fn3_group_destroy(fn3_group* g);
+const char* fn3_group_last_error(fn3_group* g);
+int32_t     fn3_group_n_devices(fn3_group* g);
+int32_t     fn3_group_peer_access(fn3_group* g);
+/* the i-th member engine (borrowed): for device-local calls — fn3_compress, fn3_pair_lists, fn3_profile_queries */
+fn3_engine* fn3_group_engine(fn3_group* g, int32_t i);
+int64_t     fn3_group_launch_count(fn3_group* g);
+
+int fn3_group_append(fn3_group* g, const int32_t* pos, const int32_t off[7], int32_t invalid, int64_t* out_row);
+int fn3_group_append_bulk(fn3_group* g, int64_t n, const int32_t* pos, const int64_t* off, const uint8_t* invalid,
+                          int64_t* out_first_row);
+int fn3_group_remove(fn3_group* g, int64_t row);
+int fn3_group_row_get(fn3_group* g, int64_t row, int32_t* pos, int64_t pos_cap, int32_t off[7], int32_t* invalid,
+                      int64_t* n_pos);
+int fn3_group_stats_get(fn3_group* g, fn3_stats* out);
+int fn3_group_set_reference(fn3_group* g, const char* reference, const int32_t* excluded, int64_t n_excluded);
+
+/* persist + mcompare (server.py:516, :530): the owner device appends the sample and compares it with its earlier rows
+ * (fn3_insert_query), every other device compares it with its whole shard (fn3_lists_vs_all), all at the same time */
+int fn3_group_insert_query(fn3_group* g, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
+                           int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out);
+int fn3_group_ingest_query(fn3_group* g, const char* sequence, int64_t max_ns, int32_t ceiling, int64_t* hist,
+                           int32_t* pos, int64_t pos_cap, int32_t off[7], char* m_chars, int64_t m_cap, int64_t* n_pos,
+                           int32_t* invalid, int64_t* out_row, fn3_hit* out, int64_t cap, int64_t* n_out);
+int fn3_group_one_vs_all(fn3_group* g, int64_t query_row, int32_t ceiling, const int64_t* rows, int64_t n_rows,
+                         fn3_hit* out, int64_t cap, int64_t* n_out);
+int fn3_group_lists_vs_all(fn3_group* g, const int32_t* pos, const int32_t off[7], int32_t invalid, int32_t ceiling,
+                           const int64_t* rows, int64_t n_rows, fn3_hit* out, int64_t cap, int64_t* n_out);
+int fn3_group_pair(fn3_group* g, int64_t row1, int64_t row2, int32_t ceiling, fn3_hit* out, int32_t* has_dist);
+/* distmat over the sharded store (:174-197): every device takes every live row of the group as a query against its own shard */
+int fn3_group_all_vs_all(fn3_group* g, int32_t ceiling, int32_t upper_only, fn3_edge* out, int64_t cap, int64_t* n_out);
+int fn3_group_consensus(fn3_group* g, const int64_t* rows, int64_t n_rows, int64_t min_votes, int32_t* pos,
+                        int64_t pos_cap, int32_t off[6], int64_t* n_pos);
+int fn3_group_consensus_lists(fn3_group* g, int64_t n, const int32_t* pos_in, const int64_t* off_in, int64_t min_votes,
+                              int32_t* pos, int64_t pos_cap, int32_t off[6], int64_t* n_pos);
+int fn3_group_msa_sites_rule(fn3_group* g, const int64_t* rows, int64_t n_rows, int32_t rule, int32_t* sites,
+                             int64_t sites_cap, int64_t* n_sites);
+int fn3_group_msa_align(fn3_group* g, const int64_t* rows, int64_t n_rows, const int32_t* sites, int64_t n_sites,
+                        uint8_t* codes, int32_t* counts);
 
 /* ---- measurement hooks (bench.py only; no effect on results) -------------------- */
 

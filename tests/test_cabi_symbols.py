@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), "libfn3.so does not export %s" % name
     assert set(_native.SIGNATURES) == set(declared_symbols())
-    assert lib.fn3_abi_version() == 3
+    assert lib.fn3_abi_version() == 4
 
 
 def _has_gpu():
@@ -57,7 +57,7 @@ def test_product_does_not_import_oracle():
     bad = re.compile(r"^\s*(from\s+\.*oracle|import\s+oracle)|libfn3_oracle|oracle/_build|fn3o_", re.M)
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), "%s reaches into oracle/" % f
 

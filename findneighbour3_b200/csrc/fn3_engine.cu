@@ -323,6 +323,16 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
                 return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", s);
         }
     }
+    if (env_ll("FN3_CARVEOUT", 1)) {
+        // every kernel of the query path asks for the same (maximal) shared-memory carve-out: an SM that must switch its
+        // L1 / shared split between two kernels drains first, which showed up as microseconds of launch floor
+        const void* ks[] = {(const void*)k_query<false, 0>, (const void*)k_query<true, 0>, (const void*)k_query<false, 1>,
+                            (const void*)k_query<true, 1>, (const void*)k_scan<false, 0>, (const void*)k_scan<true, 0>,
+                            (const void*)k_scan<false, 1>, (const void*)k_scan<true, 1>, (const void*)k_put_head,
+                            (const void*)k_scatter_heads, (const void*)k_fill, (const void*)k_build_query};
+        for (const void* k : ks) (void)cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        (void)cudaGetLastError();
+    }
     if ((s = cudaMalloc(&e->d_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS * FN3_SLOT_RING)) != cudaSuccess) return fail("cudaMalloc(slots)", s);
     if ((s = cudaHostAlloc(&e->h_slots, sizeof(QuerySlot) * FN3_MAX_SLOTS * FN3_SLOT_RING, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(slots)", s);
     if (ensure_out(e, 4096) != FN3_OK || ensure_hout(e, 4096) != FN3_OK) {
@@ -1936,7 +1946,12 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
             cudaMemsetAsync(d_pc, 0, (size_t)n * FN3_OUT_HDR, st);
         }
         for (int it = 0; it < n && rc == FN3_OK; ++it) {
-            set_slot0(e, hdrs[(size_t)it], query_rows[it], query_rows[it]);
+            // the query slot is staged in a ring of pinned slots (a query too large for shared memory is copied to the device
+            // asynchronously): drain the stream before a ring position is reused
+            job.slot_base = (it % FN3_SLOT_RING) * FN3_MAX_SLOTS;
+            if (it && job.slot_base == 0) CU(e, cudaStreamSynchronize(st));
+            QuerySlot& sl = e->h_slots[job.slot_base];
+            sl.hdr = hdrs[(size_t)it]; sl.row = query_rows[it]; sl.skip_le = -1; sl.exclude = query_rows[it]; sl.pad = 0;
             e->slot_blocks[0] = blks[(size_t)it];
             if (pass == 0 && flush_l2) { k_fill<<<e->sm_count * 4, 512, 0, st>>>(e->d_flush, e->flush_n, (uint32_t)it); e->launches += 1; }
             e->d_count = d_pc + (size_t)it * (FN3_OUT_HDR / sizeof(unsigned long long));

@@ -70,11 +70,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 // ---- one chunk of a row, already in shared memory ----------------------------------------------------
 
-// the touched-block test of four positions -> bits 0..3
-__device__ __forceinline__ uint32_t touched4(const QView& qv, const uint4& w) {
-    return touched_bit(qv, w.x) | (touched_bit(qv, w.y) << 1) | (touched_bit(qv, w.z) << 2) | (touched_bit(qv, w.w) << 3);
-}
-
 // sm[0..n) = row words [off, off+n).  Adds to the row's tally; sets t.dead once S1 exceeds the ceiling.
 __device__ __forceinline__ void scan_chunk(const QView& qv, const uint32_t* __restrict__ sm, uint32_t off, uint32_t n,
                                            uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t e4, int k,
@@ -98,7 +93,21 @@ __device__ __forceinline__ void scan_chunk(const QView& qv, const uint32_t* __re
             if (a < 4u) { w0.w = 0u; if (a < 3u) { w0.z = 0u; if (a < 2u) { w0.y = 0u; if (a < 1u) w0.x = 0u; } } }
             if (b < 4u) { w1.w = 0u; if (b < 3u) { w1.z = 0u; if (b < 2u) { w1.y = 0u; if (b < 1u) w1.x = 0u; } } }
         }
-        const uint32_t t8 = (touched4(qv, w0) | (touched4(qv, w1) << 4)) & vm;
+        // eight independent bitmap lookups: all loads first, then the bit tests; the common answer (no word of this lane
+        // in a block the query touches) costs one OR per word, the exact bits are formed only when some test fired
+        const uint32_t pw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint32_t bw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bw[j] = qv.bm[pw[j] >> 10];
+        uint32_t any = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { bw[j] >>= ((pw[j] >> 5) & 31u); any |= bw[j]; }
+        uint32_t t8 = 0u;
+        if (any & 1u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t8 |= (bw[j] & 1u) << j;
+            t8 &= vm;
+        }
         tm |= t8 << sh;
         // untouched block: the query is reference there, the candidate is not — a certain mismatch
         t.S1 += __reduce_add_sync(0xffffffffu, __popc(vm) - __popc(t8));

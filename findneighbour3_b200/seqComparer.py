@@ -24,7 +24,7 @@ import pickle
 import threading
 import uuid
 from collections import Counter
-from collections.abc import MutableMapping
+from collections.abc import MutableMapping, Sequence
 
 import numpy as np
 
@@ -49,6 +49,60 @@ class _LazyLists:
 
     def __init__(self, pos, off, m_chars, invalid):
         self.pos, self.off, self.m_chars, self.invalid = pos, off, m_chars, invalid
+
+
+class _McompareRows(Sequence):
+    """What mcompare() returns: one 9-element list per other guid (src/seqComparer.py:165-169), built when somebody looks.
+
+    The reference materialises N lists per call — at 50 000 stored samples that alone is milliseconds, for rows that are
+    almost all `[guid, guid2, None x 7]`.  This sequence keeps the snapshot of the other guids taken at call time and the
+    (few) device hits; rows are created on indexing / iteration, survivors' position sets only for survivors.
+    len(), indexing, slicing, iteration, `in`, == with a list, sorted(), list() behave as for the reference's list."""
+    __slots__ = ("_sc", "_guid", "_keys", "_found", "_s1")
+
+    def __init__(self, sc, guid, keys, found):
+        self._sc, self._guid, self._keys, self._found, self._s1 = sc, guid, keys, found, None
+
+    def __len__(self):
+        return len(self._keys)
+
+    def _hit_row(self, key2, hit):
+        sc = self._sc
+        if self._s1 is None:
+            self._s1 = sc._computeComparator(sc.seqProfile[self._guid])
+        s2 = sc._computeComparator(sc.seqProfile[key2])
+        N1pos, N2pos, Nbothpos = sc._uncertain_sets(self._s1, s2)
+        return [self._guid, key2, hit[0], hit[1], hit[2], hit[3], N1pos, N2pos, Nbothpos]
+
+    def _row(self, key2):
+        hit = self._found.get(key2)
+        if hit is None:
+            return [self._guid, key2, None, None, None, None, None, None, None]
+        return self._hit_row(key2, hit)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._row(k) for k in self._keys[i]]
+        return self._row(self._keys[i])
+
+    def __iter__(self):
+        guid, found = self._guid, self._found
+        if not found:
+            for k in self._keys:
+                yield [guid, k, None, None, None, None, None, None, None]
+            return
+        get = found.get
+        for k in self._keys:
+            hit = get(k)
+            yield [guid, k, None, None, None, None, None, None, None] if hit is None else self._hit_row(k, hit)
+
+    def __eq__(self, other):
+        if isinstance(other, (list, _McompareRows)):
+            return len(self) == len(other) and all(a == b for a, b in zip(self, other))
+        return NotImplemented
+
+    def __repr__(self):
+        return repr(list(self))
 
 
 class _Profile(MutableMapping):
@@ -230,6 +284,34 @@ class seqComparer():
                 self._guid_of[first + i] = g
                 self._key_of[g] = packing.content_key(p, f, bad)
                 self.seqProfile._d[g] = o
+
+    def persist_packed(self, guids, pos, off, invalid=None, m_chars=None):
+        """Bulk persist of samples already in the engine's list format (what device compress returns and what
+        fn3_unpickle_samples produces): n samples, `pos` concatenated, `off` int64[6n+1], `invalid` uint8[n] or None,
+        `m_chars` the mixed-base characters in M-list order (bytes/str, or None: 'M').  One device copy; a sample's dict of
+        sets is built only when `seqProfile[guid]` / `load(guid)` is asked for."""
+        guids = list(guids)
+        n = len(guids)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        if off.size != 6 * n + 1:
+            raise ValueError("off must have 6*n+1 entries")
+        inv = np.zeros(n, dtype=np.uint8) if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        m_at = 0
+        with self._lock:
+            for g in guids:
+                if g in self._row_of:
+                    self._drop_row(g)
+            first = self.engine.append_bulk(pos, off, inv)
+            for i, g in enumerate(guids):
+                o = off[6 * i: 6 * i + 7]
+                o7 = (o - o[0]).astype(np.int32)
+                n_m = int(o7[6] - o7[5])
+                mc = ['M'] * n_m if m_chars is None else [chr(c) if isinstance(c, int) else c for c in m_chars[m_at:m_at + n_m]]
+                m_at += n_m
+                self._row_of[g] = first + i
+                self._guid_of[first + i] = g
+                self._key_of[g] = None
+                self.seqProfile._d[g] = _LazyLists(pos[o[0]:o[6]], o7, mc, bool(inv[i]))
 
     def persist_pickles(self, blobs, guids):
         """Start-up reload straight from the stored form (findNeighbour3-server.py:358-362 reads GridFS pickles written by
@@ -556,24 +638,16 @@ class seqComparer():
             return {gof[int(h['row'])]: (int(h['dist']), int(h['n1']), int(h['n2']), int(h['nboth'])) for h in hits}
 
     def mcompare(self, guid, guids=None):
-        """one guid against all (or `guids`), one 9-element list per other guid (:149-172)."""
+        """one guid against all (or `guids`), one 9-element list per other guid (:149-172).  The rows come back as a
+        lazily materialised sequence (_McompareRows): the device call and a snapshot of the guids happen here, the
+        per-row Python lists are built when the caller iterates or indexes."""
         found = self.neighbours(guid, guids, self.snpCeiling)
-        others = set(self.seqProfile.keys()) if guids is None else set(guids)
-        out = []
-        s1 = None
-        for key2 in others:
-            if guid == key2:
-                continue
-            hit = found.get(key2)
-            if hit is None:
-                out.append([guid, key2, None, None, None, None, None, None, None])
-            else:
-                if s1 is None:
-                    s1 = self._computeComparator(self.seqProfile[guid])
-                s2 = self._computeComparator(self.seqProfile[key2])
-                N1pos, N2pos, Nbothpos = self._uncertain_sets(s1, s2)
-                out.append([guid, key2, hit[0], hit[1], hit[2], hit[3], N1pos, N2pos, Nbothpos])
-        return out
+        keys = list(self.seqProfile._d) if guids is None else list(set(guids))
+        try:
+            keys.remove(guid)                    # the query itself is skipped (:166)
+        except ValueError:
+            pass
+        return _McompareRows(self, guid, keys, found)
 
     def distmat(self, half=True, diagonal=False):
         """generator over the all-vs-all matrix at snpCompressionCeiling (:174-197)."""

@@ -145,10 +145,16 @@ def _blocks(length, n_blocks, total, rng):
 
 def make_collection(n_anc, max_c, genome_length=TB_LENGTH, k1=500, s=3.0, n_blocks=20, n_mean=4000, m_mean=0,
                     p_invalid=0.01, seed=1, rule="lss", ref_seed=962, excluded=None, n_lognormal_sigma=None,
-                    max_ns=130000):
-    """Generate n_anc*max_c samples -> Collection.  `excluded`: boolean[L] or None."""
+                    max_ns=130000, base=None, star=False, anc_seed=None):
+    """Generate n_anc*max_c samples -> Collection.  `excluded`: boolean[L] or None.
+    `base` = (positions, base codes): variants every ancestor starts from (shared ancestry: lineage-defining SNPs) instead
+    of the bare reference.  `star`: every sample descends from the family's ancestor directly (an outbreak: all members
+    within a few SNVs of each other) instead of from a random earlier node.  `anc_seed`: the ancestor's own substitutions are
+    drawn from this seed (several calls then share ONE ancestor: an outbreak generated in parallel pieces)."""
     rng = np.random.default_rng(seed)
     ref = random_reference(genome_length, ref_seed)
+    base_vp = np.empty(0, dtype=np.int64) if base is None else np.asarray(base[0], dtype=np.int64)
+    base_vb = np.empty(0, dtype=np.uint8) if base is None else np.asarray(base[1], dtype=np.uint8)
     n = n_anc * max_c
     off = np.zeros(6 * n + 1, dtype=np.int64)
     invalid = np.zeros(n, dtype=np.uint8)
@@ -160,9 +166,13 @@ def make_collection(n_anc, max_c, genome_length=TB_LENGTH, k1=500, s=3.0, n_bloc
         nodes = []
         for c in range(max_c):
             if c == 0:
-                vp, vb = _mutate(np.empty(0, dtype=np.int64), np.empty(0, dtype=np.uint8), ref, k1, rng, rule)
+                arng = rng if anc_seed is None else np.random.default_rng(anc_seed)
+                vp, vb = _mutate(base_vp, base_vb, ref, k1, arng, rule)
+                if anc_seed is not None:                 # a piece of a larger family: its first member is a descendant too
+                    nodes.append((vp, vb))
+                    vp, vb = _mutate(vp, vb, ref, int(rng.poisson(s)), rng, rule)
             else:
-                pp, pb = nodes[int(rng.integers(0, c))]
+                pp, pb = nodes[0] if star else nodes[int(rng.integers(0, len(nodes)))]
                 vp, vb = _mutate(pp, pb, ref, int(rng.poisson(s)), rng, rule)
             nodes.append((vp, vb))
             if rng.random() < p_invalid:
@@ -211,24 +221,32 @@ def make_collection(n_anc, max_c, genome_length=TB_LENGTH, k1=500, s=3.0, n_bloc
 
 
 def _families_task(task):
-    seeds, max_c, tb_mask = task
+    seeds, max_c, tb_mask, kw, bases = task
     mask = synthetic_mask(TB_LENGTH, TB_EXCLUDED, TB_EXCLUDED_RUNS) if tb_mask else None
-    parts = [make_collection(1, max_c, seed=int(sd), excluded=mask) for sd in seeds]
+    parts = []
+    for k, sd in enumerate(seeds):
+        base = None
+        if bases is not None:
+            base = lineage_base(kw.get("genome_length", TB_LENGTH), bases[k][0], bases[k][1], kw.get("ref_seed", 962),
+                                kw.get("rule", "lss"))
+        parts.append(make_collection(1, max_c, seed=int(sd), excluded=mask, base=base, **kw))
     return (np.concatenate([c.pos for c in parts]), np.concatenate([np.diff(c.off) for c in parts]),
             np.concatenate([c.invalid for c in parts]))
 
 
-def make_families(seeds, max_c, workers=None, tb_mask=True):
-    """One TB-shaped family per seed — make_collection(1, max_c, seed=seed), the collection BASELINE configs[2] is built
-    from — concatenated in seed order, generated by a pool of processes (the generator is single-threaded numpy:
-    200 000 samples take minutes on one core).  -> Collection; family f holds the samples of seeds[f]."""
+def make_families(seeds, max_c, workers=None, tb_mask=True, bases=None, **kw):
+    """One TB-shaped family per seed — make_collection(1, max_c, seed=seed, **kw), the collection BASELINE configs[1..4] are
+    built from — concatenated in seed order, generated by a pool of processes (the generator is single-threaded numpy:
+    200 000 samples take minutes on one core).  `bases[f]` = (lineage, sub-lineage) of family f (see lineage_base) or None.
+    -> Collection; family f holds the samples of seeds[f]."""
     import multiprocessing
     import os
     from concurrent.futures import ProcessPoolExecutor
     seeds = [int(x) for x in seeds]
     workers = max(1, min(workers or (os.cpu_count() or 1), len(seeds)))
     per = max(1, min(25, (len(seeds) + workers - 1) // workers))
-    tasks = [(seeds[i:i + per], max_c, tb_mask) for i in range(0, len(seeds), per)]
+    tasks = [(seeds[i:i + per], max_c, tb_mask, kw, None if bases is None else bases[i:i + per])
+             for i in range(0, len(seeds), per)]
     if workers == 1:
         results = [_families_task(t) for t in tasks]
     else:                                # spawn: the parent may hold a CUDA context, which must not be forked
@@ -243,7 +261,82 @@ def make_families(seeds, max_c, workers=None, tb_mask=True):
     np.cumsum(lens, out=off[1:])
     invalid = np.concatenate([r[2] for r in results]) if results else np.empty(0, dtype=np.uint8)
     family = np.repeat(np.arange(len(seeds), dtype=np.int32), max_c)
-    return Collection(TB_LENGTH, pos, off, invalid, family)
+    return Collection(kw.get("genome_length", TB_LENGTH), pos, off, invalid, family)
+
+
+# ---- collections that stress the early-exit filter -------------------------------------------------
+
+@lru_cache(maxsize=64)
+def lineage_base(genome_length, lineage, sublineage, ref_seed=962, rule="lss", k_lineage=800, k_sub=150):
+    """variants shared by every member of (lineage, sub-lineage): reference + k_lineage lineage-defining substitutions +
+    k_sub sub-lineage-defining ones — real M. tuberculosis collections look like this relative to H37Rv: two unrelated
+    lineage-4 isolates agree on hundreds of non-reference positions."""
+    ref = random_reference(genome_length, ref_seed)
+    vp, vb = _mutate(np.empty(0, dtype=np.int64), np.empty(0, dtype=np.uint8), ref, k_lineage,
+                     np.random.default_rng(1_000_003 * (int(lineage) + 1)), rule)
+    vp, vb = _mutate(vp, vb, ref, k_sub, np.random.default_rng(7_000_003 * (int(lineage) + 1) + int(sublineage) + 1), rule)
+    vp.setflags(write=False); vb.setflags(write=False)
+    return vp, vb
+
+
+def make_lineages(n_anc, max_c, seed=11, n_lineages=4, n_sub=4, workers=None, k1=500, **kw):
+    """Deep shared ancestry: every family's ancestor = its (lineage, sub-lineage) base (800 + 150 shared SNPs) + k1 own
+    substitutions, then the usual random tree.  Family f belongs to lineage f % n_lineages, sub-lineage (f // n_lineages) % n_sub.
+    -> Collection"""
+    bases = [(f % n_lineages, (f // n_lineages) % n_sub) for f in range(n_anc)]
+    return make_families([seed * 1_000_000 + f for f in range(n_anc)], max_c, workers=workers, bases=bases, k1=k1, **kw)
+
+
+def make_outbreak(n, seed=13, piece=500, workers=None, s=2.0, **kw):
+    """An outbreak: n samples that ALL descend directly from one ancestor (reference + k1 substitutions) with Poisson(s)
+    private substitutions each — every pair is within a few SNVs, so no pair can be ruled out early and every candidate is
+    a neighbour at snpCeiling 12..20.  Generated in parallel pieces that share the ancestor."""
+    n_pieces = (n + piece - 1) // piece
+    coll = make_families([seed * 1_000_000 + 17 * k for k in range(n_pieces)], piece, workers=workers, star=True, s=s,
+                         anc_seed=seed * 31 + 5, **kw)
+    if coll.n > n:
+        coll = Collection(coll.genome_length, coll.pos[: coll.off[6 * n]], coll.off[: 6 * n + 1], coll.invalid[:n], coll.family[:n])
+    return coll
+
+
+def mix_samples(a, b, max_ns=None):
+    """consensus call of a MIXTURE of two samples, as src/make_simulation.py:147-164 (mix_sequences) builds it from strings:
+    a position keeps its character where the two sequences agree and becomes a mixed base where they differ.
+    a, b = (pos, off, invalid) valid samples -> (pos, off, invalid)."""
+    (pa, oa, _), (pb, ob, _) = a, b
+    lists = []
+    for l in range(4):
+        lists.append(np.intersect1d(pa[oa[l]:oa[l + 1]], pb[ob[l]:ob[l + 1]], assume_unique=True))
+    n_both = np.intersect1d(pa[oa[4]:oa[5]], pb[ob[4]:ob[5]], assume_unique=True)
+    m_both = np.intersect1d(pa[oa[5]:oa[6]], pb[ob[5]:ob[6]], assume_unique=True)     # the same IUPAC character in both
+    touched = np.union1d(pa[:oa[6]], pb[:ob[6]])
+    same = np.concatenate(lists + [n_both])
+    mixed = np.union1d(np.setdiff1d(touched, same, assume_unique=False), m_both)
+    lists += [n_both, mixed]
+    off = np.zeros(7, dtype=np.int32)
+    off[1:] = np.cumsum([x.size for x in lists])
+    invalid = max_ns is not None and (n_both.size + mixed.size) > max_ns
+    return np.concatenate(lists).astype(np.int32), off, bool(invalid)
+
+
+def add_mixtures(coll, fraction=0.02, seed=5, max_ns=None):
+    """append round(fraction * n) mixed samples, each the mixture of two random valid samples"""
+    rng = np.random.default_rng(seed)
+    valid = np.flatnonzero(coll.invalid == 0)
+    k = int(round(fraction * coll.n))
+    chunks, offs, inv = [coll.pos], [coll.off], [coll.invalid]
+    total = int(coll.off[-1])
+    for _ in range(k):
+        i, j = rng.choice(valid, size=2, replace=False)
+        p, o, bad = mix_samples(coll.lists(int(i)), coll.lists(int(j)), max_ns)
+        if bad:
+            p, o = np.empty(0, np.int32), np.zeros(7, np.int32)
+        chunks.append(p)
+        offs.append(total + o[1:].astype(np.int64))
+        total += int(o[6])
+        inv.append(np.array([1 if bad else 0], np.uint8))
+    return Collection(coll.genome_length, np.concatenate(chunks), np.concatenate(offs), np.concatenate(inv),
+                      np.concatenate([coll.family, np.full(k, -1, np.int32)]))
 
 
 def new_sample_like(coll, i, extra_snps, seed, rule="lss", ref_seed=962):

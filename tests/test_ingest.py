@@ -148,7 +148,7 @@ def test_insert_sequence_host_layer(monkeypatch, mt):
     import findneighbour3_b200.seqComparer as base
     from fake_engine import OracleEngine
     monkeypatch.setattr(engine, "byte_histogram", _numpy_histogram)
-    monkeypatch.setattr(base, "Engine", lambda genome_length, device=0: OracleEngine(genome_length))
+    monkeypatch.setattr(base, "make_engine", lambda genome_length, device=0: OracleEngine(genome_length))
     _check_insert_sequence(600, 24, 3, max_ns=40, mt=mt)
 
 
@@ -211,7 +211,7 @@ def _check_concurrent_compress():
 def test_concurrent_compress_host_layer(monkeypatch):
     import findneighbour3_b200.seqComparer as base
     from fake_engine import OracleEngine
-    monkeypatch.setattr(base, "Engine", lambda genome_length, device=0: OracleEngine(genome_length))
+    monkeypatch.setattr(base, "make_engine", lambda genome_length, device=0: OracleEngine(genome_length))
     _check_concurrent_compress()
 
 

@@ -159,5 +159,5 @@ def test_mt_class_matches_the_reference_on_the_gpu():
 def test_mt_class_host_layer_with_the_stand_in_engine(monkeypatch):
     import findneighbour3_b200.seqComparer as base
     from fake_engine import OracleEngine
-    monkeypatch.setattr(base, "Engine", lambda genome_length, device=0: OracleEngine(genome_length))
+    monkeypatch.setattr(base, "make_engine", lambda genome_length, device=0: OracleEngine(genome_length))
     _check_everything()

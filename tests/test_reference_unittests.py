@@ -22,7 +22,7 @@ def _run_reference_tests(monkeypatch, module="seqComparer", skip=()):
     import importlib
     import findneighbour3_b200.seqComparer as base
     from fake_engine import OracleEngine
-    monkeypatch.setattr(base, "Engine", lambda genome_length, device=0: OracleEngine(genome_length))
+    monkeypatch.setattr(base, "make_engine", lambda genome_length, device=0: OracleEngine(genome_length))
     dropin = importlib.import_module("findneighbour3_b200." + module)
     ref = ref_shim.load_reference_module(module)
     original = ref.seqComparer

@@ -38,7 +38,7 @@ def _check():
 def test_compact_store_host_layer(monkeypatch):
     import findneighbour3_b200.seqComparer as base
     from fake_engine import OracleEngine
-    monkeypatch.setattr(base, "Engine", lambda genome_length, device=0: OracleEngine(genome_length))
+    monkeypatch.setattr(base, "make_engine", lambda genome_length, device=0: OracleEngine(genome_length))
     _check()
 
 

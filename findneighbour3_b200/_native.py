@@ -71,7 +71,7 @@ SIGNATURES = {
     "fn3_msa_sites_rule": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int32, _i32p, C.c_int64, _i64p]),
     "fn3_msa_align": (C.c_int, [_vp, _i64p, C.c_int64, _i32p, C.c_int64, _u8p, _i32p]),
     "fn3_unpickle_samples": (C.c_int, [C.c_int64, _u8p, _i64p, _i32p, C.c_int64, _i64p, _u8p, _i64p]),
-    "fn3_profile_queries": (C.c_int, [_vp, _i64p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i64p, _i64p]),
+    "fn3_profile_queries": (C.c_int, [_vp, _i64p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i64p, _i64p, _i64p]),
     "fn3_launch_count": (C.c_int64, [_vp]),
     # engine groups (one process, several GPUs): same argument lists as the single-engine calls of the same name
     "fn3_group_create": (_vp, [C.c_int64, C.c_int32, _i32p]),

@@ -1908,7 +1908,8 @@ extern "C" int fn3_unpickle_samples(int64_t n, const uint8_t* blobs, const int64
 // ---- measurement hook ----------------------------------------------------------------------
 
 extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int32_t n, int32_t ceiling, int32_t flush_l2,
-                                   float* ms_build, float* ms_compare, int64_t* n_hits, int64_t* bytes_touched) {
+                                   float* ms_build, float* ms_compare, int64_t* n_hits, int64_t* bytes_touched,
+                                   int64_t* n_passed) {
     if (!e || !query_rows || n < 1) return set_err(e, FN3_EARG, "fn3_profile_queries: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
@@ -1975,6 +1976,7 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
         std::vector<unsigned long long> pc((size_t)n * 4, 0);
         cudaMemcpy(pc.data(), d_pc, (size_t)n * FN3_OUT_HDR, cudaMemcpyDeviceToHost);
         if (bytes_touched) for (int it = 0; it < n; ++it) bytes_touched[it] = (int64_t)pc[(size_t)it * 4 + 1];
+        if (bytes_touched && n_passed) for (int it = 0; it < n; ++it) n_passed[it] = (int64_t)pc[(size_t)it * 4 + 2];
         else if (n_hits) for (int it = 0; it < n; ++it) n_hits[it] = (int64_t)pc[(size_t)it * 4];
     }
     for (auto ev : evs) cudaEventDestroy(ev);

@@ -456,6 +456,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     const int pos_bits = p.pos_bits;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
     unsigned long long touched = 0;
+    unsigned int passed = 0;                               // instrumented variant: candidates phase A could not rule out
 
     {
         // upper triangle: superblocks that hold only rows <= skip_le cannot contain a candidate
@@ -504,6 +505,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
         // either sits in its lane's registers already (single-candidate path: HAVE_HDR, nine shuffles) or is fetched now.
         auto survivors = [&](bool passA, int rowA, bool passB, int rowB, const bool HAVE_HDR, const uint4& ha0, const uint4& ha1) {
             uint32_t aliveA = __ballot_sync(0xffffffffu, passA), aliveB = __ballot_sync(0xffffffffu, passB);
+            if (COUNT && lane == 0) passed += __popc(aliveA) + __popc(aliveB);
             if (p.debug_stop == 2) { aliveA = 0u; aliveB = 0u; }
             while (aliveA | aliveB) {
                 const bool fromA = aliveA != 0u;
@@ -578,7 +580,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, o);
-        if (lane == 0) atomicAdd(p.touched, touched);
+        if (lane == 0) { atomicAdd(p.touched, touched); if (passed) atomicAdd(p.touched + 1, (unsigned long long)passed); }
     }
     if (p.host_flag) signal_done(p);
 }

@@ -407,19 +407,21 @@ class Engine:
         return codes, counts
 
     # -- measurement ----------------------------------------------------------------------
-    def profile_queries(self, query_rows, ceiling, flush_l2=False, count_bytes=False):
-        """device-only timing of one-vs-all for each stored row in query_rows (bench.py's `value` leg)."""
+    def profile_queries(self, query_rows, ceiling, flush_l2=False, count_bytes=False, member=None):
+        """device-only timing of one-vs-all for each stored row in query_rows (bench.py's `value` leg); rows are those of
+        ONE engine (`member`: the handle of a group member, default the first)."""
         q = np.ascontiguousarray(query_rows, dtype=np.int64)
         n = q.size
         ms_build = np.zeros(n, dtype=np.float32)
         ms_cmp = np.zeros(n, dtype=np.float32)
         n_hits = np.zeros(n, dtype=np.int64)
         touched = np.zeros(n, dtype=np.int64) if count_bytes else None
-        rc = self._f_profile_queries(self._hl, _ptr(q, _i64p), n, int(ceiling), 1 if flush_l2 else 0,
-                                           _ptr(ms_build, _f32p), _ptr(ms_cmp, _f32p), _ptr(n_hits, _i64p),
-                                           _ptr(touched, _i64p))
+        passed = np.zeros(n, dtype=np.int64) if count_bytes else None
+        rc = self._f_profile_queries(self._hl if member is None else member, _ptr(q, _i64p), n, int(ceiling),
+                                     1 if flush_l2 else 0, _ptr(ms_build, _f32p), _ptr(ms_cmp, _f32p), _ptr(n_hits, _i64p),
+                                     _ptr(touched, _i64p), _ptr(passed, _i64p))
         self._check(rc)
-        return {"ms_build": ms_build, "ms_compare": ms_cmp, "n_hits": n_hits, "bytes_touched": touched}
+        return {"ms_build": ms_build, "ms_compare": ms_cmp, "n_hits": n_hits, "bytes_touched": touched, "n_passed": passed}
 
     def launch_count(self):
         return int(self._f_launch_count(self._h))

@@ -326,10 +326,11 @@ int fn3_group_msa_align(fn3_group* g, const int64_t* rows, int64_t n_rows, const
  * synchronisation in between.  ms_build[i] / ms_compare[i] receive the CUDA-event times of step i's
  * query-map build (memset + scatter + rank) and of its compare kernel; n_hits[i] its survivor count;
  * bytes_touched[i] (may be NULL) the bytes of headers + row data the compare kernel of step i actually
- * loaded, counted by a separate instrumented pass that is NOT timed.  flush_l2 != 0 writes a 256 MiB
- * scratch buffer before each step (outside the timed events) so that every step starts with a cold L2. */
+ * loaded, counted by a separate instrumented pass that is NOT timed; n_passed[i] (may be NULL; filled with
+ * bytes_touched) the candidates the head filter could not rule out (0 for ceilings that do not use it).  flush_l2 != 0
+ * writes a 256 MiB scratch buffer before each step (outside the timed events) so that every step starts with a cold L2. */
 int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int32_t n, int32_t ceiling, int32_t flush_l2,
-                        float* ms_build, float* ms_compare, int64_t* n_hits, int64_t* bytes_touched);
+                        float* ms_build, float* ms_compare, int64_t* n_hits, int64_t* bytes_touched, int64_t* n_passed);
 
 /* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 int64_t fn3_launch_count(fn3_engine* e);

@@ -31,7 +31,8 @@ class Stats(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_live", C.c_int64), ("n_invalid", C.c_int64),
                 ("store_words", C.c_int64), ("store_bytes", C.c_int64), ("positions", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("t_pack_ns", C.c_int64),
-                ("t_enqueue_ns", C.c_int64), ("t_wait_ns", C.c_int64), ("n_timed", C.c_int64)]
+                ("t_enqueue_ns", C.c_int64), ("t_wait_ns", C.c_int64), ("n_timed", C.c_int64),
+                ("head_refreshes", C.c_int64), ("scan_mode", C.c_int64)]
 
 
 # array arguments (int32_t*, int64_t*, uint8_t*, float*) are declared void*: the callers pass plain integer addresses of
@@ -49,6 +50,7 @@ SIGNATURES = {
     "fn3_append_bulk": (C.c_int, [_vp, C.c_int64, _i32p, _i64p, _u8p, _i64p]),
     "fn3_remove": (C.c_int, [_vp, C.c_int64]),
     "fn3_stats_get": (C.c_int, [_vp, _vp]),
+    "fn3_refresh_heads": (C.c_int, [_vp, C.c_int64]),
     "fn3_row_get": (C.c_int, [_vp, C.c_int64, _i32p, C.c_int64, _i32p, _i32p, _i64p]),
     "fn3_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, _i64p, C.c_int64, _vp, C.c_int64, _i64p]),
     "fn3_insert_query": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, _vp, C.c_int64, _i64p]),

@@ -141,6 +141,20 @@ struct fn3_engine {
     unsigned char* d_vtiles = nullptr; size_t vtiles_cap = 0;   // head tiles of a virtual row set (engine groups)
     long long* d_loff = nullptr; size_t loff_cap = 0;
 
+    // background-aware heads (fn3_refresh_heads): positions that are non-reference in many rows do not go into a head
+    std::vector<uint32_t> bg_bits;          // host copy of the bitmap (fill_head); empty = no background known
+    uint32_t* d_bg = nullptr;
+    bool bg_any = false;
+    bool bg_auto = true;                    // refresh when the store has doubled since the last one (env FN3_BG_AUTO)
+    long long bg_next_at = 4096;            // live rows at which the next automatic refresh is due
+    long long bg_ppm = 10000;               // background = non-reference in >= 1 % of the live rows (env FN3_BG_PPM)
+    long long bg_refreshes = 0;
+    // FILTER <-> STREAM steering of full one-vs-all scans at low ceilings (an outbreak: every candidate passes the filter)
+    double pass_ema = 0.0;
+    bool prefer_scan = false;
+    int scan_streak = 0;
+    long long last_passed = 0;
+
     std::atomic<long long> launches{0};
 };
 
@@ -282,6 +296,8 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
     e->sb_shift = std::min(13, e->hdr_shift);                   // 8192-row superblocks: neighbours in insertion
                                                                 // order sit 256 tiles apart
     e->debug_stop = (int)env_ll("FN3_DEBUG_STOP", 0);
+    e->bg_auto = env_ll("FN3_BG_AUTO", 1) != 0;
+    e->bg_ppm = std::max<long long>(1, env_ll("FN3_BG_PPM", 10000));
     // queries per all-vs-all tile (one k_query launch): one per SM, so that with two CTAs per query every resident CTA
     // slot of the GPU (2 per SM) is filled by one wave — 148 on a B200 (128 left 40 of the 296 slots idle)
     e->n_slots = (int)env_ll("FN3_SLOTS", e->sm_count);
@@ -363,7 +379,7 @@ extern "C" int fn3_destroy(fn3_engine* e) {
     cudaFree(e->d_heads);
     cudaFree(e->d_slots);
     cudaFree(e->d_outbuf); cudaFree(e->d_rows); cudaFree(e->d_scratch);
-    cudaFree(e->d_scratch_tile); cudaFree(e->d_flush); cudaFree(e->d_done);
+    cudaFree(e->d_scratch_tile); cudaFree(e->d_flush); cudaFree(e->d_done); cudaFree(e->d_bg);
     if (e->zc_buf) cudaFreeHost(e->zc_buf);
     cudaFree(e->d_refmask); cudaFree(e->d_seq); cudaFree(e->d_mchars); cudaFree(e->d_cpos);
     cudaFree(e->d_ccounts); cudaFree(e->d_ctotals);
@@ -571,9 +587,21 @@ static void fill_head(const fn3_engine* e, RowHead& hd, const RowHdr& h, const u
         for (uint32_t i = 0; i < FN3_HEAD_FP; ++i) hd.fp[i] = e->fp_dead;
         return;
     }
-    const uint32_t nv = std::min<uint32_t>(h.end[3], FN3_HEAD_FP);
-    for (uint32_t i = 0; i < nv; ++i) hd.fp[i] = (uint16_t)(words[i] >> e->fshift);
-    for (uint32_t i = nv; i < FN3_HEAD_FP; ++i) hd.fp[i] = e->fp_pad;
+    uint32_t k = 0;
+    if (!e->bg_any) {
+        const uint32_t nv = std::min<uint32_t>(h.end[3], FN3_HEAD_FP);
+        for (; k < nv; ++k) hd.fp[k] = (uint16_t)(words[k] >> e->fshift);
+    } else {
+        // the row's first 32 positions that are NOT background (private variants rule an unrelated query out; positions half
+        // the collection shares do not), topped up with background ones — the same selection as k_rehead
+        const uint32_t nv = h.end[3];
+        const uint32_t* bg = e->bg_bits.data();
+        for (uint32_t i = 0; i < nv && k < FN3_HEAD_FP; ++i)
+            if (!((bg[words[i] >> 5] >> (words[i] & 31u)) & 1u)) hd.fp[k++] = (uint16_t)(words[i] >> e->fshift);
+        for (uint32_t i = 0; i < nv && k < FN3_HEAD_FP; ++i)
+            if ((bg[words[i] >> 5] >> (words[i] & 31u)) & 1u) hd.fp[k++] = (uint16_t)(words[i] >> e->fshift);
+    }
+    for (; k < FN3_HEAD_FP; ++k) hd.fp[k] = e->fp_pad;
 }
 
 // device address of a row's header inside its tile
@@ -797,6 +825,7 @@ extern "C" int fn3_stats_get(fn3_engine* e, fn3_stats* out) {
     out->store_words = e->store_words; out->store_bytes = e->store_bytes; out->positions = e->positions;
     out->h2d_bytes = e->h2d_bytes.load(); out->d2h_bytes = e->d2h_bytes.load();
     out->t_pack_ns = e->t_pack_ns; out->t_enqueue_ns = e->t_enqueue_ns; out->t_wait_ns = e->t_wait_ns; out->n_timed = e->n_timed;
+    out->head_refreshes = e->bg_refreshes; out->scan_mode = e->prefer_scan ? 1 : 0;
     return FN3_OK;
 }
 
@@ -881,11 +910,13 @@ struct QueryJob {                    // what enqueue_query needs beyond the engi
     long long commit_row = -1;
     cudaEvent_t split = nullptr;         // measurement hook: recorded between the optional build kernel and k_query
     bool zero_copy = false;              // results + completion through mapped host memory (one-vs-all paths)
+    bool adaptive = false;               // a full one-vs-all scan: may be steered from FILTER to STREAM (prefer_scan)
+    bool used_filter = false;            // out: which variant enqueue_query chose
 };
 
 // enqueue one query tile on q_stream.  Normally ONE kernel (k_query builds the query structure in shared memory
 // itself); queries too large for shared memory take k_build_query + the global-memory variant.
-static int enqueue_query(fn3_engine* e, const QueryJob& job) {
+static int enqueue_query(fn3_engine* e, QueryJob& job) {
     cudaStream_t st = e->q_stream;
     const int ns = job.ns;
     QuerySlot* h_sl = e->h_slots + job.slot_base;
@@ -897,7 +928,8 @@ static int enqueue_query(fn3_engine* e, const QueryJob& job) {
     uint32_t blocks = job.blocks;
     if (ns == 1 && blocks == 0) blocks = e->slot_blocks[0];
     blocks = std::min<uint32_t>(blocks, (uint32_t)e->n_blk);
-    const bool filter = use_filter_for(job.ceiling);
+    const bool filter = use_filter_for(job.ceiling) && !(job.adaptive && e->prefer_scan);
+    job.used_filter = filter;
     // dynamic shared memory: the query structure (when it fits) and, for k_scan, the row rings behind it
     const size_t q_smem = ((size_t)e->nw * sizeof(uint2) + (size_t)e->ncw * 4 + ((size_t)blocks + 1) * sizeof(QEntry) + 127) & ~(size_t)127;
     const size_t ring = filter ? 0 : FN3_SCAN_RING_BYTES;
@@ -1009,6 +1041,72 @@ static int upload_scratch(fn3_engine* e, int which, const int32_t* pos, const in
     return FN3_OK;
 }
 
+static int ensure_votes(fn3_engine* e);
+static int ensure_rows(fn3_engine* e, long long n);
+
+// Recompute the background bitmap from the live rows and rewrite every head from it (query_mu held by the caller; store_mu is
+// taken here for the whole pass: heads are rewritten in place).  ppm: a position is background when it is non-reference in
+// at least ppm / 1e6 of the live valid rows (and in at least 8 of them); ppm <= 0 clears the background.
+static int refresh_heads_locked(fn3_engine* e, long long ppm) {
+    std::lock_guard<std::mutex> g(e->store_mu);
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->q_stream;
+    const long long n = e->n_rows;
+    const long long n_words = (e->L + 31) / 32;
+    int rc;
+    if (!e->d_bg) {
+        CU(e, cudaMalloc(&e->d_bg, (size_t)n_words * 4));
+        CU(e, cudaMemsetAsync(e->d_bg, 0, (size_t)n_words * 4, st));
+    }
+    CU(e, cudaStreamSynchronize(e->copy_stream));          // heads of earlier appends are in place
+    long long n_valid = 0;
+    if ((rc = ensure_rows(e, std::max<long long>(n, 1)))) return rc;
+    for (long long r = 0; r < n; ++r)
+        if (e->h_flags[(size_t)r] == 0) e->h_rows[n_valid++] = r;
+    HdrTable ht; fill_hdr_table(e, ht);
+    if (ppm > 0 && n_valid > 0) {
+        if ((rc = ensure_votes(e))) return rc;
+        CU(e, cudaMemcpyAsync(e->d_rows, e->h_rows, (size_t)n_valid * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CU(e, cudaMemsetAsync(e->d_votes, 0, (size_t)e->vLpad * 4 * sizeof(uint32_t), st));
+        k_votes_rows<<<(unsigned)std::min<long long>(n_valid, (long long)e->sm_count * 8), FN3_VOTE_THREADS, 0, st>>>(e->d_rows, n_valid, ht, e->d_votes, e->vLpad, 0, e->pos_bits);
+        const long long thr = std::max<long long>(8, (ppm * n_valid + 999999) / 1000000);
+        k_bg_bits<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(e->d_votes, e->vLpad, e->L, (uint32_t)std::min<long long>(thr, 0xffffffffll), e->d_bg, n_words);
+        e->launches += 2;
+        CU(e, cudaGetLastError());
+    } else {
+        CU(e, cudaMemsetAsync(e->d_bg, 0, (size_t)n_words * 4, st));
+    }
+    e->bg_bits.assign((size_t)n_words + 1, 0u);
+    CU(e, cudaMemcpyAsync(e->bg_bits.data(), e->d_bg, (size_t)n_words * 4, cudaMemcpyDeviceToHost, st));
+    if (n > 0) {
+        k_rehead<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ht, n, e->d_bg, e->fshift, (uint32_t)e->fp_pad);
+        e->launches += 1;
+        CU(e, cudaGetLastError());
+    }
+    CU(e, cudaStreamSynchronize(st));
+    e->d2h_bytes += n_words * 4;
+    bool any = false;
+    for (long long w = 0; w < n_words && !any; ++w) any = e->bg_bits[(size_t)w] != 0u;
+    e->bg_any = any;
+    e->bg_refreshes++;
+    e->bg_next_at = std::max<long long>(4096, 2 * e->n_live);
+    return FN3_OK;
+}
+
+// automatic refresh: when the store has doubled since the last one (query_mu held)
+static int maybe_refresh_heads(fn3_engine* e) {
+    if (!e->bg_auto) return FN3_OK;
+    bool due;
+    { std::lock_guard<std::mutex> g(e->store_mu); due = e->n_live >= e->bg_next_at; }
+    return due ? refresh_heads_locked(e, e->bg_ppm) : FN3_OK;
+}
+
+extern "C" int fn3_refresh_heads(fn3_engine* e, int64_t min_ppm) {
+    if (!e) return FN3_EARG;
+    std::lock_guard<std::mutex> q(e->query_mu);
+    return refresh_heads_locked(e, min_ppm);
+}
+
 // shared tail of one-vs-all style calls: the query is in h_slots[0] / slot_blocks[0]; job.ht / job.n_rows are set
 static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int64_t n_list, fn3_hit* out, int64_t cap,
                           int64_t* n_out) {
@@ -1029,6 +1127,7 @@ static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int
         e->h2d_bytes += n * (long long)sizeof(long long);
         job.d_rows = e->d_rows; job.n_list = n;
     }
+    job.adaptive = !rows && n >= 1024;
     if ((rc = ensure_out(e, std::max<long long>(n, 1)))) return rc;
     const EdgeRec* recs;
     long long cnt;
@@ -1056,7 +1155,20 @@ static int run_one_vs_all(fn3_engine* e, QueryJob& job, const int64_t* rows, int
         e->qstage_busy = false;                                   // the stream has consumed everything queued before
         e->t_wait_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_wait).count();
         cnt = (long long)flag[1];
-        e->d2h_bytes += 16 + std::min<long long>(cnt, FN3_ZC_CAP) * (long long)sizeof(EdgeRec);
+        e->last_passed = (long long)flag[2];
+        if (job.adaptive && use_filter_for(job.ceiling)) {
+            // FILTER <-> STREAM steering: when the head filter lets most candidates through (an outbreak: they ARE neighbours)
+            // the next full scans go straight to k_scan; while there, the hit rate tells when to try the filter again
+            const double cand = (double)std::max<long long>(n, 1);
+            if (job.used_filter) {
+                e->pass_ema = 0.5 * e->pass_ema + 0.5 * ((double)e->last_passed / cand);
+                if (e->pass_ema > 0.25) { e->prefer_scan = true; e->scan_streak = 0; }
+            } else if (e->prefer_scan) {
+                if ((double)cnt / cand < 0.05 && ++e->scan_streak >= 8) { e->prefer_scan = false; e->pass_ema = 0.0; }
+                else if ((double)cnt / cand >= 0.05) e->scan_streak = 0;
+            }
+        }
+        e->d2h_bytes += 24 + std::min<long long>(cnt, FN3_ZC_CAP) * (long long)sizeof(EdgeRec);
         recs = reinterpret_cast<const EdgeRec*>(e->zc_buf + 64);
         *n_out = cnt;
         if (cnt > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld hits, %lld needed", (long long)cap, cnt);
@@ -1122,6 +1234,7 @@ extern "C" int fn3_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling,
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
     RowHdr qh; int rc;
+    if ((rc = maybe_refresh_heads(e))) return rc;
     if ((rc = stored_hdr(e, query_row, &qh, "fn3_one_vs_all", &e->slot_blocks[0]))) return rc;
     QueryJob job; job.ceiling = ceiling;
     snapshot_store(e, job);
@@ -1217,6 +1330,8 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
         return set_err(e, FN3_EARG, "fn3_insert_query: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
+    const int rcr = maybe_refresh_heads(e);
+    if (rcr) return rcr;
     return insert_query_locked(e, pos, off, invalid, ceiling, out_row, out, cap, n_out);
 }
 
@@ -1226,6 +1341,7 @@ extern "C" int fn3_lists_vs_all(fn3_engine* e, const int32_t* pos, const int32_t
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
     RowHdr qh; int rc;
+    if ((rc = maybe_refresh_heads(e))) return rc;
     if ((rc = upload_scratch(e, 0, pos, off, invalid, &qh, &e->slot_blocks[0]))) return rc;
     QueryJob job; job.ceiling = ceiling;
     snapshot_store(e, job);
@@ -1375,6 +1491,8 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
         return set_err(e, FN3_EARG, "fn3_all_vs_all: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
+    const int rcr = maybe_refresh_heads(e);
+    if (rcr) return rcr;
     QueryJob job; job.ceiling = ceiling;
     snapshot_store(e, job);
     const long long n_store = job.n_rows;

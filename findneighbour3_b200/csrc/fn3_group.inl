@@ -251,6 +251,7 @@ extern "C" int fn3_group_stats_get(fn3_group* g, fn3_stats* out) {
         out->n_live += s.n_live; out->n_invalid += s.n_invalid; out->store_words += s.store_words;
         out->store_bytes += s.store_bytes; out->positions += s.positions; out->h2d_bytes += s.h2d_bytes; out->d2h_bytes += s.d2h_bytes;
         out->t_pack_ns += s.t_pack_ns; out->t_enqueue_ns += s.t_enqueue_ns; out->t_wait_ns += s.t_wait_ns; out->n_timed += s.n_timed;
+        out->head_refreshes += s.head_refreshes; out->scan_mode += s.scan_mode;
     }
     out->n_rows = g->n_global;
     return FN3_OK;
@@ -285,6 +286,8 @@ static int foreign_vs_all(fn3_engine* e, const RowHdr& qh, int src_dev, bool pee
                           int32_t ceiling, const int64_t* rows, int64_t n_rows, fn3_hit* out, int64_t cap, int64_t* n_out) {
     std::lock_guard<std::mutex> q(e->query_mu);
     CU(e, cudaSetDevice(e->device));
+    const int rcr = maybe_refresh_heads(e);
+    if (rcr) return rcr;
     RowHdr h = qh;
     if (h.data && !peer && src_dev != e->device) {
         const size_t nv = h.end[3];
@@ -480,6 +483,8 @@ extern "C" int fn3_group_all_vs_all(fn3_group* g, int32_t ceiling, int32_t upper
         fn3_engine* e = g->eng[(size_t)d];
         std::lock_guard<std::mutex> q(e->query_mu);
         CU(e, cudaSetDevice(e->device));
+        const int rcr = maybe_refresh_heads(e);
+        if (rcr) return rcr;
         QueryJob job; job.ceiling = ceiling;
         snapshot_store(e, job);
         std::vector<AvaQuery> qs;

@@ -399,8 +399,10 @@ __device__ __forceinline__ void signal_done(const CompareParams& p) {
         if (t == total - 1u) {
             __threadfence();
             const unsigned long long cnt = atomicExch(p.out_count, 0ull);
+            const unsigned long long passed = atomicExch(p.out_count + 2, 0ull);
             *p.done_ctas = 0u;
             p.host_flag[1] = cnt;
+            p.host_flag[2] = passed;
             __threadfence_system();
             p.host_flag[0] = p.seq;
         }
@@ -456,7 +458,6 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     const int pos_bits = p.pos_bits;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
     unsigned long long touched = 0;
-    unsigned int passed = 0;                               // instrumented variant: candidates phase A could not rule out
 
     {
         // upper triangle: superblocks that hold only rows <= skip_le cannot contain a candidate
@@ -505,7 +506,9 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
         // either sits in its lane's registers already (single-candidate path: HAVE_HDR, nine shuffles) or is fetched now.
         auto survivors = [&](bool passA, int rowA, bool passB, int rowB, const bool HAVE_HDR, const uint4& ha0, const uint4& ha1) {
             uint32_t aliveA = __ballot_sync(0xffffffffu, passA), aliveB = __ballot_sync(0xffffffffu, passB);
-            if (COUNT && lane == 0) passed += __popc(aliveA) + __popc(aliveB);
+            // candidates the head filter could not rule out: the host steers FILTER <-> STREAM by this rate (a few atomics per
+            // launch on an ordinary collection; one per unit in an outbreak)
+            if (lane == 0 && (aliveA | aliveB)) atomicAdd(p.out_count + 2, (unsigned long long)(__popc(aliveA) + __popc(aliveB)));
             if (p.debug_stop == 2) { aliveA = 0u; aliveB = 0u; }
             while (aliveA | aliveB) {
                 const bool fromA = aliveA != 0u;
@@ -580,9 +583,69 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, o);
-        if (lane == 0) { atomicAdd(p.touched, touched); if (passed) atomicAdd(p.touched + 1, (unsigned long long)passed); }
+        if (lane == 0) atomicAdd(p.touched, touched);
     }
     if (p.host_flag) signal_done(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// background-aware heads (fn3_refresh_heads)
+// ------------------------------------------------------------------------------------------------
+// A head carries 32 of the row's V positions as fingerprints.  WHICH 32 does not matter for correctness (every V position of
+// the candidate that falls in a block the query does not touch is a certain mismatch) but it decides the filter's power: two
+// unrelated isolates of one lineage agree on most of their lineage-defining positions, so the 32 lowest coordinates of a real
+// collection are mostly SHARED and rule nothing out.  The engine therefore keeps a bitmap of BACKGROUND positions — non-reference
+// in at least a given fraction of the stored rows — and a head takes the row's first 32 positions that are NOT background
+// (its private variants), topped up with background ones only when it has fewer.
+
+// bit p of bg = the four base planes of the vote (fn3_cluster.cuh) add up to at least thr at position p
+__global__ void k_bg_bits(const uint32_t* __restrict__ cnt, long long Lpad, long long L, uint32_t thr, uint32_t* __restrict__ bg,
+                          long long n_words) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t bits = 0u;
+    for (int k = 0; k < 32; ++k) {
+        const long long pos = w * 32 + k;
+        if (pos >= L) break;
+        const uint32_t t = cnt[pos] + cnt[Lpad + pos] + cnt[2 * Lpad + pos] + cnt[3 * Lpad + pos];
+        if (t >= thr) bits |= 1u << k;
+    }
+    bg[w] = bits;
+}
+
+// one warp per row: rewrite the 32 fingerprints of the row's head from its V words and the background bitmap
+__global__ void __launch_bounds__(256) k_rehead(const HdrTable ht, long long n_rows, const uint32_t* __restrict__ bg, int fshift,
+                                                uint32_t fp_pad) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    int tl;
+    unsigned char* tile = const_cast<unsigned char*>(tile_of(ht, row, tl));
+    const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
+    const uint4 h0 = __ldcg(hp), h1 = __ldcg(hp + 1);
+    if ((h0.x | h0.y) == 0u) return;                        // invalid / removed rows keep their always-mismatching fingerprints
+    const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(((unsigned long long)h0.y << 32) | h0.x);
+    const uint32_t e3 = h1.y;
+    unsigned char* fpb = tile + FN3_TILE_FP_OFF + tl * 16;  // fingerprint f lives at fpb + (f / 8) * 512 + (f % 8) * 2
+    uint32_t k = 0;
+    for (int pass = 0; pass < 2 && k < FN3_HEAD_FP; ++pass)
+        for (uint32_t base = 0; base < e3 && k < FN3_HEAD_FP; base += 32) {
+            const uint32_t i = base + lane;
+            uint32_t w = 0u;
+            bool want = false;
+            if (i < e3) {
+                w = __ldg(d + i);
+                const bool isbg = (__ldg(bg + (w >> 5)) >> (w & 31u)) & 1u;
+                want = pass == 0 ? !isbg : isbg;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, want);
+            const uint32_t slot = k + __popc(m & lowmask(lane));
+            if (want && slot < FN3_HEAD_FP)
+                *reinterpret_cast<uint16_t*>(fpb + (slot >> 3) * 512 + (slot & 7u) * 2) = (uint16_t)(w >> fshift);
+            k += __popc(m);
+        }
+    if (k < FN3_HEAD_FP && (uint32_t)lane >= k)
+        *reinterpret_cast<uint16_t*>(fpb + ((uint32_t)lane >> 3) * 512 + ((uint32_t)lane & 7u) * 2) = (uint16_t)fp_pad;
 }
 
 // L2 flush helper for the measurement hook

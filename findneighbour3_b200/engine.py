@@ -165,6 +165,11 @@ class Engine:
         self._check(self._f_stats_get(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in N.Stats._fields_}
 
+    def refresh_heads(self, min_ppm=10000):
+        """rebuild the heads of the low-ceiling filter from a fresh background bitmap (fn3_refresh_heads; single engine: a
+        group refreshes each member automatically)"""
+        self._check(self._lib.fn3_refresh_heads(self._hl, int(min_ppm)))
+
     def row_get(self, row):
         """-> (pos int32[], off int32[7], invalid bool) of a stored row."""
         off = np.zeros(7, dtype=np.int32)

@@ -87,6 +87,8 @@ typedef struct fn3_stats {
     int64_t t_enqueue_ns;    /*   ... enqueue the copies and the kernel */
     int64_t t_wait_ns;       /*   ... wait for the result */
     int64_t n_timed;         /*   ... number of fn3_insert_query calls timed */
+    int64_t head_refreshes;  /* times the heads were rebuilt from a new background bitmap (fn3_refresh_heads, automatic or not) */
+    int64_t scan_mode;       /* 1 while full low-ceiling scans are steered to the streaming kernel (most candidates pass the head filter) */
 } fn3_stats;
 
 /* ---- life cycle ------------------------------------------------------------------ */
@@ -120,6 +122,15 @@ int fn3_append_bulk(fn3_engine* e, int64_t n, const int32_t* pos, const int64_t*
 int fn3_remove(fn3_engine* e, int64_t row);
 
 int fn3_stats_get(fn3_engine* e, fn3_stats* out);
+
+/* Rebuild the row heads the low-ceiling filter reads.  A head carries 32 of a row's variant positions; which 32 is free (any
+ * variant position of the candidate in a block the query does not touch is a certain mismatch) but decides the filter's
+ * power: isolates of one lineage share most of their low-coordinate variants, so the engine keeps a bitmap of BACKGROUND
+ * positions — non-reference in at least min_ppm / 1e6 of the live valid rows (and in at least 8) — and a head takes the row's
+ * first 32 positions that are not background.  Results never change; only how many candidates are ruled out from their
+ * head.  The engine calls this itself whenever the store has doubled (FN3_BG_AUTO=0 turns that off, FN3_BG_PPM sets the
+ * fraction: default 10 000 = 1 %); min_ppm <= 0 clears the background (heads = the first 32 positions, as before). */
+int fn3_refresh_heads(fn3_engine* e, int64_t min_ppm);
 
 /* Copy a stored row back as the six plain lists (load(), :136-141, used by tests and by
  * the sharded host layer to ship a query to other ranks).  pos_cap in int32 elements;

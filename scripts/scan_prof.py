@@ -9,8 +9,8 @@ from findneighbour3_b200.engine import Engine
 
 NPZ = "/tmp/fn3_scan_store.npz"
 if not os.path.exists(NPZ):
-    common = bench.make_common()
-    coll = bench.make_shard(50000, 0, common)
+    common = bench.make_common(os.cpu_count())
+    coll = bench.make_shard(50000, 0, common, os.cpu_count())
     qs = bench.make_queries(common, 40)
     np.savez(NPZ, pos=coll.pos, off=coll.off, invalid=coll.invalid, L=coll.genome_length,
              qpos=np.concatenate([q[0] for q in qs]), qoff=np.stack([q[1] for q in qs]),

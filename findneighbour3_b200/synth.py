@@ -222,7 +222,9 @@ def make_collection(n_anc, max_c, genome_length=TB_LENGTH, k1=500, s=3.0, n_bloc
 
 def _families_task(task):
     seeds, max_c, tb_mask, kw, bases = task
-    mask = synthetic_mask(TB_LENGTH, TB_EXCLUDED, TB_EXCLUDED_RUNS) if tb_mask else None
+    kw = dict(kw)
+    spec = kw.pop("mask_spec", None)             # (length, excluded positions, runs, seed) of another organism's mask
+    mask = synthetic_mask(*spec) if spec else (synthetic_mask(TB_LENGTH, TB_EXCLUDED, TB_EXCLUDED_RUNS) if tb_mask else None)
     parts = []
     for k, sd in enumerate(seeds):
         base = None

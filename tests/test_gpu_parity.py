@@ -397,6 +397,84 @@ def test_threads_append_while_querying():
     eng.close()
 
 
+@pytest.mark.parametrize("kind", ["engine", "group"])
+def test_stress_inserts_removals_and_queries_racing(kind):
+    """Stands in for the racecheck the pool does not offer: four threads hammer one store — fused inserts (the kernel places the
+    head by value), appends, removals (k_put_head from another stream) and queries at both kernel variants — then, at
+    quiescence, EVERY live row is queried and compared with the C oracle on exactly the rows that are live."""
+    import threading
+    from findneighbour3_b200.engine import Engine, GroupEngine
+    from oracle import c_oracle
+    coll = _synthetic(10, 40, 300000, 61, k1=300, s=3.0, n_blocks=8, n_mean=2000, m_mean=3, rule="any", p_invalid=0.03)
+    eng = Engine(coll.genome_length, 0) if kind == "engine" else GroupEngine(coll.genome_length, [0, 0, 0])
+    base = 200
+    first = coll.subset(np.arange(base))
+    eng.append_bulk(first.pos, first.off, first.invalid)
+    errors, removed, row_of = [], set(), {i: i for i in range(base)}
+    lock = threading.Lock()
+    stop = threading.Event()
+
+    def inserter(lo, hi, fused):
+        try:
+            for i in range(lo, hi):
+                p, o, inv = coll.lists(i)
+                with lock:                       # (the row number of a sample must be known to check it later; the engine calls
+                    pass                         #  themselves run unlocked and race with the other threads)
+                row = eng.insert_query(p, o, inv, 20)[0] if fused else eng.append(p, o, inv)
+                with lock:
+                    row_of[i] = row
+        except Exception as ex:      # pragma: no cover
+            errors.append(ex)
+
+    def remover():
+        rng = np.random.default_rng(1)
+        try:
+            for r in rng.choice(base, size=60, replace=False):
+                eng.remove(int(r))
+                with lock:
+                    removed.add(int(r))
+        except Exception as ex:      # pragma: no cover
+            errors.append(ex)
+
+    def querier():
+        rng = np.random.default_rng(2)
+        try:
+            while not stop.is_set():
+                q = int(rng.integers(0, base))
+                try:
+                    hits = eng.one_vs_all(q, 20 if rng.random() < 0.5 else 250)
+                except KeyError:                 # the query row was removed meanwhile: the reference raises KeyError too
+                    continue
+                for h in hits:
+                    assert int(h["row"]) != q and int(h["dist"]) <= 250
+        except Exception as ex:      # pragma: no cover
+            errors.append(ex)
+
+    threads = [threading.Thread(target=inserter, args=(base, base + 100, True)),
+               threading.Thread(target=inserter, args=(base + 100, coll.n, False)),
+               threading.Thread(target=remover), threading.Thread(target=querier)]
+    for t in threads:
+        t.start()
+    for t in threads[:3]:
+        t.join()
+    stop.set()
+    threads[3].join()
+    assert not errors, errors
+    # quiescence: the live rows, in engine row order, against the oracle
+    sample_of = {row: i for i, row in row_of.items()}
+    live_rows = sorted(r for r in sample_of if r not in removed)
+    live = coll.subset(np.array([sample_of[r] for r in live_rows]))
+    index_of = {r: k for k, r in enumerate(live_rows)}
+    assert eng.stats()["n_live"] == len(live_rows) and eng.stats()["n_rows"] == coll.n
+    for ceiling in (12, 20, 250):
+        for r in live_rows[::3]:
+            want = c_oracle.one_vs_all(live.pos, live.off, live.invalid, index_of[r], ceiling)
+            got = {index_of[int(h["row"])]: (int(h["dist"]), int(h["n1"]), int(h["n2"]), int(h["nboth"]))
+                   for h in eng.one_vs_all(r, ceiling)}
+            assert got == want, (kind, ceiling, r)
+    eng.close()
+
+
 def test_msa_golden():
     """multi_sequence_alignment / mixPORE statistics (seqComparer.py:691-1128) against the reference's outputs."""
     import math
@@ -694,32 +772,78 @@ def test_config2_full_size_50k_sampled_queries_vs_oracle():
 
 @pytest.mark.parametrize("organism", ["salm", "ngon"])
 def test_config4_high_n_and_mixed_collections(organism):
-    """BASELINE.json configs[3]: S. enterica-shaped (L = 4 857 432, SALM-exclude-sized mask) and N. gonorrhoeae-shaped
-    (L = 2 232 025, no mask) collections with tens of thousands of N and hundreds of IUPAC positions per sample, some
-    invalid through maxNs = 130 000: mixture-aware mcompare counts (dist, n1, n2, nboth) vs the C oracle."""
+    """BASELINE.json configs[3] at the size SURVEY 8(d) names: 5 000 samples of an S. enterica-shaped (L = 4 857 432,
+    SALM-exclude-sized mask) and of an N. gonorrhoeae-shaped (L = 2 232 025, no mask) collection with tens of thousands of N
+    and hundreds of IUPAC positions per sample, some invalid through maxNs = 130 000, plus 2 % MIXED samples built as
+    src/make_simulation.py:147-164 (mix_sequences) builds them — mixture-aware mcompare counts (dist, n1, n2, nboth) vs the
+    C oracle, with mixtures among the queries."""
     from findneighbour3_b200 import synth
     from findneighbour3_b200.engine import Engine
     from oracle import c_oracle
+    workers = max(1, min(16, os.cpu_count() or 1))
     if organism == "salm":
         L = 4857432
-        mask = synth.synthetic_mask(L, 51897, 58, seed=44)
-        coll = synth.make_collection(40, 25, genome_length=L, seed=4, k1=5000, s=5.0, n_blocks=60, n_mean=30000, m_mean=300,
-                                     rule="any", n_lognormal_sigma=0.9, max_ns=130000, excluded=mask, ref_seed=4)
+        coll = synth.make_families([4_000_000 + a for a in range(200)], 25, workers=workers, tb_mask=False,
+                                   mask_spec=(L, 51897, 58, 44), genome_length=L, k1=5000, s=5.0, n_blocks=60, n_mean=30000,
+                                   m_mean=300, rule="any", n_lognormal_sigma=0.9, max_ns=130000, ref_seed=4)
     else:
         L = 2232025
-        coll = synth.make_collection(40, 25, genome_length=L, seed=5, k1=3000, s=5.0, n_blocks=50, n_mean=20000, m_mean=1000,
-                                     rule="any", n_lognormal_sigma=0.9, max_ns=130000, p_invalid=0.02, ref_seed=5)
+        coll = synth.make_families([5_000_000 + a for a in range(200)], 25, workers=workers, tb_mask=False, genome_length=L,
+                                   k1=3000, s=5.0, n_blocks=50, n_mean=20000, m_mean=1000, rule="any", n_lognormal_sigma=0.9,
+                                   max_ns=130000, p_invalid=0.02, ref_seed=5)
+    assert coll.n == 5000
+    coll = synth.add_mixtures(coll, 0.02, seed=5, max_ns=130000)
+    assert coll.n == 5100
     eng = Engine(L, 0)
     eng.append_bulk(coll.pos, coll.off, coll.invalid)
     rng = np.random.default_rng(8)
-    nthreads = max(1, min(16, os.cpu_count() or 1))
     n_checked = 0
-    for q in rng.choice(coll.n, size=10, replace=False):
-        want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, int(q), 20, nthreads=nthreads)
-        assert hits_to_dict(eng.one_vs_all(int(q), 20)) == want
-        n_checked += len(want)
-    assert n_checked > 0
+    mixed_valid = [q for q in range(5000, 5100) if not coll.invalid[q]]
+    queries = [int(q) for q in rng.choice(5000, size=10, replace=False)] + mixed_valid[:6]
+    for q in queries:
+        for ceiling in (20, 100000):             # 100 000: every valid pair reports its counts (mixtures are far from everything)
+            want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, q, ceiling, nthreads=workers)
+            assert hits_to_dict(eng.one_vs_all(q, ceiling)) == want, (organism, q, ceiling)
+            n_checked += len(want)
+    assert n_checked > 0 and len(mixed_valid) > 0
     eng.close()
+
+
+def test_config0_full_thousand_incremental_inserts_every_insert_checked():
+    """BASELINE.json configs[0] as SURVEY 8(d) states it: 1 000 samples (20 families x 50, TB-length genome, TB-exclude-shaped
+    mask, 1 % invalid) inserted one by one through the drop-in class, mcompare after EVERY insert, every row of every result —
+    neighbours and the None rows — checked against the C oracle: 499 500 pairs."""
+    from findneighbour3_b200 import synth
+    from findneighbour3_b200.seqComparer import seqComparer
+    from oracle import c_oracle
+    L = synth.TB_LENGTH
+    mask = synth.synthetic_mask(L, synth.TB_EXCLUDED, synth.TB_EXCLUDED_RUNS)
+    coll = synth.make_families([1_000 + a for a in range(20)], 50, workers=max(1, min(16, os.cpu_count() or 1)), m_mean=2,
+                               rule="any")
+    assert coll.n == 1000
+    ref = synth.reference_string(synth.random_reference(L))
+    sc = seqComparer(reference=ref, maxNs=130000, snpCeiling=20, excludePositions=set(np.flatnonzero(mask).tolist()))
+    pairs = neighbours = 0
+    for i in range(coll.n):
+        sc.persist(coll.as_dict(i), "s%d" % i)
+        res = sc.mcompare("s%d" % i)
+        assert len(res) == i
+        got, none_rows = {}, 0
+        for (g1, g2, d, n1, n2, nboth, a, b, c) in res:
+            assert g1 == "s%d" % i
+            if d is None:
+                assert (n1, n2, nboth, a, b, c) == (None,) * 6
+                none_rows += 1
+            else:
+                got[int(g2[1:])] = (d, n1, n2, nboth)
+                assert (len(a), len(b), len(c)) == (n1, n2, nboth)         # the position sets of a surviving pair (:416-418)
+        want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, i, 20, nthreads=4)
+        want = {r: v for r, v in want.items() if r < i}
+        assert got == want and none_rows == i - len(want), i
+        pairs += i
+        neighbours += len(want)
+    assert pairs == 499500 and neighbours > 10000
+    assert sc.summarise_stored_items()["server|scstat|nSeqs"] == 1000
 
 
 def test_low_ceiling_filter_with_removed_and_invalid_rows():

@@ -756,6 +756,8 @@ def main():
         except Exception as ex:   # pragma: no cover
             errors["all_vs_all"] = repr(ex)
             log("all_vs_all leg failed:", repr(ex))
+            if world > 1:                        # the other ranks are inside this leg's collectives: fail fast, do not strand them
+                raise
 
     # ================================================================================================
     # leg 6 (every N): BASELINE configs[4] — collection resident across the GPUs, streamed inserts each queried
@@ -951,13 +953,16 @@ def run_allvsall(args, rank, world, local, workers, barrier, max_over_ranks, sum
         sel = np.isin(edges["row1"], np.array(mine_rows, dtype=np.int64))
         for e in edges[sel]:
             by_row.setdefault(int(e["row1"]), {})[int(e["row2"])] = (int(e["dist"]), int(e["n1"]), int(e["n2"]), int(e["nboth"]))
-    checked = 0
+    checked = bad = 0
     for r in mine_rows:
         want = c_oracle.one_vs_all(full.pos, full.off, full.invalid, r, args.ava_ceiling, nthreads=max(1, workers))
         want = {k: v for k, v in want.items() if k > r}
-        assert by_row.get(r, {}) == want, "all-vs-all parity: row %d differs from the C oracle" % r
+        if by_row.get(r, {}) != want:            # (no assert here: a rank that left the leg early would strand the others
+            bad += 1                             #  in the collectives below)
+            log("all-vs-all parity: row", r, "differs from the C oracle on rank", rank)
         checked += 1
     checked = int(sum_over_ranks(float(checked)))
+    bad = int(sum_over_ranks(float(bad)))
     pairs = n * (n - 1) / 2
     b_pair = (4.0 * st["positions"] + 32.0 * st["n_live"]) / max(st["n_live"], 1)
     out = None
@@ -968,7 +973,7 @@ def run_allvsall(args, rank, world, local, workers, barrier, max_over_ranks, sum
                "samples": int(n), "ceiling": args.ava_ceiling, "n_gpus": world, "scaling": "strong",
                "seconds": t, "seconds_compute_max_rank": t_compute, "seconds_first_pass": runs[0][0],
                "edges": int(len(all_edges)), "pairs": int(pairs),
-               "comparisons_per_s": pairs / t, "edge_checksum": cs, "parity_rows_checked": checked,
+               "comparisons_per_s": pairs / t, "edge_checksum": cs, "parity_rows_checked": checked, "parity_rows_wrong": bad,
                "gpu_launches": int(launches), "setup_s": t_setup,
                "canonical_GBps": pairs * b_pair / t / 1e9, "frac_canonical": pairs * b_pair / t / 1e9 / (peak * world),
                "note": "seconds = max over ranks of (fn3_all_vs_all of the rank's block rows + gather of all edges on rank 0); the "

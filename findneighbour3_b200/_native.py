@@ -51,6 +51,7 @@ SIGNATURES = {
     "fn3_remove": (C.c_int, [_vp, C.c_int64]),
     "fn3_stats_get": (C.c_int, [_vp, _vp]),
     "fn3_refresh_heads": (C.c_int, [_vp, C.c_int64]),
+    "fn3_compact": (C.c_int, [_vp, _i64p, C.c_int64, _i64p, _i64p]),
     "fn3_row_get": (C.c_int, [_vp, C.c_int64, _i32p, C.c_int64, _i32p, _i32p, _i64p]),
     "fn3_one_vs_all": (C.c_int, [_vp, C.c_int64, C.c_int32, _i64p, C.c_int64, _vp, C.c_int64, _i64p]),
     "fn3_insert_query": (C.c_int, [_vp, _i32p, _i32p, C.c_int32, C.c_int32, _i64p, _vp, C.c_int64, _i64p]),

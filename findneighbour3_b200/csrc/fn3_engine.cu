@@ -16,6 +16,7 @@
 #include "fn3_types.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -169,6 +170,36 @@ static int set_err(fn3_engine* e, int code, const char* fmt, ...) {
 #define CU(e, call) do { cudaError_t _s = (call); if (_s != cudaSuccess) \
     return set_err((e), FN3_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_s), __FILE__, __LINE__); } while (0)
 
+// Every entry point works on its engine's device and then gives the calling thread its own device back: a caller that also
+// uses CUDA itself (PyTorch in bench.py; another engine on another GPU) must not find its current device changed.  The
+// previous device is restored only if it has a live primary context (cuDevicePrimaryCtxGetState through dlsym: libcuda is
+// not linked) — a thread that never chose a device reports 0, and "restoring" that would create a context on GPU 0.
+static bool primary_ctx_active(int dev) {
+    typedef int (*state_fn)(int, unsigned int*, int*);
+    static state_fn fn = []() -> state_fn {
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libcuda.so.1", RTLD_NOW);
+        return h ? (state_fn)dlsym(h, "cuDevicePrimaryCtxGetState") : nullptr;
+    }();
+    if (!fn) return true;
+    unsigned int flags = 0; int active = 0;
+    return fn(dev, &flags, &active) != 0 || active != 0;
+}
+
+struct DeviceGuard {
+    int prev = -1, dev;
+    bool ok;
+    explicit DeviceGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; (void)cudaGetLastError(); }
+        ok = prev == d || cudaSetDevice(d) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev && primary_ctx_active(prev)) (void)cudaSetDevice(prev);
+    }
+};
+#define FN3_ON_DEVICE(e) DeviceGuard _dg((e)->device); \
+    if (!_dg.ok) return set_err((e), FN3_ECUDA, "cudaSetDevice(%d) failed (%s:%d)", (e)->device, __FILE__, __LINE__)
+
 static long long env_ll(const char* name, long long dflt) {
     const char* s = getenv(name);
     if (!s || !*s) return dflt;
@@ -281,7 +312,8 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
         fn3_destroy(e);
         return nullptr;
     };
-    if ((s = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", s);
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail("cudaSetDevice", cudaGetLastError());
     cudaDeviceProp prop;
     if ((s = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", s);
     e->sm_count = prop.multiProcessorCount;
@@ -370,7 +402,7 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
 
 extern "C" int fn3_destroy(fn3_engine* e) {
     if (!e) return FN3_OK;
-    cudaSetDevice(e->device);
+    DeviceGuard dg(e->device);
     if (e->q_stream) cudaStreamSynchronize(e->q_stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     for (auto p : e->data_chunks) cudaFree(p);
@@ -668,7 +700,7 @@ static void parallel_rows(long long n, int max_threads, F fn, long long min_rows
 static int append_impl(fn3_engine* e, long long n, const int32_t* pos, const long long* off6, const uint8_t* invalid,
                        long long* out_first_row) {
     std::lock_guard<std::mutex> g(e->store_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     const int host_threads = (int)std::max<long long>(1, std::min<long long>(env_ll("FN3_HOST_THREADS", 16),
                                                                              (long long)std::thread::hardware_concurrency()));
     // pass 1: validate + size (rows are independent: host threads)
@@ -799,7 +831,7 @@ extern "C" int fn3_remove(fn3_engine* e, int64_t row) {
     std::lock_guard<std::mutex> g(e->store_mu);
     if (row < 0 || row >= e->n_rows) return set_err(e, FN3_ENOTFOUND, "fn3_remove: row %lld does not exist", (long long)row);
     if (e->h_flags[(size_t)row] & 2) return FN3_OK;          // removing twice is silent (seqComparer.py:131-134)
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     RowHdr dead; memset(&dead, 0, sizeof dead);
     RowHead dead_head;
     fill_head(e, dead_head, dead, nullptr);           // zero header + fingerprints that always mismatch
@@ -845,7 +877,7 @@ extern "C" int fn3_row_get(fn3_engine* e, int64_t row, int32_t* pos, int64_t pos
     if (fl & 1) return FN3_OK;
     if ((int64_t)np > pos_cap) return set_err(e, FN3_ECAPACITY, "fn3_row_get: need room for %u positions", np);
     std::vector<uint32_t> w(h.end[5]);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     if (h.end[5]) CU(e, cudaMemcpy(w.data(), (const void*)(uintptr_t)h.data, (size_t)h.end[5] * 4, cudaMemcpyDeviceToHost));
     int64_t k = 0;
     const uint32_t pmask = (e->pos_bits >= 32) ? 0xffffffffu : ((1u << e->pos_bits) - 1u);
@@ -1049,7 +1081,7 @@ static int ensure_rows(fn3_engine* e, long long n);
 // at least ppm / 1e6 of the live valid rows (and in at least 8 of them); ppm <= 0 clears the background.
 static int refresh_heads_locked(fn3_engine* e, long long ppm) {
     std::lock_guard<std::mutex> g(e->store_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     cudaStream_t st = e->q_stream;
     const long long n = e->n_rows;
     const long long n_words = (e->L + 31) / 32;
@@ -1090,6 +1122,97 @@ static int refresh_heads_locked(fn3_engine* e, long long ppm) {
     e->bg_any = any;
     e->bg_refreshes++;
     e->bg_next_at = std::max<long long>(4096, 2 * e->n_live);
+    return FN3_OK;
+}
+
+// remove(guid) leaves a tombstone: the row's words stay in HBM and its slot in the head tiles is scanned (and skipped) by every
+// query.  fn3_compact rebuilds the store ON THE DEVICE: the live rows are copied into fresh chunks in row order (one warp per
+// row), renumbered densely, their heads rebuilt from the row data (k_place_hdrs + k_rehead) — no row travels through the
+// host.  new_row[r] receives the new number of old row r, or -1 if it was removed.
+extern "C" int fn3_compact(fn3_engine* e, int64_t* new_row, int64_t cap, int64_t* n_before, int64_t* n_after) {
+    if (!e || !n_before || !n_after) return set_err(e, FN3_EARG, "fn3_compact: bad arguments");
+    std::lock_guard<std::mutex> q(e->query_mu);
+    std::lock_guard<std::mutex> g(e->store_mu);
+    FN3_ON_DEVICE(e);
+    const long long n = e->n_rows;
+    *n_before = n; *n_after = e->n_live;
+    if (n > cap || (n > 0 && !new_row)) return set_err(e, FN3_ECAPACITY, "fn3_compact: the row map needs %lld entries", n);
+    if (e->n_live == n) { for (long long r = 0; r < n; ++r) new_row[r] = r; return FN3_OK; }
+    cudaStream_t st = e->q_stream;
+    CU(e, cudaStreamSynchronize(e->copy_stream));
+    CU(e, cudaStreamSynchronize(st));
+    // 1. lay the live rows out in fresh chunks
+    std::vector<uint32_t*> chunks; std::vector<size_t> caps; size_t used = 0;
+    std::vector<RowCopy> copies; std::vector<RowHdr> hdrs;
+    std::vector<uint8_t> flags; std::vector<uint32_t> npos, nblk;
+    long long words_total = 0, k = 0;
+    auto fail = [&](int rc) { for (auto p : chunks) cudaFree(p); return rc; };
+    for (long long r = 0; r < n; ++r) {
+        if (e->h_flags[(size_t)r] & 2) { new_row[r] = -1; continue; }
+        new_row[r] = k++;
+        RowHdr h = e->h_hdr[(size_t)r];
+        if (h.data) {
+            const size_t need = row_alloc_words(h.end[5], h.end[3]);
+            if (chunks.empty() || used + need > caps.back()) {
+                const size_t c = std::max(e->chunk_words, need);
+                uint32_t* p = nullptr;
+                if (cudaMalloc(&p, c * 4) != cudaSuccess) { (void)cudaGetLastError(); return fail(set_err(e, FN3_ENOMEM, "fn3_compact: no room for a second copy of the store")); }
+                chunks.push_back(p); caps.push_back(c); used = 0;
+            }
+            RowCopy c; c.src = h.data; c.dst = (unsigned long long)(uintptr_t)(chunks.back() + used); c.words = (uint32_t)need; c.pad = 0;
+            copies.push_back(c);
+            h.data = c.dst;
+            used += need; words_total += (long long)need;
+        }
+        hdrs.push_back(h); flags.push_back(e->h_flags[(size_t)r]); npos.push_back(e->h_npos[(size_t)r]); nblk.push_back(e->h_nblk[(size_t)r]);
+    }
+    const long long m = k;
+    // 2. copy the rows, place the headers in fresh tiles, rebuild the fingerprints
+    RowCopy* d_copies = nullptr; RowHdr* d_hdrs = nullptr;
+    std::vector<unsigned char*> tiles;
+    auto fail2 = [&](int rc) { cudaFree(d_copies); cudaFree(d_hdrs); for (auto p : tiles) cudaFree(p); return fail(rc); };
+    if (!copies.empty()) {
+        if (cudaMalloc(&d_copies, copies.size() * sizeof(RowCopy)) != cudaSuccess) return fail2(set_err(e, FN3_ENOMEM, "fn3_compact: cudaMalloc failed"));
+        cudaMemcpy(d_copies, copies.data(), copies.size() * sizeof(RowCopy), cudaMemcpyHostToDevice);
+        k_copy_rows<<<(unsigned)std::min<long long>(((long long)copies.size() + 7) / 8, (long long)e->sm_count * 16), 256, 0, st>>>(d_copies, (long long)copies.size());
+        e->launches += 1;
+    }
+    HdrTable ht; memset(&ht, 0, sizeof ht);
+    ht.shift = e->hdr_shift; ht.sb_shift = e->sb_shift;
+    const size_t tile_bytes = ((size_t)FN3_TILE_BYTES / 32) << e->hdr_shift;
+    for (long long c = 0; c <= (std::max<long long>(m, 1) - 1) >> e->hdr_shift; ++c) {
+        unsigned char* p = nullptr;
+        if (cudaMalloc(&p, tile_bytes) != cudaSuccess) { (void)cudaGetLastError(); return fail2(set_err(e, FN3_ENOMEM, "fn3_compact: cudaMalloc of a header chunk failed")); }
+        cudaMemsetAsync(p, 0, tile_bytes, st);
+        tiles.push_back(p); ht.chunk[c] = p;
+    }
+    if (m > 0) {
+        if (cudaMalloc(&d_hdrs, (size_t)m * sizeof(RowHdr)) != cudaSuccess) return fail2(set_err(e, FN3_ENOMEM, "fn3_compact: cudaMalloc failed"));
+        cudaMemcpyAsync(d_hdrs, hdrs.data(), (size_t)m * sizeof(RowHdr), cudaMemcpyHostToDevice, st);
+        k_place_hdrs<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_hdrs, m, ht, (uint32_t)e->fp_dead, (uint32_t)e->fp_pad);
+        if (!e->d_bg) {
+            const long long n_words = (e->L + 31) / 32;
+            if (cudaMalloc(&e->d_bg, (size_t)n_words * 4) != cudaSuccess) return fail2(set_err(e, FN3_ENOMEM, "fn3_compact: cudaMalloc failed"));
+            cudaMemsetAsync(e->d_bg, 0, (size_t)n_words * 4, st);
+        }
+        k_rehead<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(ht, m, e->d_bg, e->fshift, (uint32_t)e->fp_pad);
+        e->launches += 2;
+    }
+    const cudaError_t err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) return fail2(set_err(e, FN3_ECUDA, "fn3_compact: %s", cudaGetErrorString(err)));
+    cudaFree(d_copies); cudaFree(d_hdrs);
+    // 3. switch over
+    for (auto p : e->data_chunks) cudaFree(p);
+    for (auto p : e->hdr_chunks) cudaFree(p);
+    e->data_chunks = chunks; e->data_chunk_cap = caps; e->cur_used = used;
+    e->hdr_chunks = tiles;
+    e->h_hdr = hdrs; e->h_flags = flags; e->h_npos = npos; e->h_nblk = nblk;
+    e->n_rows = m;
+    e->store_words = words_total;
+    e->store_bytes = 0;
+    for (size_t c : caps) e->store_bytes += (long long)c * 4;
+    e->store_bytes += (long long)tiles.size() * (long long)tile_bytes;
+    e->edges_ready = -1;
     return FN3_OK;
 }
 
@@ -1232,7 +1355,7 @@ extern "C" int fn3_one_vs_all(fn3_engine* e, int64_t query_row, int32_t ceiling,
                               fn3_hit* out, int64_t cap, int64_t* n_out) {
     if (!e || !n_out || (cap > 0 && !out) || (rows && n_rows < 0)) return set_err(e, FN3_EARG, "fn3_one_vs_all: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     RowHdr qh; int rc;
     if ((rc = maybe_refresh_heads(e))) return rc;
     if ((rc = stored_hdr(e, query_row, &qh, "fn3_one_vs_all", &e->slot_blocks[0]))) return rc;
@@ -1329,7 +1452,7 @@ extern "C" int fn3_insert_query(fn3_engine* e, const int32_t* pos, const int32_t
     if (!e || !n_out || !out_row || (cap > 0 && !out) || (!invalid && !off))
         return set_err(e, FN3_EARG, "fn3_insert_query: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     const int rcr = maybe_refresh_heads(e);
     if (rcr) return rcr;
     return insert_query_locked(e, pos, off, invalid, ceiling, out_row, out, cap, n_out);
@@ -1339,7 +1462,7 @@ extern "C" int fn3_lists_vs_all(fn3_engine* e, const int32_t* pos, const int32_t
                                 const int64_t* rows, int64_t n_rows, fn3_hit* out, int64_t cap, int64_t* n_out) {
     if (!e || !n_out || (cap > 0 && !out) || (!invalid && !off)) return set_err(e, FN3_EARG, "fn3_lists_vs_all: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     RowHdr qh; int rc;
     if ((rc = maybe_refresh_heads(e))) return rc;
     if ((rc = upload_scratch(e, 0, pos, off, invalid, &qh, &e->slot_blocks[0]))) return rc;
@@ -1352,7 +1475,7 @@ extern "C" int fn3_lists_vs_all(fn3_engine* e, const int32_t* pos, const int32_t
 extern "C" int fn3_pair(fn3_engine* e, int64_t row1, int64_t row2, int32_t ceiling, fn3_hit* out, int32_t* has_dist) {
     if (!e || !out || !has_dist) return set_err(e, FN3_EARG, "fn3_pair: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     RowHdr qh, ch; int rc;
     if ((rc = stored_hdr(e, row1, &qh, "fn3_pair", &e->slot_blocks[0]))) return rc;
     if ((rc = stored_hdr(e, row2, &ch, "fn3_pair"))) return rc;
@@ -1370,7 +1493,7 @@ extern "C" int fn3_pair_lists(fn3_engine* e, const int32_t* pos1, const int32_t 
                               fn3_hit* out, int32_t* has_dist) {
     if (!e || !out || !has_dist) return set_err(e, FN3_EARG, "fn3_pair_lists: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     *has_dist = 0;
     RowHdr qh, ch; int rc;
     if ((rc = upload_scratch(e, 0, pos1, off1, invalid1, &qh, &e->slot_blocks[0]))) return rc;
@@ -1490,7 +1613,7 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
     if (!e || !n_out || (cap > 0 && !out) || stride < 1 || phase < 0 || phase >= stride)
         return set_err(e, FN3_EARG, "fn3_all_vs_all: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     const int rcr = maybe_refresh_heads(e);
     if (rcr) return rcr;
     QueryJob job; job.ceiling = ceiling;
@@ -1521,7 +1644,7 @@ extern "C" int fn3_all_vs_all(fn3_engine* e, int32_t ceiling, int32_t upper_only
 extern "C" int fn3_all_vs_all_fetch(fn3_engine* e, fn3_edge* out, int64_t cap, int64_t* n_out) {
     if (!e || !n_out || (cap > 0 && !out)) return set_err(e, FN3_EARG, "fn3_all_vs_all_fetch: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     if (e->edges_ready < 0) return set_err(e, FN3_ENOTFOUND, "fn3_all_vs_all_fetch: no all-vs-all result is pending");
     *n_out = e->edges_ready;
     if (e->edges_ready > cap) return set_err(e, FN3_ECAPACITY, "output buffer holds %lld edges, %lld needed", (long long)cap, e->edges_ready);
@@ -1535,7 +1658,7 @@ extern "C" int fn3_set_reference(fn3_engine* e, const char* reference, const int
     if (!e || !reference || n_excluded < 0 || (n_excluded > 0 && !excluded))
         return set_err(e, FN3_EARG, "fn3_set_reference: bad arguments");
     std::lock_guard<std::mutex> g(e->ingest_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     const long long per_cta = (long long)FN3_CMP_THREADS * FN3_CMP_PER_THREAD;
     e->cmp_ctas = (int)((e->L + per_cta - 1) / per_cta);
     e->Lpad = (long long)e->cmp_ctas * per_cta;
@@ -1582,7 +1705,7 @@ extern "C" int fn3_set_reference(fn3_engine* e, const char* reference, const int
 static int compress_locked(fn3_engine* e, const char* sequence, int32_t* pos, int64_t pos_cap, int32_t off[7],
                            char* m_chars, int64_t m_cap, int64_t* n_pos, int64_t* hist, const char* who) {
     if (!e->d_refmask) return set_err(e, FN3_EARG, "%s: call fn3_set_reference first", who);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     cudaStream_t st = e->in_stream;
     // staged through pinned memory in 1 MB pieces: the DMA of one piece runs under the host copy of the next
     for (size_t o = 0; o < (size_t)e->L; o += FN3_STAGE_PIECE) {
@@ -1683,7 +1806,8 @@ extern "C" int fn3_byte_histogram(int32_t device, const uint8_t* bytes, int64_t 
     if (n == 0) return FN3_OK;
     HistCtx& c = g_hist[device];
     std::lock_guard<std::mutex> g(c.mu);
-    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return FN3_ECUDA; }   // no device: no CPU path either
+    DeviceGuard dg(device);
+    if (!dg.ok) { cudaGetLastError(); return FN3_ECUDA; }   // no device: no CPU path either
     if (!c.st) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FN3_ECUDA;
@@ -1859,7 +1983,7 @@ extern "C" int fn3_consensus(fn3_engine* e, const int64_t* rows, int64_t n_rows,
     if (!e || !off || !n_pos || n_rows < 0 || (n_rows > 0 && !rows) || min_votes < 1)
         return set_err(e, FN3_EARG, "fn3_consensus: bad arguments (min_votes must be >= 1)");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     int rc;
     HdrTable ht;
     if ((rc = cluster_rows(e, rows, n_rows, false, "fn3_consensus", &ht))) return rc;
@@ -1881,7 +2005,7 @@ extern "C" int fn3_consensus_lists(fn3_engine* e, int64_t n, const int32_t* pos_
         }
     }
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     int rc;
     if ((rc = ensure_votes(e))) return rc;
     cudaStream_t st = e->q_stream;
@@ -1927,7 +2051,7 @@ extern "C" int fn3_msa_sites_rule(fn3_engine* e, const int64_t* rows, int64_t n_
     *n_sites = 0;
     if (n_rows == 0) return FN3_OK;
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     int rc;
     HdrTable ht;
     if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_sites", &ht))) return rc;
@@ -1982,7 +2106,7 @@ extern "C" int fn3_msa_align(fn3_engine* e, const int64_t* rows, int64_t n_rows,
     if ((rc = msa_align_check_sites(e, sites, n_sites))) return rc;
     if (n_rows == 0) return FN3_OK;
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     HdrTable ht;
     if ((rc = cluster_rows(e, rows, n_rows, true, "fn3_msa_align", &ht))) return rc;
     return msa_align_core(e, ht, n_rows, sites, n_sites, codes, counts);
@@ -2030,7 +2154,7 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
                                    int64_t* n_passed) {
     if (!e || !query_rows || n < 1) return set_err(e, FN3_EARG, "fn3_profile_queries: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     QueryJob job; job.ceiling = ceiling;
     snapshot_store(e, job);
     e->edges_ready = -1;

@@ -116,6 +116,7 @@ extern "C" fn3_group* fn3_group_create(int64_t genome_length, int32_t n_devices,
         g->eng.push_back(e); g->dev.push_back(device_ids[d]);
     }
     // peer access between every pair of distinct devices (NVLink / NVSwitch on an HGX board)
+    DeviceGuard dg(g->dev[0]);
     for (int a = 0; a < n_devices; ++a)
         for (int b = 0; b < n_devices; ++b) {
             if (g->dev[(size_t)a] == g->dev[(size_t)b]) continue;
@@ -129,7 +130,6 @@ extern "C" fn3_group* fn3_group_create(int64_t genome_length, int32_t n_devices,
             }
             if (!can) g->peer_all = false;
         }
-    cudaSetDevice(g->dev[0]);
     for (int d = 1; d < n_devices; ++d) g->w[(size_t)d].th = std::thread(group_worker, g, d);
     return g;
 }
@@ -285,7 +285,7 @@ static int group_hdr(fn3_group* g, long long row, RowHdr* h, uint32_t* nblk, uin
 static int foreign_vs_all(fn3_engine* e, const RowHdr& qh, int src_dev, bool peer, uint32_t nblk, long long tag,
                           int32_t ceiling, const int64_t* rows, int64_t n_rows, fn3_hit* out, int64_t cap, int64_t* n_out) {
     std::lock_guard<std::mutex> q(e->query_mu);
-    CU(e, cudaSetDevice(e->device));
+    FN3_ON_DEVICE(e);
     const int rcr = maybe_refresh_heads(e);
     if (rcr) return rcr;
     RowHdr h = qh;
@@ -482,7 +482,7 @@ extern "C" int fn3_group_all_vs_all(fn3_group* g, int32_t ceiling, int32_t upper
     int rc = group_run(g, [&](int d) -> int {
         fn3_engine* e = g->eng[(size_t)d];
         std::lock_guard<std::mutex> q(e->query_mu);
-        CU(e, cudaSetDevice(e->device));
+        FN3_ON_DEVICE(e);
         const int rcr = maybe_refresh_heads(e);
         if (rcr) return rcr;
         QueryJob job; job.ceiling = ceiling;
@@ -543,7 +543,8 @@ extern "C" int fn3_group_consensus(fn3_group* g, const int64_t* rows, int64_t n_
     if ((rc = group_virtual(g, rows, n_rows, false, "fn3_group_consensus", hdrs))) return rc;
     fn3_engine* e = g->eng[0];
     std::lock_guard<std::mutex> q(e->query_mu);
-    if (cudaSetDevice(e->device) != cudaSuccess) return gset_err(g, FN3_ECUDA, "cudaSetDevice failed");
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return gset_err(g, FN3_ECUDA, "cudaSetDevice failed");
     HdrTable ht;
     if ((rc = virtual_rows(e, hdrs.data(), n_rows, &ht))) return gfrom(g, 0, rc);
     return gfrom(g, 0, consensus_core(e, ht, n_rows, min_votes, pos, pos_cap, off, n_pos, "fn3_group_consensus"));
@@ -567,7 +568,8 @@ extern "C" int fn3_group_msa_sites_rule(fn3_group* g, const int64_t* rows, int64
     if ((rc = group_virtual(g, rows, n_rows, true, "fn3_group_msa_sites", hdrs))) return rc;
     fn3_engine* e = g->eng[0];
     std::lock_guard<std::mutex> q(e->query_mu);
-    if (cudaSetDevice(e->device) != cudaSuccess) return gset_err(g, FN3_ECUDA, "cudaSetDevice failed");
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return gset_err(g, FN3_ECUDA, "cudaSetDevice failed");
     HdrTable ht;
     if ((rc = virtual_rows(e, hdrs.data(), n_rows, &ht))) return gfrom(g, 0, rc);
     return gfrom(g, 0, msa_sites_core(e, ht, n_rows, rule, sites, sites_cap, n_sites));
@@ -585,7 +587,8 @@ extern "C" int fn3_group_msa_align(fn3_group* g, const int64_t* rows, int64_t n_
     if ((rc = group_virtual(g, rows, n_rows, true, "fn3_group_msa_align", hdrs))) return rc;
     fn3_engine* e = g->eng[0];
     std::lock_guard<std::mutex> q(e->query_mu);
-    if (cudaSetDevice(e->device) != cudaSuccess) return gset_err(g, FN3_ECUDA, "cudaSetDevice failed");
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return gset_err(g, FN3_ECUDA, "cudaSetDevice failed");
     HdrTable ht;
     if ((rc = virtual_rows(e, hdrs.data(), n_rows, &ht))) return gfrom(g, 0, rc);
     return gfrom(g, 0, msa_align_core(e, ht, n_rows, sites, n_sites, codes, counts));

@@ -648,6 +648,33 @@ __global__ void __launch_bounds__(256) k_rehead(const HdrTable ht, long long n_r
         *reinterpret_cast<uint16_t*>(fpb + ((uint32_t)lane >> 3) * 512 + ((uint32_t)lane & 7u) * 2) = (uint16_t)fp_pad;
 }
 
+// ------------------------------------------------------------------------------------------------
+// device-side compaction (fn3_compact): live rows are copied into fresh chunks, heads rebuilt
+// ------------------------------------------------------------------------------------------------
+struct RowCopy { unsigned long long src, dst; uint32_t words; uint32_t pad; };     // words: multiple of 4
+
+__global__ void __launch_bounds__(256) k_copy_rows(const RowCopy* __restrict__ list, long long n) {
+    const int lane = threadIdx.x & 31;
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const RowCopy c = list[i];
+        const uint4* s = reinterpret_cast<const uint4*>(c.src);
+        uint4* d = reinterpret_cast<uint4*>(c.dst);
+        for (uint32_t k = lane; k < c.words / 4; k += 32) d[k] = __ldcs(s + k);
+    }
+}
+
+// headers of rows 0..n-1 into their tiles; every fingerprint starts as "pad" (valid rows: k_rehead fills them in) or as
+// the always-mismatching id (invalid rows)
+__global__ void k_place_hdrs(const RowHdr* __restrict__ hdrs, long long n, const HdrTable ht, uint32_t fp_dead, uint32_t fp_pad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RowHead h;
+    h.hdr = hdrs[i];
+    const uint16_t f = (uint16_t)(h.hdr.data ? fp_pad : fp_dead);
+    for (int k = 0; k < FN3_HEAD_FP; ++k) h.fp[k] = f;
+    put_head(ht, i, h);
+}
+
 // L2 flush helper for the measurement hook
 __global__ void k_fill(uint4* p, long long n, uint32_t v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

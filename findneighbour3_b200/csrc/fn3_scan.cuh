@@ -201,7 +201,11 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
         nxt0 = make_uint4(0, 0, 0, 0); nxt1 = nxt0; nxt_row = -1;
         nxt_ok = su < (unsigned long long)sub_total;
         if (!nxt_ok) return;
-        const uint32_t uu = ufirst + (uint32_t)(su >> ss), part = (uint32_t)su & ((1u << ss) - 1u);
+        // sub-unit -> (tile, part of the tile) with the TILE in the low digits: a CTA's sub-units b, b + grid, b + 2 grid, ...
+        // then cover all parts of the tiles evenly (with the part in the low bits and a grid that is a multiple of four,
+        // CTA b would always draw part b & 3 — and the rows of a half-filled last superblock all sit in part 0)
+        const uint32_t n_units = units - ufirst;
+        const uint32_t uu = ufirst + (uint32_t)(su % n_units), part = (uint32_t)(su / n_units);
         if (((uint32_t)lane >> (5 - ss)) != part) return;  // this lane's row belongs to another sub-unit of the tile
         const unsigned char* tile;
         int tl = lane, row = -1;

@@ -170,6 +170,18 @@ class Engine:
         group refreshes each member automatically)"""
         self._check(self._lib.fn3_refresh_heads(self._hl, int(min_ppm)))
 
+    def compact(self):
+        """reclaim tombstoned rows on the device (fn3_compact) -> int64 array: new row of every old row, -1 = was removed.
+        Single engine only (a group keeps global row g on device g % G: its shards cannot be renumbered independently)."""
+        if self.n_devices != 1:
+            raise NotImplementedError("device-side compaction is per engine")
+        n = int(self.stats()["n_rows"])
+        m = np.empty(max(n, 1), dtype=np.int64)
+        nb, na = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.fn3_compact(self._hl, _ptr(m), m.size, C.byref(nb), C.byref(na)))
+        self._n_rows = int(na.value)
+        return m[: nb.value]
+
     def row_get(self, row):
         """-> (pos int32[], off int32[7], invalid bool) of a stored row."""
         off = np.zeros(7, dtype=np.int32)

@@ -353,15 +353,21 @@ class seqComparer():
 
     def compact_store(self):
         """Rebuild the device store without the rows remove() and re-persist have tombstoned (they keep their words in
-        HBM: rows are never reused, include/fn3.h).  Maintenance call for a long-running server: every live row is read
-        back (fn3_row_get), bulk-appended to a fresh engine in the old row order, and the guid<->row maps are switched
-        over under the lock.  Returns (rows before, rows after)."""
+        HBM and their slot in the head tiles: rows are never reused, include/fn3.h).  Maintenance call for a long-running
+        server.  One engine: fn3_compact does it ON THE DEVICE (live rows copied to fresh chunks, heads rebuilt, rows
+        renumbered) and only the guid<->row maps change here.  An engine group (or a stand-in engine without compact()):
+        every live row is read back and bulk-appended to a fresh engine.  Returns (rows before, rows after)."""
         with self._lock:
             old = self.engine
             live = sorted(self._guid_of.keys())
             before = int(old.stats()["n_rows"])
             if len(live) == before:
                 return before, before
+            if getattr(old, "n_devices", 0) == 1 and hasattr(old, "compact"):
+                new_row = old.compact()
+                self._row_of = {g: int(new_row[r]) for g, r in self._row_of.items()}
+                self._guid_of = {row: guid for guid, row in self._row_of.items()}
+                return before, len(live)
             packed = [old.row_get(r) for r in live]
             n = len(packed)
             off = np.zeros(6 * n + 1, dtype=np.int64)

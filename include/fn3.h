@@ -123,6 +123,12 @@ int fn3_remove(fn3_engine* e, int64_t row);
 
 int fn3_stats_get(fn3_engine* e, fn3_stats* out);
 
+/* Reclaim the tombstones remove() leaves behind (its words stay in HBM, its head slot is still scanned): rebuild the store
+ * ON THE DEVICE — live rows copied into fresh chunks in row order, renumbered densely, heads rebuilt from the row data; no
+ * row travels through the host.  new_row[r] (r < *n_before, cap >= the current row count) receives the new number of old
+ * row r, or -1 if it was removed; the caller re-keys its guid <-> row maps.  Needs room for a second copy of the live rows. */
+int fn3_compact(fn3_engine* e, int64_t* new_row, int64_t cap, int64_t* n_before, int64_t* n_after);
+
 /* Rebuild the row heads the low-ceiling filter reads.  A head carries 32 of a row's variant positions; which 32 is free (any
  * variant position of the candidate in a block the query does not touch is a certain mismatch) but decides the filter's
  * power: isolates of one lineage share most of their low-coordinate variants, so the engine keeps a bitmap of BACKGROUND

@@ -194,7 +194,9 @@ struct DeviceGuard {
         ok = prev == d || cudaSetDevice(d) == cudaSuccess;
     }
     ~DeviceGuard() {
-        if (prev >= 0 && prev != dev && primary_ctx_active(prev)) (void)cudaSetDevice(prev);
+        int cur = -1;
+        if (prev < 0 || cudaGetDevice(&cur) != cudaSuccess || cur == prev) return;
+        if (primary_ctx_active(prev)) (void)cudaSetDevice(prev);
     }
 };
 #define FN3_ON_DEVICE(e) DeviceGuard _dg((e)->device); \

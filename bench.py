@@ -776,8 +776,8 @@ def main():
                 have = target.stats()["n_rows"]
                 want_total = per * world
                 fam_at = 0
-                while have < want_total:                 # top the store up, 25 000 samples (500 families) at a time
-                    n_f = min(500, (want_total - have + 49) // 50)
+                while have < want_total:                 # top the store up, 125 000 samples (2 500 families) at a time
+                    n_f = min(2500, (want_total - have + 49) // 50)
                     extra = synth.make_families([5_000_000 + fam_at + a for a in range(n_f)], 50, workers=cpus)
                     fam_at += n_f
                     target.append_bulk(extra.pos, extra.off, extra.invalid)

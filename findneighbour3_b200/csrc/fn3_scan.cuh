@@ -73,7 +73,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // sm[0..n) = row words [off, off+n).  Adds to the row's tally; sets t.dead once S1 exceeds the ceiling.
 __device__ __forceinline__ void scan_chunk(const QView& qv, const uint32_t* __restrict__ sm, uint32_t off, uint32_t n,
                                            uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t e4, int k,
-                                           int pos_bits, uint32_t pmask, int lane, Tally& t) {
+                                           int pos_bits, uint32_t pmask, int lane, Tally& t, int& lane_S1) {
+    const bool early = k < 0x3fffffff;                           // warp-uniform: is there a ceiling a row could exceed?
     const uint32_t v_n = e3 > off ? min(e3 - off, n) : 0u;       // V words (A,C,G,T positions) in this chunk
     uint32_t tm = 0u;                                            // this lane's words whose block the query touches
     // 256 words per warp step: lane l takes words 4l..4l+3 of each half (two conflict-free 128-bit LDS)
@@ -110,8 +111,12 @@ __device__ __forceinline__ void scan_chunk(const QView& qv, const uint32_t* __re
         }
         tm |= t8 << sh;
         // untouched block: the query is reference there, the candidate is not — a certain mismatch
-        t.S1 += __reduce_add_sync(0xffffffffu, __popc(vm) - __popc(t8));
-        if (t.S1 > k) { t.dead = true; return; }
+        if (early) {
+            t.S1 += __reduce_add_sync(0xffffffffu, __popc(vm) - __popc(t8));
+            if (t.S1 > k) { t.dead = true; return; }
+        } else {
+            lane_S1 += __popc(vm) - __popc(t8);           // no ceiling to exceed: one reduction per row, at the end
+        }
     }
     if (__any_sync(0xffffffffu, tm != 0u)) {
         int m2 = 0;
@@ -125,8 +130,12 @@ __device__ __forceinline__ void scan_chunk(const QView& qv, const uint32_t* __re
                 t.qdefV += r >> 1;
             }
         } while (__any_sync(0xffffffffu, tm != 0u));
-        t.S1 += __reduce_add_sync(0xffffffffu, m2);
-        if (t.S1 > k) { t.dead = true; return; }
+        if (early) {
+            t.S1 += __reduce_add_sync(0xffffffffu, m2);
+            if (t.S1 > k) { t.dead = true; return; }
+        } else {
+            lane_S1 += m2;
+        }
     }
     // run words: [start, start+len) of N (row index below e4) or M
     for (uint32_t i = (e3 > off ? e3 - off : 0u) + lane; i < n; i += 32) {
@@ -341,18 +350,20 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
     // ---- consumer ------------------------------------------------------------------------------------------
     uint32_t c_slot = 0u, phases = 0u;
     Tally t; t.S1 = 0; t.qdefV = 0; t.qdefU = 0; t.nNc = 0; t.nNU = 0; t.nNM = 0; t.dead = false;
+    int lane_S1 = 0;                                       // per-lane share of S1 when no ceiling asks for it step by step
     while (outstanding) {
         __syncwarp();                                      // the issuing lane's meta stores are visible to the warp
         mbar_wait(my_bar + c_slot * 8, (phases >> c_slot) & 1u);
         phases ^= 1u << c_slot;
         const uint4* m = reinterpret_cast<const uint4*>(my_meta + c_slot * FN3_SCAN_META_WORDS);
         const uint4 h0 = m[0], h1 = m[1], mi = m[2];       // mi = {row, first word, words, last chunk}
-        if (mi.y == 0u) { t.S1 = 0; t.qdefV = 0; t.qdefU = 0; t.nNc = 0; t.nNU = 0; t.nNM = 0; t.dead = false; }
+        if (mi.y == 0u) { t.S1 = 0; t.qdefV = 0; t.qdefU = 0; t.nNc = 0; t.nNU = 0; t.nNM = 0; t.dead = false; lane_S1 = 0; }
         if (!t.dead) {
-            scan_chunk(qv, my_ring + c_slot * FN3_SCAN_CH, mi.y, mi.z, h0.z, h0.w, h1.x, h1.y, h1.z, k, pos_bits, pmask, lane, t);
+            scan_chunk(qv, my_ring + c_slot * FN3_SCAN_CH, mi.y, mi.z, h0.z, h0.w, h1.x, h1.y, h1.z, k, pos_bits, pmask, lane, t, lane_S1);
             if (t.dead) {
                 if (p_lane >= 0 && p_row == (int)mi.x) p_lane = -1;      // do not fetch the rest of a row that is out
             } else if (mi.w) {
+                if (k >= 0x3fffffff) t.S1 += __reduce_add_sync(0xffffffffu, lane_S1);
                 emit(t, (long long)(int)mi.x);
             }
         }

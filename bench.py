@@ -717,6 +717,11 @@ def main():
                 valid = np.flatnonzero(wc.invalid == 0)
                 wq = [synth.new_sample_like(wc, int(rng.choice(valid)), int(rng.integers(0, 4)), seed=500 + k) for k in range(48)]
                 rows_w = [we.append(p, o, inv) for (p, o, inv) in wq[:24]]
+                # the head filter's pass rate (heads refreshed on entry: the store holds >= 4 096 rows), then real queries: the
+                # engine settles on FILTER or STREAM for this collection, and the timed launches take that variant
+                tb0 = we.profile_queries(rows_w[4:], ceiling, flush_l2=False, count_bytes=True)
+                for r_ in rows_w[:4]:
+                    we.one_vs_all(r_, ceiling)
                 we.profile_queries(rows_w[:4], ceiling, flush_l2=True)
                 pr = we.profile_queries(rows_w[4:], ceiling, flush_l2=True)
                 tb = we.profile_queries(rows_w[4:], ceiling, flush_l2=False, count_bytes=True)
@@ -735,8 +740,10 @@ def main():
                         assert hits_to_dict(hits) == wo.neighbours(s, ceiling), "workload %s: parity" % name
                         checked += 1
                     wo.inserted(s)
-                n_w = we.stats()["n_rows"]
-                workloads[name] = {"samples": int(wc.n), "filter_pass_rate": float(tb["n_passed"].mean()) / max(n_w - 1, 1),
+                st_w = we.stats()
+                n_w = st_w["n_rows"]
+                workloads[name] = {"samples": int(wc.n), "filter_pass_rate": float(tb0["n_passed"].mean()) / max(n_w - 1, 1),
+                                   "head_refreshes": int(st_w["head_refreshes"]), "steered_to_k_scan": bool(st_w["scan_mode"]),
                                    "device_p50_ms": float(np.median(ms)), "device_p95_ms": float(pct(ms.tolist(), 0.95)),
                                    "e2e_p50_ms": 1e3 * statistics.median(lat[2:]), "e2e_p95_ms": 1e3 * pct(lat[2:], 0.95),
                                    "fullscan_ms": float(np.median(fs["ms_compare"])),

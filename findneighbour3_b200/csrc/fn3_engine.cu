@@ -2157,11 +2157,13 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     if (!e || !query_rows || n < 1) return set_err(e, FN3_EARG, "fn3_profile_queries: bad arguments");
     std::lock_guard<std::mutex> q(e->query_mu);
     FN3_ON_DEVICE(e);
+    int rc = maybe_refresh_heads(e);                 // as every query entry point does
+    if (rc) return rc;
     QueryJob job; job.ceiling = ceiling;
     snapshot_store(e, job);
+    job.adaptive = job.n_rows >= 1024;               // the variant a real full scan would take now (FILTER / STREAM steering)
     e->edges_ready = -1;
     e->count_dirty = true;
-    int rc = FN3_OK;
     if ((rc = ensure_out(e, std::max<long long>(job.n_rows, 1)))) return rc;
     if (flush_l2 && !e->d_flush) {
         e->flush_n = (256ll << 20) / 16;

@@ -2165,7 +2165,6 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     e->edges_ready = -1;
     e->count_dirty = true;
     if ((rc = ensure_out(e, std::max<long long>(job.n_rows, 1)))) return rc;
-    const bool flush_read = env_ll("FN3_FLUSH_READ", 0) != 0;
     if (flush_l2 && !e->d_flush) {
         e->flush_n = (256ll << 20) / 16;
         CU(e, cudaMalloc(&e->d_flush, (size_t)e->flush_n * 16));
@@ -2202,11 +2201,7 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
             QuerySlot& sl = e->h_slots[job.slot_base];
             sl.hdr = hdrs[(size_t)it]; sl.row = query_rows[it]; sl.skip_le = -1; sl.exclude = query_rows[it]; sl.pad = 0;
             e->slot_blocks[0] = blks[(size_t)it];
-            if (pass == 0 && flush_l2) {
-                if (flush_read) k_sweep<<<e->sm_count * 4, 512, 0, st>>>(e->d_flush, e->flush_n, reinterpret_cast<uint32_t*>(e->d_flush));
-                else k_fill<<<e->sm_count * 4, 512, 0, st>>>(e->d_flush, e->flush_n, (uint32_t)it);
-                e->launches += 1;
-            }
+            if (pass == 0 && flush_l2) { k_fill<<<e->sm_count * 4, 512, 0, st>>>(e->d_flush, e->flush_n, (uint32_t)it); e->launches += 1; }
             e->d_count = d_pc + (size_t)it * (FN3_OUT_HDR / sizeof(unsigned long long));
             job.count_bytes = pass == 1;
             job.split = pass == 0 ? evs[(size_t)it * 3 + 1] : nullptr;

@@ -731,17 +731,6 @@ __global__ void k_place_hdrs(const RowHdr* __restrict__ hdrs, long long n, const
     put_head(ht, i, h);
 }
 
-// L2 flush by READING a buffer larger than L2 (measurement hook, FN3_FLUSH=read): evicts the store's lines without leaving
-// the L2 full of dirty lines whose write-back then runs under the timed kernel
-__global__ void k_sweep(const uint4* __restrict__ p, long long n, uint32_t* sink) {
-    uint32_t acc = 0u;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const uint4 v = __ldcg(p + i);
-        acc ^= v.x ^ v.y ^ v.z ^ v.w;
-    }
-    if (acc == 0x9e3779b9u) *sink = acc;             // never true for the zero-filled buffer: keeps the loads alive
-}
-
 // L2 flush helper for the measurement hook
 __global__ void k_fill(uint4* p, long long n, uint32_t v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

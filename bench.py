@@ -95,7 +95,8 @@ def pct(a, q):
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed regions (NVML, every 2 ms, own thread)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
+        self.period = period
         self.samples, self.reasons = [], set()
         self.stop_flag = threading.Event()
         self.thread = self.h = self.max_mhz = None
@@ -129,7 +130,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self.h is not None:
@@ -446,6 +447,7 @@ def main():
     prof = eng.profile_queries(resident[W:], ceiling, flush_l2=True)          # EXACTLY K timed steps
     launches = eng.launch_count() - launches0 - K      # minus the untimed L2-flush launches
     barrier()
+    clocks = sampler.stop()                          # the timed region of `value` is over: every rank stops polling NVML
     step_ms = (prof["ms_build"] + prof["ms_compare"]).astype(np.float64)
     warm = eng.profile_queries(resident[W:], ceiling, flush_l2=False)
     touched = eng.profile_queries(resident[W:W + min(K, 50)], ceiling, flush_l2=False, count_bytes=True)
@@ -554,12 +556,18 @@ def main():
             want = check.neighbours(s, ceiling, below=below)
             assert got == want, "e2e parity: neighbours of a timed insert differ from the C oracle"
             checked += 1
-        return {"seconds": t, "lat": lat, "neighbours": n_nb, "comparisons": comps, "parity_checked": checked}
+        order = sorted(range(len(lat)), key=lambda i_: -lat[i_])[:3]
+        return {"seconds": t, "lat": lat, "neighbours": n_nb, "comparisons": comps, "parity_checked": checked,
+                "slowest": [[i_, 1e3 * lat[i_]] for i_ in order]}
 
     e2e = None
-    e2e_extra = {}
     grp = None
     ostore = None
+    # (NVML queries from eight processes at 500 Hz stalled the group's launches for milliseconds: during the end-to-end legs
+    #  only rank 0 samples, every 25 ms)
+    sampler2 = ClockSampler(local, period=0.025) if rank == 0 else None
+    if sampler2:
+        sampler2.start()
     if world == 1:
         ostore = OracleStore(oracle_threads)
         ostore.add(coll)
@@ -576,7 +584,7 @@ def main():
                "d2h_bytes_per_step": (st2["d2h_bytes"] - st1["d2h_bytes"]) / (n_e2e + W),
                "ms_per_step": 1e3 * r["seconds"] / n_e2e, "p50_ms": 1e3 * statistics.median(r["lat"]),
                "p95_ms": 1e3 * pct(r["lat"], 0.95), "neighbours_per_query": r["neighbours"] / n_e2e,
-               "parity_steps_checked": r["parity_checked"],
+               "parity_steps_checked": r["parity_checked"], "slowest_steps_ms": r["slowest"],
                "call": "fn3_insert_query via ctypes (server insert(): persist + mcompare, findNeighbour3-server.py:516+530)",
                "two_calls": {"ms_per_step": 1e3 * two["seconds"] / n_e2e, "p50_ms": 1e3 * statistics.median(two["lat"]),
                              "call": "fn3_append + fn3_one_vs_all (seqComparer.persist, then seqComparer.mcompare)"}}
@@ -603,7 +611,7 @@ def main():
                        "d2h_bytes_per_step": (st2["d2h_bytes"] - st1["d2h_bytes"]) / (n_e2e + W),
                        "ms_per_step": 1e3 * r["seconds"] / n_e2e, "p50_ms": 1e3 * statistics.median(r["lat"]),
                        "p95_ms": 1e3 * pct(r["lat"], 0.95), "neighbours_per_query": r["neighbours"] / n_e2e,
-                       "parity_steps_checked": r["parity_checked"], "candidates": int(st1["n_rows"]),
+                       "parity_steps_checked": r["parity_checked"], "slowest_steps_ms": r["slowest"], "candidates": int(st1["n_rows"]),
                        "peer_access": grp.peer_access,
                        "call": "fn3_group_insert_query via ctypes: ONE process (rank 0) drives all %d GPUs — one host thread per "
                                "device inside libfn3, the sample host->every device, neighbour records through each device's "
@@ -620,7 +628,9 @@ def main():
                 errors["e2e_group"] = repr(ex)
                 log("e2e group leg failed:", repr(ex))
         host_barrier()
-    clocks = sampler.stop()
+    if sampler2:
+        c2 = sampler2.stop()
+        clocks["e2e_region"] = {k: c2.get(k) for k in ("sm_mhz", "sm_mhz_min", "reasons", "samples")}
 
     # ================================================================================================
     # leg 3: latency through the drop-in class (rank 0)
@@ -805,6 +815,7 @@ def main():
                       "p50_ms": 1e3 * statistics.median(r["lat"]), "p95_ms": 1e3 * pct(r["lat"], 0.95),
                       "inserts_per_s": args.c4_inserts / r["seconds"], "comparisons_per_s": r["comparisons"] / r["seconds"],
                       "neighbours_per_query": r["neighbours"] / args.c4_inserts, "parity_rows_checked": r["parity_checked"],
+                      "slowest_steps_ms": r["slowest"],
                       "store_bytes_per_gpu": int(target.stats()["store_bytes"] // world), "setup_s": t_setup}
             except Exception as ex:   # pragma: no cover
                 errors["config4"] = repr(ex)

@@ -447,7 +447,6 @@ def main():
     prof = eng.profile_queries(resident[W:], ceiling, flush_l2=True)          # EXACTLY K timed steps
     launches = eng.launch_count() - launches0 - K      # minus the untimed L2-flush launches
     barrier()
-    clocks = sampler.stop()                          # the timed region of `value` is over: every rank stops polling NVML
     step_ms = (prof["ms_build"] + prof["ms_compare"]).astype(np.float64)
     warm = eng.profile_queries(resident[W:], ceiling, flush_l2=False)
     touched = eng.profile_queries(resident[W:W + min(K, 50)], ceiling, flush_l2=False, count_bytes=True)
@@ -565,6 +564,7 @@ def main():
     ostore = None
     # (NVML queries from eight processes at 500 Hz stalled the group's launches for milliseconds: during the end-to-end legs
     #  only rank 0 samples, every 25 ms)
+    clocks = sampler.stop()                          # the device-timed legs are over: every rank stops polling NVML at 500 Hz
     sampler2 = ClockSampler(local, period=0.025) if rank == 0 else None
     if sampler2:
         sampler2.start()

@@ -189,6 +189,24 @@ extern "C" int fn3_group_append_bulk(fn3_group* g, int64_t n, const int32_t* pos
     for (int64_t i = 0; i < 6 * n; ++i)
         if (off[i + 1] < off[i]) return gset_err(g, FN3_EARG, "list offsets must be non-decreasing");
     const int G = g->G;
+    // validate EVERYTHING before anything is stored: a sample that only one shard would reject must not leave the other
+    // shards appended and the group out of step (the per-engine call validates its own share again; that is the cheap part)
+    {
+        fn3_engine* e0 = g->eng[0];
+        std::atomic<int> bad{0};
+        const int host_threads = (int)std::max<long long>(1, std::min<long long>(env_ll("FN3_HOST_THREADS", 16),
+                                                                                 (long long)std::thread::hardware_concurrency()));
+        parallel_rows(n, host_threads, [&](long long lo, long long hi) {
+            for (long long i = lo; i < hi && !bad.load(std::memory_order_relaxed); ++i) {
+                if (invalid && invalid[i]) continue;
+                long long o[7];
+                for (int b = 0; b < 7; ++b) o[b] = off[6 * i + b];
+                if (row_words_needed(e0, pos, o, 0) < 0) { bad.store(1); return; }
+                if (!raw_disjoint(pos, o)) { set_err(e0, FN3_EARG, "the six lists of a sample must be mutually disjoint"); bad.store(1); return; }
+            }
+        });
+        if (bad.load()) return gfrom(g, 0, FN3_EARG);
+    }
     std::vector<int64_t> got((size_t)G, -1);
     const int rc = group_run(g, [&](int d) -> int {
         // samples i with (first + i) % G == d, in order
@@ -212,8 +230,7 @@ extern "C" int fn3_group_append_bulk(fn3_group* g, int64_t n, const int32_t* pos
         }
         return fn3_append_bulk(g->eng[(size_t)d], cnt, p.data(), o.data(), invalid ? inv.data() : nullptr, &got[(size_t)d]);
     });
-    if (rc) return rc;                     // (a bad sample fails the whole call; shards that were valid may have been appended:
-                                           //  the group is then out of step and says so on the next call)
+    if (rc) return rc;                     // (only an allocation / CUDA failure can get here: the samples were validated above)
     for (int d = 0; d < G; ++d) {
         const long long i0 = ((d - first) % G + G) % G;
         if (i0 < n && got[(size_t)d] != (first + i0) / G)

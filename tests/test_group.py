@@ -159,3 +159,36 @@ def test_class_insert_sequence_on_a_group():
         want = {r[1]: tuple(r[2:6]) for r in port.mcompare(store, {}, s, 20) if r[2] is not None}
         assert found == want, (s, found, want)
         assert int(hist[ord("A")]) == s.count("A")
+
+
+def test_group_rejects_a_bad_sample_before_anything_is_stored():
+    """a bulk append with ONE malformed sample (out of range, unsorted, overlapping lists) fails as a whole — no shard keeps
+    its share — and the group stays in step: the next append and every query work, rows are numbered as if nothing happened"""
+    from findneighbour3_b200.engine import GroupEngine
+    from oracle import c_oracle
+    coll = _synthetic(4, 12, 100000, 3, k1=100, s=2.0, n_blocks=4, n_mean=500, m_mean=2, rule="any")
+    eng = GroupEngine(coll.genome_length, _devices())
+    first = coll.subset(np.arange(20))
+    assert eng.append_bulk(first.pos, first.off, first.invalid) == 0
+    rest = coll.subset(np.arange(20, coll.n))
+    for kind in ("range", "order", "overlap"):
+        pos = rest.pos.copy()
+        i = 11                                                    # a sample whose shard is not the first one
+        o = rest.off[6 * i: 6 * i + 7]
+        assert o[1] - o[0] >= 2
+        if kind == "range":
+            pos[o[0]] = coll.genome_length + 5
+        elif kind == "order":
+            pos[o[0]], pos[o[0] + 1] = pos[o[0] + 1], pos[o[0]]
+        else:
+            pos[o[4]] = pos[o[0]] if o[5] > o[4] else pos[o[0]]
+            if o[5] == o[4]:
+                continue
+        with pytest.raises(ValueError):
+            eng.append_bulk(pos, rest.off, rest.invalid)
+        assert eng.stats()["n_rows"] == 20
+    assert eng.append_bulk(rest.pos, rest.off, rest.invalid) == 20
+    for q in (0, 5, 21, coll.n - 1):
+        want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, q, 20)
+        assert hits_to_dict(eng.one_vs_all(q, 20)) == want
+    eng.close()

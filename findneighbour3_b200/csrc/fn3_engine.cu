@@ -1017,13 +1017,18 @@ static int enqueue_query(fn3_engine* e, QueryJob& job) {
         p.ring_off = (unsigned int)(in_smem ? q_smem : 0);
         ctas = std::min<long long>(std::max<long long>(1, ((units << ss) + warps_per_cta - 1) / warps_per_cta), cta_cap);
     }
+    size_t smem_launch = smem;
+    if (e->debug_stop == 3) {                        // launch-floor experiments (the kernel returns at entry): grid / smem overrides
+        ctas = env_ll("FN3_DBG_CTAS", ctas);
+        smem_launch = (size_t)env_ll("FN3_DBG_SMEM", (long long)smem);
+    }
     dim3 g((unsigned)ctas, (unsigned)ns);
     if (in_smem) {
-        if (job.count_bytes) launch_query<true, 1>(filter, g, smem, st, p);
-        else launch_query<false, 1>(filter, g, smem, st, p);
+        if (job.count_bytes) launch_query<true, 1>(filter, g, smem_launch, st, p);
+        else launch_query<false, 1>(filter, g, smem_launch, st, p);
     } else {
-        if (job.count_bytes) launch_query<true, 0>(filter, g, smem, st, p);
-        else launch_query<false, 0>(filter, g, smem, st, p);
+        if (job.count_bytes) launch_query<true, 0>(filter, g, smem_launch, st, p);
+        else launch_query<false, 0>(filter, g, smem_launch, st, p);
     }
     e->launches += 1;
     CU(e, cudaGetLastError());

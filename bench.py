@@ -429,7 +429,7 @@ def main():
     eng.append_bulk(coll.pos, coll.off, coll.invalid)       # server start-up reload path: validate, pack, copy, place heads
     t_bulk = time.perf_counter() - t_bulk
     n_e2e = max(K, 200)                              # the latency legs use at least 200 steps, whatever K is
-    queries = make_queries(common, (K + W) + 2 * (n_e2e + W) + 64)      # the same new samples on every rank
+    queries = make_queries(common, (K + W) + 2 * (n_e2e + max(W, 2 * world)) + 64)      # the same new samples on every rank
     t_gen = time.time() - t_gen
 
     resident = [eng.append(p, o, inv) for (p, o, inv) in queries[:K + W]]
@@ -527,14 +527,18 @@ def main():
     fresh = queries[K + W:]
     oracle_threads = cpus
 
-    def timed_inserts(insert, samples, n_rows_now, check=None, check_every=0):
-        """W untimed + len-W timed calls of insert(sample) -> hits; optional parity check of a sample of the steps"""
+    WG = max(W, 2 * world)                           # group legs: every device has had its turn as the owner before the clock starts
+
+    def timed_inserts(insert, samples, n_rows_now, check=None, check_every=0, warm=None):
+        """`warm` untimed + the remaining timed calls of insert(sample) -> hits; optional parity check of a sample of the steps"""
+        warm = W if warm is None else warm
         lat, n_nb, comps, checked = [], 0, 0, 0
-        for s in samples[:W]:
+        for s in samples[:warm]:
             hits = insert(s)
             if check:
                 check.inserted(s)
-        timed = samples[W:]
+        n_rows_now += warm
+        timed = samples[warm:]
         pending = []
         gc.collect()
         gc.disable()                                 # a generation-2 pass over this process's big host-side collections
@@ -603,15 +607,16 @@ def main():
                 log("group of", world, "devices loaded with", grp.stats()["n_rows"], "rows in %.1f s" % (time.time() - t0),
                     "peer access:", grp.peer_access)
                 st1 = grp.stats()
-                r = timed_inserts(lambda s: grp.insert_query(s[0], s[1], s[2], ceiling)[1], fresh[:W + n_e2e], st1["n_rows"],
-                                  ostore, max(1, n_e2e // 8))
+                r = timed_inserts(lambda s: grp.insert_query(s[0], s[1], s[2], ceiling)[1], fresh[:WG + n_e2e], st1["n_rows"],
+                                  ostore, max(1, n_e2e // 8), warm=WG)
                 st2 = grp.stats()
                 e2e = {"value": r["comparisons"] / r["seconds"], "unit": UNIT, "steps": n_e2e,
-                       "h2d_bytes_per_step": (st2["h2d_bytes"] - st1["h2d_bytes"]) / (n_e2e + W),
-                       "d2h_bytes_per_step": (st2["d2h_bytes"] - st1["d2h_bytes"]) / (n_e2e + W),
+                       "h2d_bytes_per_step": (st2["h2d_bytes"] - st1["h2d_bytes"]) / (n_e2e + WG),
+                       "d2h_bytes_per_step": (st2["d2h_bytes"] - st1["d2h_bytes"]) / (n_e2e + WG),
                        "ms_per_step": 1e3 * r["seconds"] / n_e2e, "p50_ms": 1e3 * statistics.median(r["lat"]),
                        "p95_ms": 1e3 * pct(r["lat"], 0.95), "neighbours_per_query": r["neighbours"] / n_e2e,
                        "parity_steps_checked": r["parity_checked"], "slowest_steps_ms": r["slowest"], "candidates": int(st1["n_rows"]),
+                       "warmup_steps": WG,
                        "peer_access": grp.peer_access,
                        "call": "fn3_group_insert_query via ctypes: ONE process (rank 0) drives all %d GPUs — one host thread per "
                                "device inside libfn3, the sample host->every device, neighbour records through each device's "
@@ -805,10 +810,10 @@ def main():
                     ostore.add(extra)
                     have += extra.n
                 t_setup = time.time() - t0
-                c4q = make_queries(common, args.c4_inserts + W, seed=777)
+                c4q = make_queries(common, args.c4_inserts + WG, seed=777)
                 st1 = target.stats()
                 r = timed_inserts(lambda s: target.insert_query(s[0], s[1], s[2], ceiling)[1], c4q, st1["n_rows"], ostore,
-                                  max(1, args.c4_inserts // 6))
+                                  max(1, args.c4_inserts // 6), warm=WG)
                 c4 = {"workload": "configs[4]: %d samples resident across %d GPU(s), %d streamed inserts each queried one-vs-all at "
                                   "snpCeiling %d" % (st1["n_rows"], world, args.c4_inserts, ceiling),
                       "samples": int(st1["n_rows"]), "samples_per_gpu": per, "inserts": args.c4_inserts,

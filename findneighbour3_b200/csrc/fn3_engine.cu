@@ -393,6 +393,10 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
     e->zero_copy = env_ll("FN3_ZERO_COPY", 1) != 0 && e->debug_stop == 0;
     if ((s = cudaHostAlloc(&e->zc_buf, 64 + (size_t)FN3_ZC_CAP * sizeof(EdgeRec), cudaHostAllocMapped)) != cudaSuccess) return fail("cudaHostAlloc(mapped)", s);
     memset(e->zc_buf, 0, 64);
+    // the insert path's pinned staging row: allocated now, not by the first insert this engine owns (a few ms of cudaHostAlloc
+    // showed up as the three slowest steps of an eight-GPU group: each device's first turn as the owner)
+    e->istage_words = 1u << 16;
+    if ((s = cudaHostAlloc(&e->istage, e->istage_words * 4, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc(istage)", s);
     if ((s = cudaMalloc(&e->d_done, sizeof(unsigned int))) != cudaSuccess) return fail("cudaMalloc(done)", s);
     if ((s = cudaMemset(e->d_done, 0, sizeof(unsigned int))) != cudaSuccess) return fail("cudaMemset(done)", s);
     if ((s = cudaMalloc(&e->d_scratch_tile, FN3_TILE_BYTES)) != cudaSuccess) return fail("cudaMalloc(scratch tile)", s);

@@ -76,6 +76,40 @@ __device__ __forceinline__ void block_exscan3(uint32_t& a, uint32_t& b, uint32_t
     a = ws[warp] + ia - a; b = ws[33 + warp] + ib - b; c = ws[66 + warp] + ic - c;
 }
 
+// One-barrier variants for the query build (called once each, on disjoint scratch: no guard barrier in front, and no third
+// barrier behind — every warp sums the warp totals in front of it itself, two REDUX).  ws: 32 words per scanned value.
+#define FN3_WS_WORDS 128
+__device__ __forceinline__ uint32_t block_exscan_1b(uint32_t v, uint32_t* ws, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    const uint32_t w = lane < nwarp ? ws[lane] : 0u;
+    *total = __reduce_add_sync(0xffffffffu, w);
+    return __reduce_add_sync(0xffffffffu, lane < warp ? w : 0u) + inc - v;
+}
+
+__device__ __forceinline__ void block_exscan3_1b(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t* ws,
+                                                 uint32_t& ta, uint32_t& tb, uint32_t& tc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t ia = a, ib = b, ic = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t x = __shfl_up_sync(0xffffffffu, ia, o), y = __shfl_up_sync(0xffffffffu, ib, o), z = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) { ia += x; ib += y; ic += z; }
+    }
+    if (lane == 31) { ws[warp] = ia; ws[32 + warp] = ib; ws[64 + warp] = ic; }
+    __syncthreads();
+    const uint32_t wa = lane < nwarp ? ws[lane] : 0u, wb = lane < nwarp ? ws[32 + lane] : 0u, wc = lane < nwarp ? ws[64 + lane] : 0u;
+    ta = __reduce_add_sync(0xffffffffu, wa); tb = __reduce_add_sync(0xffffffffu, wb); tc = __reduce_add_sync(0xffffffffu, wc);
+    const bool before = lane < warp;
+    a = __reduce_add_sync(0xffffffffu, before ? wa : 0u) + ia - a;
+    b = __reduce_add_sync(0xffffffffu, before ? wb : 0u) + ib - b;
+    c = __reduce_add_sync(0xffffffffu, before ? wc : 0u) + ic - c;
+}
+
 // address of the tile holding `row`, and the row's lane in it
 __device__ __forceinline__ const unsigned char* tile_of(const HdrTable& ht, long long row, int& lane) {
     const long long local = row & ((1ll << ht.shift) - 1);
@@ -115,7 +149,7 @@ __global__ void k_scatter_heads(const RowHead* __restrict__ src, long long first
 template <bool GLOBAL> __device__ __forceinline__ uint32_t ldq(const uint32_t* p) { return GLOBAL ? __ldcg(p) : *p; }
 
 // All threads of the CTA must call.  bm: 2*nw words (bitmap, then prefix); coarse: ncw words; en: (touched+1)
-// entries; ws: 99 words.
+// entries; ws: FN3_WS_WORDS words.
 // tot[0..2] = |V_q|, |U_q|, |M_q|; returns the number of touched blocks.
 template <bool GLOBAL>
 __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int ncw, int fshift, int pos_bits,
@@ -159,7 +193,7 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
     uint32_t local = 0;
     for (int w = lo; w < hi; ++w) local += __popc(ldq<GLOBAL>(&bm[w]));
     uint32_t nE;
-    uint32_t run = block_exscan(local, ws, &nE);
+    uint32_t run = block_exscan_1b(local, ws, &nE);
     for (int w = lo; w < hi; ++w) { const uint32_t b = ldq<GLOBAL>(&bm[w]); pref[w] = run; run += __popc(b); }
     {
         uint4* z = reinterpret_cast<uint4*>(en);                 // 3. clear entries incl. the sentinel
@@ -200,7 +234,7 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
         sD += __popc(ldq<GLOBAL>(&en[i].mDef)); sU += __popc(ldq<GLOBAL>(&en[i].mU)); sM += __popc(ldq<GLOBAL>(&en[i].mM));
     }
     uint32_t tD, tU, tM;
-    block_exscan3(sD, sU, sM, ws, tD, tU, tM);
+    block_exscan3_1b(sD, sU, sM, ws + 32, tD, tU, tM);
     for (uint32_t i = elo; i < ehi; ++i) {
         const uint32_t a = __popc(ldq<GLOBAL>(&en[i].mDef)), b = __popc(ldq<GLOBAL>(&en[i].mU)), c = __popc(ldq<GLOBAL>(&en[i].mM));
         en[i].cDef = sD; en[i].cU = sU; en[i].cM = sM;
@@ -216,7 +250,7 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
 
 __global__ void __launch_bounds__(FN3_Q_THREADS) k_build_query(const QuerySlot* __restrict__ slots, const QueryState qs,
                                                                int nw, int ncw, int fshift, int pos_bits) {
-    __shared__ uint32_t ws[99];
+    __shared__ uint32_t ws[FN3_WS_WORDS];
     const int slot = blockIdx.x;
     const QuerySlot q = slots[slot];
     uint32_t tot[3];
@@ -418,7 +452,7 @@ __device__ __forceinline__ void signal_done(const CompareParams& p) {
 template <bool COUNT, int QMODE>
 __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const CompareParams p) {
     extern __shared__ __align__(128) uint4 qsm[];
-    __shared__ uint32_t ws[99];
+    __shared__ uint32_t ws[FN3_WS_WORDS];
     // survivors of the head filter, per CTA: phase A queues them, then ALL warps of the CTA draw from the queue — a warp
     // whose 32 candidates hold two relatives of the query no longer streams them one after the other while fifteen warps
     // idle (measured: the step went from 16.8 to 20.8 us once 400 appended relatives made such collisions common)

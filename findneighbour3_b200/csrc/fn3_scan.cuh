@@ -156,7 +156,7 @@ __device__ __forceinline__ void scan_chunk(const QView& qv, const uint32_t* __re
 template <bool COUNT, int QMODE>
 __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParams p) {
     extern __shared__ __align__(128) uint4 qsm[];
-    __shared__ uint32_t ws[99];
+    __shared__ uint32_t ws[FN3_WS_WORDS];
     __shared__ unsigned int next_unit;
     if (p.debug_stop == 3) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

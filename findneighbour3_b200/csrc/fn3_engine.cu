@@ -950,6 +950,7 @@ struct QueryJob {                    // what enqueue_query needs beyond the engi
     bool zero_copy = false;              // results + completion through mapped host memory (one-vs-all paths)
     bool adaptive = false;               // a full one-vs-all scan: may be steered from FILTER to STREAM (prefer_scan)
     bool used_filter = false;            // out: which variant enqueue_query chose
+    bool split_recorded = false;         // out: a build kernel ran and `split` was recorded behind it
 };
 
 // enqueue one query tile on q_stream.  Normally ONE kernel (k_query builds the query structure in shared memory
@@ -983,8 +984,10 @@ static int enqueue_query(fn3_engine* e, QueryJob& job) {
         k_build_query<<<ns, FN3_Q_THREADS, 0, st>>>(d_sl, e->qstate, e->nw, e->ncw, e->fshift, e->pos_bits);
         e->launches += 1;
         CU(e, cudaGetLastError());
+        // (the split event only where there IS a build kernel: an event record between the step's first event and the compare
+        //  kernel costs 2.7 us of stream time by itself — it used to be counted into every step)
+        if (job.split) { CU(e, cudaEventRecord(job.split, st)); job.split_recorded = true; }
     }
-    if (job.split) CU(e, cudaEventRecord(job.split, st));
     CompareParams p;
     memset(&p, 0, sizeof p);
     p.hdr = job.ht; p.qs = e->qstate; p.rows = job.d_rows; p.n_list = job.n_list; p.n_rows = job.n_rows;
@@ -2181,6 +2184,7 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     }
     cudaStream_t st = e->q_stream;
     std::vector<cudaEvent_t> evs((size_t)n * 3, nullptr);
+    std::vector<uint8_t> has_split((size_t)n, 0);
     for (auto& ev : evs) CU(e, cudaEventCreate(&ev));
     unsigned long long* d_pc = nullptr;                       // per-step counters: [hits, touched, -, -]
     CU(e, cudaMalloc(&d_pc, (size_t)n * FN3_OUT_HDR));
@@ -2215,8 +2219,9 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
             job.count_bytes = pass == 1;
             job.split = pass == 0 ? evs[(size_t)it * 3 + 1] : nullptr;
             if (pass == 0) cudaEventRecord(evs[(size_t)it * 3 + 0], st);
+            job.split_recorded = false;
             rc = enqueue_query(e, job);
-            if (pass == 0) cudaEventRecord(evs[(size_t)it * 3 + 2], st);
+            if (pass == 0) { cudaEventRecord(evs[(size_t)it * 3 + 2], st); has_split[(size_t)it] = job.split_recorded ? 1 : 0; }
         }
         e->d_count = saved;
     }
@@ -2224,8 +2229,12 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     if (rc == FN3_OK && sync == cudaSuccess) {
         for (int it = 0; it < n; ++it) {
             float a = 0, b = 0;
-            cudaEventElapsedTime(&a, evs[(size_t)it * 3 + 0], evs[(size_t)it * 3 + 1]);
-            cudaEventElapsedTime(&b, evs[(size_t)it * 3 + 1], evs[(size_t)it * 3 + 2]);
+            if (has_split[(size_t)it]) {
+                cudaEventElapsedTime(&a, evs[(size_t)it * 3 + 0], evs[(size_t)it * 3 + 1]);
+                cudaEventElapsedTime(&b, evs[(size_t)it * 3 + 1], evs[(size_t)it * 3 + 2]);
+            } else {
+                cudaEventElapsedTime(&b, evs[(size_t)it * 3 + 0], evs[(size_t)it * 3 + 2]);      // no build kernel: one interval
+            }
             if (ms_build) ms_build[it] = a;
             if (ms_compare) ms_compare[it] = b;
         }

@@ -340,8 +340,9 @@ int fn3_group_msa_align(fn3_group* g, const int64_t* rows, int64_t n_rows, const
 
 /* Run the one-vs-all DEVICE work (query-map build + compare kernel, inputs already resident in HBM) once
  * for each of the n stored rows in query_rows, queued back to back on the engine's stream with no host
- * synchronisation in between.  ms_build[i] / ms_compare[i] receive the CUDA-event times of step i's
- * query-map build (memset + scatter + rank) and of its compare kernel; n_hits[i] its survivor count;
+ * synchronisation in between.  ms_compare[i] receives the CUDA-event time of step i's compare kernel (the query
+ * structure is built inside it); ms_build[i] that of the separate build kernel a query too large for shared memory needs
+ * (0 otherwise: no event is recorded between the step's first event and the kernel); n_hits[i] its survivor count;
  * bytes_touched[i] (may be NULL) the bytes of headers + row data the compare kernel of step i actually
  * loaded, counted by a separate instrumented pass that is NOT timed; n_passed[i] (may be NULL; filled with
  * bytes_touched) the candidates the head filter could not rule out (0 for ceilings that do not use it).  flush_l2 != 0

@@ -1,18 +1,18 @@
 """seqComparer.compact_store(): the device store rebuilt without tombstones answers every query as before.
-(CPU: oracle-backed stand-in engine; -m gpu: the CUDA engine.  Sorted last on purpose: it is the only GPU test of this
-round that could not be run on a B200 before the round closed — it uses fn3_row_get / fn3_append_bulk only.)"""
+(CPU: oracle-backed stand-in engine; -m gpu: the CUDA engine: device-side fn3_compact for one engine, the host-side rebuild
+for an engine group.)"""
 import numpy as np
 import pytest
 
 
-def _check():
+def _check(device=None):
     from findneighbour3_b200 import synth
     from findneighbour3_b200.seqComparer import seqComparer
     L = 40000
     coll = synth.make_collection(4, 10, genome_length=L, seed=5, k1=60, s=2.0, n_blocks=3, n_mean=200, m_mean=3, rule="any",
                                  p_invalid=0.08)
     ref = synth.reference_string(synth.random_reference(L, 962))
-    sc = seqComparer(reference=ref, maxNs=1e8, snpCeiling=20)
+    sc = seqComparer(reference=ref, maxNs=1e8, snpCeiling=20, device=device)
     for i in range(coll.n):
         sc.persist(coll.as_dict(i), "g%d" % i)
     for i in range(0, coll.n, 3):
@@ -43,5 +43,7 @@ def test_compact_store_host_layer(monkeypatch):
 
 
 @pytest.mark.gpu
-def test_compact_store_on_the_device():
-    _check()
+@pytest.mark.parametrize("device", [0, [0, 0, 0]])
+def test_compact_store_on_the_device(device):
+    """one engine: fn3_compact (rows copied and heads rebuilt on the device); a group: the rebuild through the host"""
+    _check(device)

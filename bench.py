@@ -270,37 +270,83 @@ def cpu_c_oracle(coll, queries, ceiling, budget_s, threads):
                       % (nq, coll.n, threads, t_used)}
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path, timed on this host.
-    The reference is pure Python and cannot travel to the GPU box, so its restatement (oracle port) runs."""
-    if rank != 0:
-        return
-    workers = os.cpu_count() or 1
-    common = make_common(workers)
-    coll = make_shard(min(args.samples, 5000), 0, common, workers)
-    queries = make_queries(common, max(args.steps + args.warmup, 4))
-    budget = max(5.0, min(90.0, args.cpu_seconds * 3))
+def _reference_worker(conn, coll, lo, hi, ceiling):
+    """one host process of the reference arm: the Python-set algorithm over candidates [lo, hi) of the shard"""
     from oracle import seqcomparer_port as port
     from findneighbour3_b200 import packing
-    m = min(coll.n, 1500)
-    store = {i: coll.as_dict(i) for i in range(coll.n - m, coll.n)}     # includes the queries' own families
-    for (p, o, inv) in queries[:min(args.warmup, 1)]:
+    store = {i: coll.as_dict(i) for i in range(lo, hi)}
+    conn.send(len(store))
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            return
+        p, o, inv = msg
         store["q"] = {"invalid": 1} if inv else packing.unpack_lists(p, o, None)
-        port.mcompare(store, {}, "q", args.ceiling)
-    t_used, steps = 0.0, 0
-    for (p, o, inv) in queries[args.warmup:args.warmup + args.steps]:
-        store["q"] = {"invalid": 1} if inv else packing.unpack_lists(p, o, None)
+        conn.send(len(port.mcompare(store, {}, "q", ceiling)))
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, timed on this host.
+    The reference is pure Python and cannot travel to the GPU box, so its restatement (oracle port) runs.  The class the
+    server imports is single-threaded and seqComparer_mt's threads share one GIL (src/seqComparer_mt.py:363-385), so to give
+    the algorithm every host core the candidates of a step are split over one PROCESS per core, each holding its slice of
+    the store as the reference holds it (dicts of Python sets)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = os.cpu_count() or 1
+    per = 1500                                                  # candidates per process and step: ~0.5-0.7 s of set algebra
+    try:
+        import psutil
+        procs = max(1, min(workers, int(0.25 * psutil.virtual_memory().available / (per * 0.35e6))))
+    except Exception:       # pragma: no cover
+        procs = workers
+    common = make_common(workers)
+    m = min(int(args.samples), per * procs)
+    procs = max(1, min(procs, m // 200))
+    coll = make_shard(m, 0, common, workers)
+    m = coll.n
+    queries = make_queries(common, max(args.steps + args.warmup, 4))
+    budget = max(5.0, min(90.0, args.cpu_seconds * 3))
+    ctx = mp.get_context("fork")                                # the shard is inherited, not pickled; no CUDA in this arm
+    bounds = [m * i // procs for i in range(procs + 1)]
+    conns, kids = [], []
+    for i in range(procs):
+        a, b = ctx.Pipe()
+        k = ctx.Process(target=_reference_worker, args=(b, coll, bounds[i], bounds[i + 1], args.ceiling), daemon=True)
+        k.start()
+        conns.append(a)
+        kids.append(k)
+    assert sum(c.recv() for c in conns) == m
+
+    def step(q):
         t0 = time.perf_counter()
-        port.mcompare(store, {}, "q", args.ceiling)
-        t_used += time.perf_counter() - t0
+        for c in conns:
+            c.send(q)
+        n = sum(c.recv() for c in conns)
+        dt = time.perf_counter() - t0
+        assert n == m, (n, m)                                   # one row per candidate, as mcompare returns them
+        return dt
+
+    n_warm = min(args.warmup, 1)
+    for q in queries[:n_warm]:
+        step(q)
+    t_used, steps = 0.0, 0
+    for q in queries[args.warmup:args.warmup + args.steps]:
+        t_used += step(q)
         steps += 1
         if t_used > budget:
             break
+    for c in conns:
+        c.send(None)
+    for k in kids:
+        k.join(10)
     value = steps * m / t_used
-    sample = ("%d steps, each one query x %d candidates (bounded sample of the 50k workload), single thread: "
-              "Python-set restatement of seqComparer.mcompare (oracle/seqcomparer_port.py)" % (steps, m))
+    sample = ("%d steps, each one query x %d candidates (bounded sample of the 50k workload) split over %d processes: "
+              "Python-set restatement of seqComparer.mcompare (oracle/seqcomparer_port.py), the query sent to and the row "
+              "counts read from each process inside the timed region" % (steps, m, procs))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_used / steps, "higher_is_better": True,
+            "warmup": n_warm, "ms_per_step": 1e3 * t_used / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": "configs[1]: 50,000 synthetic TB sequences per GPU, one new-sample one-vs-all query "
                                    "per step, snpCeiling %d" % args.ceiling,
@@ -308,7 +354,7 @@ def run_reference(args, rank, world):
                        "candidates_per_step": m,
                        "sample": "each step compares the query with a bounded sample of %d of the shard's candidates "
                                  "(the reference's cost is linear in the candidates)" % m},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "host_cpus": os.cpu_count()}
     try:

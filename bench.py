@@ -868,6 +868,24 @@ def main():
                       "neighbours_per_query": r["neighbours"] / args.c4_inserts, "parity_rows_checked": r["parity_checked"],
                       "slowest_steps_ms": r["slowest"],
                       "store_bytes_per_gpu": int(target.stats()["store_bytes"] // world), "setup_s": t_setup}
+                # the STREAM kernel over ONE device's share of this store (2.5 x the headline shard): launch + query build,
+                # ~13 us of every k_scan launch whatever the store holds, weigh less the more rows a GPU holds
+                try:
+                    big = {}
+                    qrows = list(range(1000, 1000 + min(K, 24) + 3))
+                    for name, c in (("ceiling_250", 250), ("no_ceiling", 2 ** 31 - 1)):
+                        target.profile_queries(qrows[:3], c, flush_l2=True)
+                        pr = target.profile_queries(qrows[3:], c, flush_l2=True, count_bytes=True)
+                        ms = float(np.median(pr["ms_compare"]))
+                        mv = float(pr["bytes_touched"].mean())
+                        big[name] = {"ceiling": c, "launch_ms": ms, "launch_ms_p95": float(pct(pr["ms_compare"].tolist(), 0.95)),
+                                     "moved_bytes_per_launch": mv, "achieved": mv / (ms * 1e-3) / 1e9,
+                                     "frac": mv / (ms * 1e-3) / 1e9 / peak, "neighbours_per_query": float(pr["n_hits"].mean())}
+                    c4["scan_one_device"] = dict(big, bound="hbm", unit="GB/s", peak=peak, rows=int(per),
+                                                 kernel="k_scan over the %d rows one device holds of this store" % per)
+                except Exception as ex:   # pragma: no cover
+                    errors["config4_scan"] = repr(ex)
+                    log("config4 scan block failed:", repr(ex))
             except Exception as ex:   # pragma: no cover
                 errors["config4"] = repr(ex)
                 log("config4 leg failed:", repr(ex))

@@ -94,6 +94,7 @@ struct fn3_engine {
     int stage_limit = 0;                   // = max_smem, or 0 to force the global-memory query variants
     int q_static_smem = 0;                 // static shared memory of k_query
     int debug_stop = 0;                    // env FN3_DEBUG_STOP (profiling aid, wrong results when set)
+    int scan_ss = -1;                      // env FN3_SCAN_SS: forces k_scan's split of the 32-row tiles (profiling aid)
     uint32_t slot_blocks[1];               // touched-block bound of the single query of a one-vs-all call (sizes smem)
     QuerySlot* d_slots = nullptr; QuerySlot* h_slots = nullptr;   // [FN3_SLOT_RING tiles][FN3_MAX_SLOTS]; h_slots pinned
     // survivor buffer: one allocation = [32-byte counter block | records]; the pinned mirror is used by the
@@ -330,6 +331,7 @@ extern "C" fn3_engine* fn3_create(int64_t genome_length, int32_t device) {
     e->sb_shift = std::min(13, e->hdr_shift);                   // 8192-row superblocks: neighbours in insertion
                                                                 // order sit 256 tiles apart
     e->debug_stop = (int)env_ll("FN3_DEBUG_STOP", 0);
+    e->scan_ss = (int)env_ll("FN3_SCAN_SS", -1);
     e->bg_auto = env_ll("FN3_BG_AUTO", 1) != 0;
     e->bg_ppm = std::max<long long>(1, env_ll("FN3_BG_PPM", 10000));
     // queries per all-vs-all tile (one k_query launch): one per SM, so that with two CTAs per query every resident CTA
@@ -955,6 +957,32 @@ struct QueryJob {                    // what enqueue_query needs beyond the engi
 
 // enqueue one query tile on q_stream.  Normally ONE kernel (k_query builds the query structure in shared memory
 // itself); queries too large for shared memory take k_build_query + the global-memory variant.
+// k_scan: into how many sub-units (1 << ss, ss = 0..3) a 32-row head tile is split.  A warp takes whole sub-units, so the
+// launch ends when the warp with the most rows ends: per split, (sub-units a warp must take) x (rows of a sub-unit + the cost
+// of drawing one and fetching its headers, about half a row) is estimated and the cheapest split taken.  Sub-units that hold
+// no row — the unused lanes of the last, partly filled superblock — are not counted.  Measured on the 50 000-row bench store
+// (one-vs-all at ceiling 250 / none, scripts/variant_prof.py with FN3_SCAN_SS): ss 0: 45.0 / 84.8 us, 1: 34.9 / 51.3,
+// 2: 35.8 / 52.1, 3: 36.8 / 53.3, 4: 36.9 / 53.8, 5: 39.8 / 57.3 — this rule picks 1 there and 3 from ~100 000 rows on.
+static int pick_scan_split(long long n_rows, int sb_shift, bool list, long long n_list, long long warps) {
+    int best = 0;
+    double best_cost = 1e300;
+    for (int ss = 0; ss <= 3; ++ss) {
+        const long long r = 32 >> ss;
+        long long subs, rows_per;
+        if (list) { subs = ((n_list + 31) / 32) << ss; rows_per = r; }
+        else {
+            const long long tiles = 1ll << (sb_shift - 5), full = n_rows >> sb_shift, rem = n_rows & ((1ll << sb_shift) - 1);
+            const long long lanes = (rem + tiles - 1) / tiles;          // lanes of the last superblock's tiles that hold a row
+            subs = full * (tiles << ss) + tiles * std::min<long long>(1ll << ss, (lanes + r - 1) / r);
+            rows_per = full ? r : std::min<long long>(r, lanes);
+        }
+        const long long per_warp = (subs + warps - 1) / std::max<long long>(warps, 1);
+        const double cost = (double)per_warp * ((double)rows_per + 0.5);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = ss; }
+    }
+    return best;
+}
+
 static int enqueue_query(fn3_engine* e, QueryJob& job) {
     cudaStream_t st = e->q_stream;
     const int ns = job.ns;
@@ -1016,10 +1044,10 @@ static int enqueue_query(fn3_engine* e, QueryJob& job) {
     if (filter) {
         ctas = std::min<long long>(std::max<long long>(1, (units + warps_per_cta - 1) / warps_per_cta), cta_cap);
     } else {
-        // k_scan: a warp streams its rows one after the other, so the unit of balance is small — split the 32-row tiles
-        // until every warp of the launch can draw about three sub-units (50 000 rows = 1 792 tiles for 2 368 warps)
-        int ss = 0;
-        while (ss < 3 && (units << ss) < 3 * cta_cap * warps_per_cta) ++ss;
+        // k_scan: a warp streams its rows one after the other; the 32-row tiles are split into sub-units so that the rows
+        // spread over all warps of the launch (pick_scan_split)
+        int ss = pick_scan_split(job.n_rows, e->sb_shift, job.d_rows != nullptr, job.n_list, cta_cap * warps_per_cta);
+        if (e->scan_ss >= 0 && e->scan_ss <= 5) ss = e->scan_ss;
         p.split_shift = ss;
         p.ring_off = (unsigned int)(in_smem ? q_smem : 0);
         ctas = std::min<long long>(std::max<long long>(1, ((units << ss) + warps_per_cta - 1) / warps_per_cta), cta_cap);
@@ -2250,5 +2278,16 @@ extern "C" int fn3_profile_queries(fn3_engine* e, const int64_t* query_rows, int
     if (sync != cudaSuccess) return set_err(e, FN3_ECUDA, "fn3_profile_queries: %s", cudaGetErrorString(sync));
     return FN3_OK;
 }
+
+#if FN3_TRACE
+// trace build only (scripts/trace_prof.py): the SM clocks left by the last compare launch, then cleared
+extern "C" int fn3_debug_trace(unsigned long long* out, int n_words) {
+    const size_t bytes = std::min<size_t>((size_t)n_words * 8, sizeof(unsigned long long) * FN3_TRACE_CTAS * FN3_TRACE_PTS);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out, fn3_trace_buf, bytes) != cudaSuccess) return -1;
+    std::vector<unsigned long long> z(FN3_TRACE_CTAS * FN3_TRACE_PTS, 0ull);
+    return cudaMemcpyToSymbol(fn3_trace_buf, z.data(), z.size() * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 #include "fn3_group.inl"

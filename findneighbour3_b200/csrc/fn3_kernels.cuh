@@ -10,6 +10,29 @@
 // small device helpers
 // ------------------------------------------------------------------------------------------------
 
+// -DFN3_TRACE=1 (scripts/trace_prof.py, never the shipped build): thread 0 of every CTA leaves its SM clock at numbered
+// points of the compare kernels, read back through fn3_debug_trace()
+#ifndef FN3_TRACE
+#define FN3_TRACE 0
+#endif
+#if FN3_TRACE
+#define FN3_TRACE_CTAS 512
+#define FN3_TRACE_PTS 40
+__device__ unsigned long long fn3_trace_buf[FN3_TRACE_CTAS * FN3_TRACE_PTS];
+#define FN3_TR(i) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < FN3_TRACE_CTAS) \
+        fn3_trace_buf[blockIdx.x * FN3_TRACE_PTS + (i)] = (unsigned long long)clock64(); } while (0)
+__device__ __forceinline__ unsigned long long fn3_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FN3_TRG(i) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < FN3_TRACE_CTAS) \
+        fn3_trace_buf[blockIdx.x * FN3_TRACE_PTS + (i)] = fn3_globaltimer(); } while (0)
+#else
+#define FN3_TR(i) do { } while (0)
+#define FN3_TRG(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint4 ld_stream_v4(const uint32_t* p) {
     // candidate row data is read once per comparison: do not let it displace anything in L1
     uint4 r;
@@ -110,6 +133,15 @@ __device__ __forceinline__ void block_exscan3_1b(uint32_t& a, uint32_t& b, uint3
     c = __reduce_add_sync(0xffffffffu, before ? wc : 0u) + ic - c;
 }
 
+#ifndef FN3_PF
+#define FN3_PF 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one instruction asks `bytes` (multiple of 16) into L2 through the bulk-copy engine: nothing enters the load/store queue
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // address of the tile holding `row`, and the row's lane in it
 __device__ __forceinline__ const unsigned char* tile_of(const HdrTable& ht, long long row, int& lane) {
     const long long local = row & ((1ll << ht.shift) - 1);
@@ -151,19 +183,31 @@ template <bool GLOBAL> __device__ __forceinline__ uint32_t ldq(const uint32_t* p
 // All threads of the CTA must call.  bm: 2*nw words (bitmap, then prefix); coarse: ncw words; en: (touched+1)
 // entries; ws: FN3_WS_WORDS words.
 // tot[0..2] = |V_q|, |U_q|, |M_q|; returns the number of touched blocks.
-template <bool GLOBAL>
-__device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int ncw, int fshift, int pos_bits,
+#if FN3_EXP_NOATOM          // timing experiment only (wrong masks): what do the shared-memory atomics of the build cost?
+#define FN3_OR(p, v) (*(p) = (v))
+#else
+#define FN3_OR(p, v) atomicOr((p), (v))
+#endif
+#if FN3_BUILD_TWICE
+#define FN3_BUILD_INLINE __noinline__
+#else
+#define FN3_BUILD_INLINE __forceinline__
+#endif
+template <bool GLOBAL, int NT>                               // NT = blockDim.x (a constant: the ranges below divide by it)
+__device__ FN3_BUILD_INLINE uint32_t build_query(const QuerySlot& q, int nw, int ncw, int fshift, int pos_bits,
                                                 uint32_t* bm, uint32_t* coarse, QEntry* en, uint32_t* ws, uint32_t tot[3]) {
     uint32_t* pref = bm + nw;
     const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(q.hdr.data);
     const uint32_t e0 = q.hdr.end[0], e1 = q.hdr.end[1], e2 = q.hdr.end[2], e3 = q.hdr.end[3],
                    e4 = q.hdr.end[4], e5 = d ? q.hdr.end[5] : 0u;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x;
+    constexpr int nt = NT;
     // the row is read once: up to FN3_BUILD_KEEP words per thread stay in registers for the second pass
     uint32_t keep[FN3_BUILD_KEEP];
 #pragma unroll
     for (int r = 0; r < FN3_BUILD_KEEP; ++r) { const uint32_t i = tid + r * nt; keep[r] = i < e5 ? __ldg(d + i) : 0u; }
+    FN3_TR(1);
     {
         uint4* z = reinterpret_cast<uint4*>(bm);
         for (int i = tid; i < nw / 4; i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -172,6 +216,7 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
     }
     if (GLOBAL) __threadfence_block();
     __syncthreads();
+    FN3_TR(2);
     const int cs = fshift - 5;                                   // coarse block = 1 << cs fine blocks
     uint8_t* cmap = reinterpret_cast<uint8_t*>(coarse);          // one BYTE per coarse block: 1 = touched
     if (tid == 0) cmap[ncw * 4 - 1] = 1;                         // the id padded fingerprints carry: never counts
@@ -183,24 +228,56 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
             const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u);
             b0 = s >> 5; b1 = (s + len - 1u) >> 5;
         }
-        for (uint32_t blk = b0; blk <= b1; ++blk) atomicOr(&bm[blk >> 5], 1u << (blk & 31u));
+        for (uint32_t blk = b0; blk <= b1; ++blk) FN3_OR(&bm[blk >> 5], 1u << (blk & 31u));
         for (uint32_t cb = b0 >> cs; cb <= (b1 >> cs); ++cb) cmap[cb] = 1;      // plain byte stores: every writer writes 1
     }
     if (GLOBAL) __threadfence_block();
     __syncthreads();
-    const int chunk = (nw + nt - 1) / nt;                        // 2. prefix of touched-block counts
-    const int lo = min(nw, tid * chunk), hi = min(nw, lo + chunk);
+    FN3_TR(3);
+    // 2. prefix of touched-block counts: every thread owns `c4` consecutive groups of four words (nw is a multiple of 4;
+    //    128-bit accesses a group apart per lane are conflict-free for c4 = 1, 3; the words stay in registers in between)
+    constexpr int MAXC4 = 4;
+    const int n4 = nw >> 2, c4 = (n4 + nt - 1) / nt;
+    const int lo4 = min(n4, tid * c4), hi4 = min(n4, lo4 + c4);
+    FN3_TR(32);
     uint32_t local = 0;
-    for (int w = lo; w < hi; ++w) local += __popc(ldq<GLOBAL>(&bm[w]));
+    uint4 own[MAXC4];
+    if (!GLOBAL && c4 <= MAXC4) {
+#pragma unroll
+        for (int j = 0; j < MAXC4; ++j) {
+            own[j] = (lo4 + j < hi4) ? reinterpret_cast<const uint4*>(bm)[lo4 + j] : make_uint4(0u, 0u, 0u, 0u);
+            local += __popc(own[j].x) + __popc(own[j].y) + __popc(own[j].z) + __popc(own[j].w);
+        }
+    } else {
+        for (int w = lo4 * 4; w < hi4 * 4; ++w) local += __popc(ldq<GLOBAL>(&bm[w]));
+    }
+    FN3_TR(24);
     uint32_t nE;
     uint32_t run = block_exscan_1b(local, ws, &nE);
-    for (int w = lo; w < hi; ++w) { const uint32_t b = ldq<GLOBAL>(&bm[w]); pref[w] = run; run += __popc(b); }
+    FN3_TR(25);
+    if (!GLOBAL && c4 <= MAXC4) {
+#pragma unroll
+        for (int j = 0; j < MAXC4; ++j) {
+            if (lo4 + j < hi4) {
+                uint4 pr;
+                pr.x = run; run += __popc(own[j].x);
+                pr.y = run; run += __popc(own[j].y);
+                pr.z = run; run += __popc(own[j].z);
+                pr.w = run; run += __popc(own[j].w);
+                reinterpret_cast<uint4*>(pref)[lo4 + j] = pr;
+            }
+        }
+    } else {
+        for (int w = lo4 * 4; w < hi4 * 4; ++w) { const uint32_t b = ldq<GLOBAL>(&bm[w]); pref[w] = run; run += __popc(b); }
+    }
+    FN3_TR(26);
     {
         uint4* z = reinterpret_cast<uint4*>(en);                 // 3. clear entries incl. the sentinel
         for (uint32_t i = tid; i < 2u * (nE + 1u); i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (GLOBAL) __threadfence_block();
     __syncthreads();
+    FN3_TR(4);
     for (uint32_t i = tid, r = 0; i < e5; i += nt, ++r) {       // 4. per-position masks
         const uint32_t w = r < FN3_BUILD_KEEP ? keep[r < FN3_BUILD_KEEP ? r : 0] : __ldg(d + i);
         if (i < e3) {
@@ -209,9 +286,9 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
             QEntry* t = en + (by + __popc(bx & lowmask(blk & 31u)));
             const uint32_t pb = 1u << (w & 31u);
             const uint32_t base = (i >= e0) + (i >= e1) + (i >= e2);
-            atomicOr(&t->mDef, pb);
-            if (base & 1u) atomicOr(&t->mB0, pb);
-            if (base & 2u) atomicOr(&t->mB1, pb);
+            FN3_OR(&t->mDef, pb);
+            if (base & 1u) FN3_OR(&t->mB0, pb);
+            if (base & 2u) FN3_OR(&t->mB1, pb);
         } else {
             const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u), e = s + len;
             for (uint32_t blk = s >> 5; blk <= ((e - 1u) >> 5); ++blk) {
@@ -220,33 +297,76 @@ __device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int 
                 const uint32_t m = (to >= 32u ? 0xffffffffu : lowmask(to)) & ~lowmask(from);
                 const uint32_t bx = ldq<GLOBAL>(&bm[blk >> 5]), by = ldq<GLOBAL>(&pref[blk >> 5]);
                 QEntry* t = en + (by + __popc(bx & lowmask(blk & 31u)));
-                atomicOr(&t->mU, m);
-                if (i >= e4) atomicOr(&t->mM, m);
+                FN3_OR(&t->mU, m);
+                if (i >= e4) FN3_OR(&t->mM, m);
             }
         }
     }
     if (GLOBAL) __threadfence_block();
     __syncthreads();
-    const uint32_t echunk = (nE + nt - 1) / nt;                  // 5. running counts
-    const uint32_t elo = min(nE, tid * echunk), ehi = min(nE, elo + echunk);
+    FN3_TR(5);
+    // 5. running counts.  Warp w owns a contiguous run of entries, its lanes take them INTERLEAVED (lane l: first + l,
+    //    first + 32 + l, ...): neighbouring lanes read neighbouring 32-byte entries.  (One contiguous chunk per THREAD put
+    //    the lanes of a warp a whole chunk apart — an 8- to 32-way bank conflict on every access; in-kernel clocks: this phase
+    //    took 2.2 of the build's 4.3 us.)
+    const uint32_t lane5 = tid & 31u, warp5 = tid >> 5;
+    constexpr uint32_t nwarp5 = (uint32_t)NT >> 5;
+    const uint32_t per_w = ((nE + nwarp5 * 32u - 1u) / (nwarp5 * 32u)) * 32u;
+    const uint32_t wlo = min(nE, warp5 * per_w), whi = min(nE, wlo + per_w);
+    // (in shared memory an entry is read as its two 128-bit halves: 32-bit reads of one field of 32 neighbouring entries
+    //  fall into four banks)
+    auto masks = [&](uint32_t i, uint32_t& d, uint32_t& u, uint32_t& m) {
+        if (GLOBAL) { d = __ldcg(&en[i].mDef); u = __ldcg(&en[i].mU); m = __ldcg(&en[i].mM); }
+        else {
+            const uint4 a = reinterpret_cast<const uint4*>(en)[2u * i], b = reinterpret_cast<const uint4*>(en)[2u * i + 1u];
+            d = a.x; u = a.y; m = b.x;
+        }
+    };
     uint32_t sD = 0, sU = 0, sM = 0;
-    for (uint32_t i = elo; i < ehi; ++i) {
-        sD += __popc(ldq<GLOBAL>(&en[i].mDef)); sU += __popc(ldq<GLOBAL>(&en[i].mU)); sM += __popc(ldq<GLOBAL>(&en[i].mM));
+    FN3_TR(30);
+    for (uint32_t i = wlo + lane5; i < whi; i += 32u) {
+        uint32_t d, u, m;
+        masks(i, d, u, m);
+        sD += __popc(d); sU += __popc(u); sM += __popc(m);
     }
+    FN3_TR(31);
+    sD = __reduce_add_sync(0xffffffffu, sD); sU = __reduce_add_sync(0xffffffffu, sU); sM = __reduce_add_sync(0xffffffffu, sM);
+    if (lane5) { sD = 0u; sU = 0u; sM = 0u; }                    // one value per warp goes into the block scan
+    FN3_TR(27);
     uint32_t tD, tU, tM;
     block_exscan3_1b(sD, sU, sM, ws + 32, tD, tU, tM);
-    for (uint32_t i = elo; i < ehi; ++i) {
-        const uint32_t a = __popc(ldq<GLOBAL>(&en[i].mDef)), b = __popc(ldq<GLOBAL>(&en[i].mU)), c = __popc(ldq<GLOBAL>(&en[i].mM));
-        en[i].cDef = sD; en[i].cU = sU; en[i].cM = sM;
-        sD += a; sU += b; sM += c;
+    FN3_TR(28);
+    uint32_t bD = __shfl_sync(0xffffffffu, sD, 0), bU = __shfl_sync(0xffffffffu, sU, 0), bM = __shfl_sync(0xffffffffu, sM, 0);
+    for (uint32_t i0 = wlo; i0 < whi; i0 += 32u) {               // warp-uniform trip count
+        const uint32_t i = i0 + lane5;
+        const bool ok = i < whi;
+        uint32_t d = 0u, u = 0u, m = 0u;
+        if (ok) masks(i, d, u, m);
+        const uint32_t a = __popc(d), b = __popc(u), c = __popc(m);
+        uint32_t ia = a, ib = b, ic = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, ia, o), y = __shfl_up_sync(0xffffffffu, ib, o),
+                           z = __shfl_up_sync(0xffffffffu, ic, o);
+            if ((int)lane5 >= o) { ia += x; ib += y; ic += z; }
+        }
+        if (ok) {
+            if (GLOBAL) { en[i].cDef = bD + ia - a; en[i].cU = bU + ib - b; en[i].cM = bM + ic - c; }
+            else reinterpret_cast<uint4*>(en)[2u * i + 1u] = make_uint4(m, bD + ia - a, bU + ib - b, bM + ic - c);
+        }
+        bD += __shfl_sync(0xffffffffu, ia, 31); bU += __shfl_sync(0xffffffffu, ib, 31); bM += __shfl_sync(0xffffffffu, ic, 31);
     }
     if (tid == 0) { en[nE].cDef = tD; en[nE].cU = tU; en[nE].cM = tM; }
+    FN3_TR(29);
     __syncthreads();
+    FN3_TR(6);
     tot[0] = tD; tot[1] = tU; tot[2] = tM;
     return nE;
 }
 
+#ifndef FN3_Q_THREADS
 #define FN3_Q_THREADS 512
+#endif
 
 __global__ void __launch_bounds__(FN3_Q_THREADS) k_build_query(const QuerySlot* __restrict__ slots, const QueryState qs,
                                                                int nw, int ncw, int fshift, int pos_bits) {
@@ -254,7 +374,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS) k_build_query(const QuerySlot* 
     const int slot = blockIdx.x;
     const QuerySlot q = slots[slot];
     uint32_t tot[3];
-    const uint32_t nE = build_query<true>(q, nw, ncw, fshift, pos_bits, qs.bm + (long long)slot * 2 * nw,
+    const uint32_t nE = build_query<true, FN3_Q_THREADS>(q, nw, ncw, fshift, pos_bits, qs.bm + (long long)slot * 2 * nw,
                                           qs.coarse + (long long)slot * ncw, qs.ent + (long long)slot * qs.ent_stride, ws, tot);
     if (threadIdx.x == 0) qs.info[slot] = make_uint4(nE, tot[0], tot[1], tot[2]);
 }
@@ -460,6 +580,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     __shared__ int q_row[FN3_SURV_CAP];
     __shared__ unsigned int q_count, q_head;
     if (p.debug_stop == 3) return;
+    FN3_TR(0); FN3_TRG(22);
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.y;
     const QuerySlot qs = p.slot_inline ? p.slot0 : p.slots[slot];
@@ -480,6 +601,20 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
     const uint32_t units = p.rows ? (uint32_t)((p.n_list + 31) >> 5)
                            : (uint32_t)(((p.n_rows + (1ll << p.hdr.sb_shift) - 1) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5));
     const uint32_t u0 = (uint32_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+#if FN3_PF
+    // the head tile this warp will test first is asked into L2 now (one bulk prefetch of its 3 072 bytes by one lane, no
+    // register held, nothing in the load/store queue the build is about to fill): its way from HBM overlaps the query build
+    // instead of following it (in-kernel clocks: head arrival 1.4 -> 0.7 us after the request; 24 per-line prefetch
+    // instructions per warp did the same but slowed the build's shared-memory phases by as much)
+    if (!p.rows) {
+        const int sl0 = (int)qs.skip_le;
+        const uint32_t uf = sl0 < 0 ? 0u : (((uint32_t)sl0 + 1u) >> p.hdr.sb_shift) << (p.hdr.sb_shift - 5);
+        const uint32_t ust = gridDim.x * (FN3_Q_THREADS / 32);
+        for (uint32_t uu = uf + u0, i = 0; i < (p.ceiling < 16 ? 2u : 1u) && uu < units; ++i, uu += ust)
+            if (lane == 0)
+                prefetch_l2_bulk(p.hdr.chunk[uu >> tshift] + (size_t)(uu & ((1u << tshift) - 1u)) * FN3_TILE_BYTES, FN3_TILE_BYTES);
+    }
+#endif
     uint32_t nVq, nUq, nMq;
     QView qv;
     if (QMODE == 1) {
@@ -487,7 +622,12 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
         uint32_t* sm_co = reinterpret_cast<uint32_t*>(qsm + nw / 2);
         QEntry* sm_en = reinterpret_cast<QEntry*>(qsm + nw / 2 + ncw / 4);
         uint32_t tot[3];
-        build_query<false>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
+#if FN3_BUILD_TWICE                                        // experiment: is the build bound by cold instruction fetch?
+        build_query<false, FN3_Q_THREADS>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
+        __syncthreads();
+        FN3_TR(21);
+#endif
+        build_query<false, FN3_Q_THREADS>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
         nVq = tot[0]; nUq = tot[1]; nMq = tot[2];
         qv.bm = sm_bm; qv.pref = sm_bm + nw; qv.cmap = reinterpret_cast<const uint8_t*>(sm_co); qv.ent = reinterpret_cast<const uint4*>(sm_en);
     } else {
@@ -499,6 +639,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
         qv.ent = reinterpret_cast<const uint4*>(p.qs.ent + (long long)slot * p.qs.ent_stride);
     }
     if (p.debug_stop == 1) return;
+    FN3_TR(7);
     if (QMODE != 1) __syncthreads();                       // the survivor queue's counters are initialised
     const int k = p.ceiling;
     const int pos_bits = p.pos_bits;
@@ -643,6 +784,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
                 const unsigned char* tile;
                 int tl;
                 const int row = locate(u, tile, tl);
+                FN3_TR(33);
                 const uint4* hp = reinterpret_cast<const uint4*>(tile + tl * 32);
                 const uint4* fp = reinterpret_cast<const uint4*>(tile + FN3_TILE_FP_OFF + tl * 16);
                 uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
@@ -651,15 +793,21 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
                     h0 = ld_head_v4(hp); h1 = ld_head_v4(hp + 1);
                     const uint4 f0 = ld_head_v4(fp), f1 = ld_head_v4(fp + 32), f2 = ld_head_v4(fp + 64), f3 = ld_head_v4(fp + 96);
                     if (COUNT) touched += 96;
-                    int S = count8(f0) + count8(f1) + count8(f2);
+                    int S = count8(f0);
+                    FN3_TR(34);
+                    S += count8(f1) + count8(f2);
                     if (S <= k) S += count8(f3);
                     pass = S <= k;
                 }
+                FN3_TR(8);
                 survivors(pass, row, false, -1, true, h0, h1);
+                FN3_TR(9);
             }
         }
         // ---- phase B: every warp of the CTA draws queued survivors ------------------------------------------
+        FN3_TR(10);
         __syncthreads();
+        FN3_TR(11);
         const unsigned int n_q = min(q_count, (unsigned int)FN3_SURV_CAP);
         for (;;) {
             unsigned int i = 0u;
@@ -670,6 +818,7 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
             stream_one(q_row[i], h0, h1, (h0.x | h0.y) != 0u);
         }
     }
+    FN3_TR(12); FN3_TRG(23);
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, o);

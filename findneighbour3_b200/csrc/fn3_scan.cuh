@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
     __shared__ uint32_t ws[FN3_WS_WORDS];
     __shared__ unsigned int next_unit;
     if (p.debug_stop == 3) return;
+    FN3_TR(13); FN3_TRG(22);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
     const QuerySlot qs = p.slot_inline ? p.slot0 : p.slots[slot];
@@ -168,6 +169,10 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
         if (p.host_flag) signal_done(p);
         return;
     }
+#if FN3_PF
+    if (QMODE == 1 && threadIdx.x * 32u < qs.hdr.end[5])   // the query's own row, wanted by the build below: on its way into L2
+        prefetch_l2(reinterpret_cast<const uint32_t*>(qs.hdr.data) + threadIdx.x * 32u);   // while the first rows are requested
+#endif
     // ring carve-out: [slots: WARPS x D x CH words | meta: WARPS x D x 12 words | staged records: WARPS x R x 32 bytes |
     //                  mbarriers: WARPS x D x 8 bytes]
     unsigned char* ring_base = reinterpret_cast<unsigned char*>(qsm) + p.ring_off;
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
     }
     if (threadIdx.x == 0) next_unit = 0u;
     __syncthreads();                                       // the unit counter is initialised (each warp's mbarriers are its own)
+    FN3_TR(14);
     unsigned long long touched = 0;
 
     // ---- work units ---------------------------------------------------------------------------------
@@ -196,7 +202,6 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
     const uint32_t ufirst = (p.rows || skip_le < 0) ? 0u : (((uint32_t)skip_le + 1u) >> sb_shift) << gs;
     const int ss = p.split_shift;                          // a unit is drawn as 1 << ss sub-units of 32 >> ss rows
     const uint32_t sub_total = (units - ufirst) << ss;
-
     uint4 cur0 = make_uint4(0, 0, 0, 0), cur1 = cur0, nxt0 = cur0, nxt1 = cur0;     // headers of the current / next sub-unit
     int cur_row = -1, nxt_row = -1;
     bool nxt_ok = false;
@@ -285,10 +290,12 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
         cur0 = nxt0; cur1 = nxt1; cur_row = nxt_row;
         fetch_next();                                      // ... and of the second
         p_mask = __ballot_sync(0xffffffffu, cur_row >= 0 && (cur0.x | cur0.y) != 0u);
+        FN3_TR(15);
 #pragma unroll 1
         for (int i = 0; i < FN3_SCAN_D; ++i)
             if (!issue_one()) break;
     }
+    FN3_TR(16);
 
     const int nw = p.nw, ncw = p.ncw;
     uint32_t nVq, nUq, nMq;
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
         uint32_t* sm_co = reinterpret_cast<uint32_t*>(qsm + nw / 2);
         QEntry* sm_en = reinterpret_cast<QEntry*>(qsm + nw / 2 + ncw / 4);
         uint32_t tot[3];
-        build_query<false>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
+        build_query<false, FN3_SCAN_THREADS>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
         nVq = tot[0]; nUq = tot[1]; nMq = tot[2];
         qv.bm = sm_bm; qv.pref = sm_bm + nw; qv.cmap = reinterpret_cast<const uint8_t*>(sm_co); qv.ent = reinterpret_cast<const uint4*>(sm_en);
     } else {
@@ -312,6 +319,7 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
     const int k = p.ceiling;
     const int pos_bits = p.pos_bits;
     const uint32_t pmask = (pos_bits >= 32) ? 0xffffffffu : ((1u << pos_bits) - 1u);
+    FN3_TR(17);
 
     // ---- neighbour records: collected per warp, appended FN3_SCAN_R at a time with one atomic ---------------
     // (one atomic per record on the single counter bounds a scan in which every row is a neighbour — an outbreak, or
@@ -372,7 +380,9 @@ __global__ void __launch_bounds__(FN3_SCAN_THREADS, 1) k_scan(const CompareParam
         --outstanding;
         issue_one();
     }
+    FN3_TR(19);
     if (n_staged) flush();
+    FN3_TR(20); FN3_TRG(23);
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, o);

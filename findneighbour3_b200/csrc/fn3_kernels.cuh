@@ -183,18 +183,8 @@ template <bool GLOBAL> __device__ __forceinline__ uint32_t ldq(const uint32_t* p
 // All threads of the CTA must call.  bm: 2*nw words (bitmap, then prefix); coarse: ncw words; en: (touched+1)
 // entries; ws: FN3_WS_WORDS words.
 // tot[0..2] = |V_q|, |U_q|, |M_q|; returns the number of touched blocks.
-#if FN3_EXP_NOATOM          // timing experiment only (wrong masks): what do the shared-memory atomics of the build cost?
-#define FN3_OR(p, v) (*(p) = (v))
-#else
-#define FN3_OR(p, v) atomicOr((p), (v))
-#endif
-#if FN3_BUILD_TWICE
-#define FN3_BUILD_INLINE __noinline__
-#else
-#define FN3_BUILD_INLINE __forceinline__
-#endif
 template <bool GLOBAL, int NT>                               // NT = blockDim.x (a constant: the ranges below divide by it)
-__device__ FN3_BUILD_INLINE uint32_t build_query(const QuerySlot& q, int nw, int ncw, int fshift, int pos_bits,
+__device__ __forceinline__ uint32_t build_query(const QuerySlot& q, int nw, int ncw, int fshift, int pos_bits,
                                                 uint32_t* bm, uint32_t* coarse, QEntry* en, uint32_t* ws, uint32_t tot[3]) {
     uint32_t* pref = bm + nw;
     const uint32_t* __restrict__ d = reinterpret_cast<const uint32_t*>(q.hdr.data);
@@ -228,7 +218,7 @@ __device__ FN3_BUILD_INLINE uint32_t build_query(const QuerySlot& q, int nw, int
             const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u);
             b0 = s >> 5; b1 = (s + len - 1u) >> 5;
         }
-        for (uint32_t blk = b0; blk <= b1; ++blk) FN3_OR(&bm[blk >> 5], 1u << (blk & 31u));
+        for (uint32_t blk = b0; blk <= b1; ++blk) atomicOr(&bm[blk >> 5], 1u << (blk & 31u));
         for (uint32_t cb = b0 >> cs; cb <= (b1 >> cs); ++cb) cmap[cb] = 1;      // plain byte stores: every writer writes 1
     }
     if (GLOBAL) __threadfence_block();
@@ -286,9 +276,9 @@ __device__ FN3_BUILD_INLINE uint32_t build_query(const QuerySlot& q, int nw, int
             QEntry* t = en + (by + __popc(bx & lowmask(blk & 31u)));
             const uint32_t pb = 1u << (w & 31u);
             const uint32_t base = (i >= e0) + (i >= e1) + (i >= e2);
-            FN3_OR(&t->mDef, pb);
-            if (base & 1u) FN3_OR(&t->mB0, pb);
-            if (base & 2u) FN3_OR(&t->mB1, pb);
+            atomicOr(&t->mDef, pb);
+            if (base & 1u) atomicOr(&t->mB0, pb);
+            if (base & 2u) atomicOr(&t->mB1, pb);
         } else {
             const uint32_t s = w & pmask, len = (pos_bits >= 32) ? 1u : ((w >> pos_bits) + 1u), e = s + len;
             for (uint32_t blk = s >> 5; blk <= ((e - 1u) >> 5); ++blk) {
@@ -297,8 +287,8 @@ __device__ FN3_BUILD_INLINE uint32_t build_query(const QuerySlot& q, int nw, int
                 const uint32_t m = (to >= 32u ? 0xffffffffu : lowmask(to)) & ~lowmask(from);
                 const uint32_t bx = ldq<GLOBAL>(&bm[blk >> 5]), by = ldq<GLOBAL>(&pref[blk >> 5]);
                 QEntry* t = en + (by + __popc(bx & lowmask(blk & 31u)));
-                FN3_OR(&t->mU, m);
-                if (i >= e4) FN3_OR(&t->mM, m);
+                atomicOr(&t->mU, m);
+                if (i >= e4) atomicOr(&t->mM, m);
             }
         }
     }
@@ -622,11 +612,6 @@ __global__ void __launch_bounds__(FN3_Q_THREADS, FN3_Q_MINB) k_query(const Compa
         uint32_t* sm_co = reinterpret_cast<uint32_t*>(qsm + nw / 2);
         QEntry* sm_en = reinterpret_cast<QEntry*>(qsm + nw / 2 + ncw / 4);
         uint32_t tot[3];
-#if FN3_BUILD_TWICE                                        // experiment: is the build bound by cold instruction fetch?
-        build_query<false, FN3_Q_THREADS>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
-        __syncthreads();
-        FN3_TR(21);
-#endif
         build_query<false, FN3_Q_THREADS>(qs, nw, ncw, p.fshift, p.pos_bits, sm_bm, sm_co, sm_en, ws, tot);
         nVq = tot[0]; nUq = tot[1]; nMq = tot[2];
         qv.bm = sm_bm; qv.pref = sm_bm + nw; qv.cmap = reinterpret_cast<const uint8_t*>(sm_co); qv.ent = reinterpret_cast<const uint4*>(sm_en);

@@ -13,7 +13,7 @@ from findneighbour3_b200.engine import Engine
 PTS, CTAS, MHZ = 40, 512, 1965.0
 NAMES = {0: "k_query entry", 1: "build: row loads issued", 2: "build: zeroed + row words arrived", 3: "build: touched blocks set",
          4: "build: prefix + entries cleared", 5: "build: masks", 6: "build: counts (done)", 7: "after build",
-         21: "first build done (BUILD_TWICE)", 8: "phase A: heads tested (warp 0)", 9: "phase A: survivors queued", 10: "phase A loop left", 11: "phase B barrier passed",
+         8: "phase A: heads tested (warp 0)", 9: "phase A: survivors queued", 10: "phase A loop left", 11: "phase B barrier passed",
          12: "phase B drained", 13: "k_scan entry", 14: "mbarriers ready", 15: "first headers arrived", 16: "first copies issued",
          17: "query built", 19: "rows done", 20: "records flushed", 24: "build/prefix: popc of own words", 25: "build/prefix: block scan", 26: "build/prefix: written",
          27: "build/counts: warp sums", 28: "build/counts: block scan", 29: "build/counts: written",

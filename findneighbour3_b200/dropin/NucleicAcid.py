@@ -1,2 +1,1 @@
-"""`from NucleicAcid import NucleicAcid` (src/findNeighbour3-server.py:72)."""
-from findneighbour3_b200.NucleicAcid import NucleicAcid  # noqa: F401
+from findneighbour3_b200.NucleicAcid import NucleicAcid  # noqa: F401 -- `from NucleicAcid import NucleicAcid` (findNeighbour3-server.py:72) lands here

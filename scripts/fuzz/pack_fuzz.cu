@@ -1,6 +1,6 @@
 // ASan/UBSan differential fuzz of the host-side sample validation and row packing of fn3_engine.cu (no GPU needed: the
 // engine struct is filled by hand the way fn3_create does):
-//   nvcc -std=c++17 -g -I ../../include -Xcompiler -fsanitize=address,undefined pack_fuzz.cu -o /tmp/pack_fuzz
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -g -I ../../include -Xcompiler -fsanitize=address -Xcompiler -fsanitize=undefined pack_fuzz.cu -o /tmp/pack_fuzz
 //   ASAN_OPTIONS=protect_shadow_gap=0:detect_leaks=0 /tmp/pack_fuzz
 // Checks, on random valid and damaged samples over several genome lengths: row_words_needed + pack_row (bulk path) and
 // pack_checked (insert path) give the same verdict, the same words and the same list ends; the packed row decodes back to the

@@ -294,6 +294,32 @@ def test_synthetic_vs_c_oracle(shape, staged, monkeypatch):
     eng.close()
 
 
+@pytest.mark.parametrize("split", [None, 0, 1, 2, 3, 5])
+def test_scan_every_split_of_the_head_tiles(split, monkeypatch):
+    """k_scan hands its warps sub-units of a 32-row head tile; the split (fn3_engine.cu pick_scan_split, or FN3_SCAN_SS) must
+    not show in the result: one full superblock of 8 192 rows plus a partly filled one, full scans and explicit candidate
+    lists, at the recompression ceiling and with none."""
+    from findneighbour3_b200.engine import Engine
+    from oracle import c_oracle
+    if split is not None:
+        monkeypatch.setenv("FN3_SCAN_SS", str(split))
+    coll = _synthetic(190, 50, 300000, 21, k1=150, s=3.0, n_blocks=6, n_mean=600, m_mean=2, rule="any", p_invalid=0.01)
+    assert coll.n > 8192 + 300
+    eng = Engine(coll.genome_length, 0)
+    eng.append_bulk(coll.pos, coll.off, coll.invalid)
+    rng = np.random.default_rng(split or 0)
+    queries = [int(q) for q in rng.choice(coll.n, size=6, replace=False)]
+    subset = np.sort(rng.choice(coll.n, size=3001, replace=False)).astype(np.int64)
+    in_subset = set(int(r) for r in subset)
+    for ceiling in (250, 2 ** 31 - 1):
+        for q in queries:
+            want = c_oracle.one_vs_all(coll.pos, coll.off, coll.invalid, q, ceiling, nthreads=4)
+            assert hits_to_dict(eng.one_vs_all(q, ceiling)) == want, (split, ceiling, q)
+            got = hits_to_dict(eng.one_vs_all(q, ceiling, rows=subset))
+            assert got == {r: v for r, v in want.items() if r in in_subset}, (split, ceiling, q, "list")
+    eng.close()
+
+
 def test_incremental_insert_then_query_matches_bulk(monkeypatch):
     """config 1 flow: persist one by one with a query after each insert; small store chunks force the arena
     and the header table to roll over."""

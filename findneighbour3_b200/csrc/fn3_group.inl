@@ -60,6 +60,13 @@ static int gfrom(fn3_group* g, int d, int rc) {
     return rc;
 }
 
+// a job on device d; a C++ exception (the per-device buffers are std::vectors) becomes an error code, not std::terminate
+static int group_call(fn3_group* g, const std::function<int(int)>& f, int d) {
+    try { return f(d); }
+    catch (const std::bad_alloc&) { return set_err(g->eng[(size_t)d], FN3_ENOMEM, "out of host memory"); }
+    catch (const std::exception& ex) { return set_err(g->eng[(size_t)d], FN3_ECUDA, "unexpected exception: %s", ex.what()); }
+}
+
 static void group_worker(fn3_group* g, int d) {
     cudaSetDevice(g->dev[(size_t)d]);
     uint64_t seen = 0;
@@ -80,7 +87,7 @@ static void group_worker(fn3_group* g, int d) {
             spins = 0;
         }
         seen = s;
-        g->w[(size_t)d].rc = (*g->job)(d);
+        g->w[(size_t)d].rc = group_call(g, *g->job, d);
         g->w[(size_t)d].done.store(s, std::memory_order_release);
     }
 }
@@ -94,7 +101,7 @@ static int group_run(fn3_group* g, const std::function<int(int)>& f) {
         g->job_seq.store(seq);
         if (g->sleepers.load() > 0) { std::lock_guard<std::mutex> lk(g->cv_mu); g->cv.notify_all(); }
     }
-    g->w[0].rc = f(0);
+    g->w[0].rc = group_call(g, f, 0);
     for (int d = 1; d < g->G; ++d)
         while (g->w[(size_t)d].done.load(std::memory_order_acquire) != seq) FN3_CPU_RELAX();
     for (int d = 0; d < g->G; ++d)

@@ -962,7 +962,8 @@ struct QueryJob {                    // what enqueue_query needs beyond the engi
 // of drawing one and fetching its headers, about half a row) is estimated and the cheapest split taken.  Sub-units that hold
 // no row — the unused lanes of the last, partly filled superblock — are not counted.  Measured on the 50 000-row bench store
 // (one-vs-all at ceiling 250 / none, scripts/variant_prof.py with FN3_SCAN_SS): ss 0: 45.0 / 84.8 us, 1: 34.9 / 51.3,
-// 2: 35.8 / 52.1, 3: 36.8 / 53.3, 4: 36.9 / 53.8, 5: 39.8 / 57.3 — this rule picks 1 there and 3 from ~100 000 rows on.
+// 2: 35.8 / 52.1, 3: 36.8 / 53.3, 4: 36.9 / 53.8, 5: 39.8 / 57.3 — this rule picks 1 there, 3 for the 125 000 rows per GPU of
+// configs[4] (measured: 0.57 of the HBM peak at ceiling 250) and whole tiles again once every warp gets several of them.
 static int pick_scan_split(long long n_rows, int sb_shift, bool list, long long n_list, long long warps) {
     int best = 0;
     double best_cost = 1e300;
@@ -981,6 +982,11 @@ static int pick_scan_split(long long n_rows, int sb_shift, bool list, long long 
         if (cost < best_cost - 1e-9) { best_cost = cost; best = ss; }
     }
     return best;
+}
+
+// host-only view of the rule above for tests/test_cabi_symbols.py (no device is touched)
+extern "C" int fn3_debug_scan_split(int64_t n_rows, int32_t sb_shift, int64_t n_list, int64_t warps) {
+    return pick_scan_split(n_rows, sb_shift, n_list >= 0, n_list < 0 ? 0 : n_list, warps);
 }
 
 static int enqueue_query(fn3_engine* e, QueryJob& job) {

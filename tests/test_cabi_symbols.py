@@ -75,3 +75,28 @@ def test_dropin_directory_shadows_the_reference_module_names():
     assert out.returncode == 0, out.stderr
     assert out.stdout.split() == ["findneighbour3_b200.seqComparer", "findneighbour3_b200.seqComparer_mt",
                                   "findneighbour3_b200.NucleicAcid"]
+
+
+def test_scan_split_rule_is_host_logic_with_the_measured_choices():
+    """k_scan's split of the 32-row head tiles (fn3_engine.cu pick_scan_split; no device involved): the choices the A/B
+    runs of profiles/README.md found best, and the invariants of the rule."""
+    from findneighbour3_b200 import _native
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    f = lib.fn3_debug_scan_split
+    f.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64]
+    f.restype = ctypes.c_int
+    warps = 148 * 24                                            # one CTA of 24 warps per SM of a B200
+    assert f(50040, 13, -1, warps) == 1                         # the bench store: ONE 16-row sub-unit per warp
+    assert f(125016, 13, -1, warps) == 3                        # configs[4]'s share of a GPU: eight 4-row sub-units per tile
+    assert f(1000000, 13, -1, warps) == 0                       # nine whole tiles per warp: nothing to gain from drawing more often
+    for n_rows in (1, 31, 255, 256, 4097, 8192, 8193, 20000, 60000, 300000):
+        for w in (24, warps // 128, warps):
+            ss = f(n_rows, 13, -1, w)
+            assert 0 <= ss <= 3
+            # never whole tiles while that leaves warps of the launch without a row
+            full, rem = divmod(n_rows, 8192)
+            tiles_used = full * 256 + min(256, rem)
+            if tiles_used < w and n_rows >= 2 * w:
+                assert ss > 0, (n_rows, w)
+    assert f(0, 13, 3001, warps) in (0, 1, 2, 3)                # an explicit candidate list
+    assert f(0, 13, 32 * warps * 40, warps) == 0                # forty whole tiles per warp

@@ -512,7 +512,7 @@ def main():
     moved = float(touched["bytes_touched"].mean())
     traffic = ncu_traffic() or {}
     roofline = {
-        "bound": "latency", "kernel": "k_query (FILTER variant)", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+        "bound": "hbm", "regime": "latency", "kernel": "k_query (FILTER variant)", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
         "achieved": moved / (cmp_ms * 1e-3) / 1e9, "frac": moved / (cmp_ms * 1e-3) / 1e9 / peak,
         "traffic": moved, "traffic_source": "instrumented pass of the same launches in this run (heads + row words loaded)",
         "traffic_ncu": traffic.get("k_query_bytes_per_launch"), "traffic_ncu_source": traffic.get("source"),
